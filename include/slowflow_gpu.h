@@ -1,0 +1,208 @@
+/*
+ * slowflow_gpu.h -- C ABI of libslowflow_gpu.so: the B200 (sm_100a) implementation of Slow Flow's
+ * variational energy-minimisation hot path.
+ *
+ * The library is a drop-in for ONE path of JJanai/slowflow and nothing else.  Every entry point
+ * cites the reference interface it replaces (paths relative to the reference root).  All
+ * signatures are plain C: pointers, sizes, PODs -- no CUDA, torch or C++ types.
+ *
+ *   1. Legacy drop-in:  variational() / variational_params_default() with the reference's exact
+ *      signatures (epic_flow_extended/variational.h:27,30), callers adaptiveFR.cpp:574 and
+ *      epicflow.cpp:127.  Host buffers in, host buffers out, abort-on-error like the reference.
+ *   2. Handle API (sfgpu_*): re-entrant, one context per host thread / device / stream, int status
+ *      codes + sfgpu_last_error().  Adds the multi-frame entry (Variational_MT::variational,
+ *      epic_flow_extended/variational_mt.h:37, callers slow_flow.cpp:888,1023), device-resident
+ *      and pipelined-sequence variants for the sharded driver, and operator-level twins of
+ *      variational_aux.h:12-29 / solver.h:11 for parity tests.
+ *
+ * There is NO CPU fallback: every compute entry fails (status != 0, or abort for the legacy entry)
+ * when no CUDA device is usable.
+ */
+#ifndef SLOWFLOW_GPU_H_
+#define SLOWFLOW_GPU_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- containers: identical layout to epic_flow_extended/image.h:17-34.  If the reference's
+ * image.h was included first its definitions are used (same names, same fields). ---- */
+#ifndef __IMAGE_H_
+typedef struct image_s {
+    int width;   /* valid columns */
+    int height;  /* rows */
+    int stride;  /* floats per row = ceil4(width) (image.c:25) */
+    float *data; /* 16-byte aligned, row-major */
+} image_t;
+
+typedef struct color_image_s {
+    int width, height, stride;
+    float *c1, *c2, *c3; /* planar; c2 = c1 + stride*height, c3 = c2 + stride*height (image.c:80-87) */
+} color_image_t;
+#endif
+
+/* ---- two-frame parameters: identical to epic_flow_extended/variational.h:15-24 ---- */
+#ifndef __VARIATIONAL_H_
+typedef struct variational_params_s {
+    float alpha;      /* smoothness weight */
+    float gamma;      /* gradient constancy weight */
+    float delta;      /* colour constancy weight */
+    float sigma;      /* presmoothing (unused: disabled in the reference, variational.c:124-136) */
+    int niter_outer;  /* warping fixed-point iterations */
+    int niter_inner;  /* lagged-nonlinearity iterations */
+    int niter_solver; /* SOR sweeps */
+    float sor_omega;  /* SOR relaxation */
+} variational_params_t;
+
+/* replaces variational.c:85-98 */
+void variational_params_default(variational_params_t *params);
+/* replaces variational.c:101-143.  wx, wy: in/out flow planes (host); im1, im2: host colour images.
+ * params == NULL -> defaults.  Uses a thread-local default context on the current CUDA device.
+ * Errors print to stderr and exit(1) (the reference's convention, image.c:19-30). */
+void variational(image_t *wx, image_t *wy, const color_image_t *im1, const color_image_t *im2,
+                 variational_params_t *params);
+#endif
+
+/* ---- multi-frame parameters: POD of the ParameterList keys Variational_MT reads
+ * (variational_mt.cpp:173-192, 250-251, 533-568; key names in comments) ---- */
+#define SF_MT_MAX_REF 8
+enum { SF_ROBUST_QUADRATIC = 0, SF_ROBUST_MODL1 = 1, SF_ROBUST_LORENTZIAN = 2, SF_ROBUST_TRUNC_MODL1 = 3,
+       SF_ROBUST_GEMAN_MCCLURE = 4 }; /* select_robust_function, variational_aux_mt.cpp:906-925 */
+
+typedef struct sf_mt_params_s {
+    int S;                       /* slow_flow_S: ref = S-1, F = 2*ref+1 frames */
+    int layers;                  /* slow_flow_layers */
+    float p_scale;               /* slow_flow_p_scale */
+    float alpha, gamma, delta;   /* slow_flow_alpha / gamma / delta */
+    int dataterm;                /* slow_flow_dataterm (1 = normalised data term) */
+    int smoothing;               /* slow_flow_smoothing (0 or 1) */
+    int one_direction;           /* slow_flow_method == "forward" (or Variational_MT::one_direction) */
+    float rho[SF_MT_MAX_REF];    /* slow_flow_rho_a */
+    float omega[SF_MT_MAX_REF];  /* slow_flow_omega_a */
+    int robust_color;  float robust_color_eps, robust_color_truncation;
+    int robust_grad;   float robust_grad_eps, robust_grad_truncation;  /* robust_grad < 0: reuse colour settings (Q8) */
+    int robust_reg;    float robust_reg_eps, robust_reg_truncation;
+    int niter_alter, niter_outer, niter_inner, niter_solver, niter_graphc;
+    float thres_outer, thres_inner, sor_omega;
+    int occlusion_reasoning;     /* slow_flow_occlusion_reasoning */
+    float occlusion_penalty, occlusion_alpha;
+    int graphcut_int_terms;      /* 1: emulate gco's integer EnergyTermType (costs truncate to 0) */
+    int hbit;                    /* 16bit */
+    float img_norm_avg[3], img_norm_std[3]; /* slow_flow_img_norm_{avg,std}_{1,2,3} (written by normalize) */
+} sf_mt_params_t;
+
+/* defaults of slow_flow.cpp:64-128 (setDefault) */
+void sf_mt_params_default(sf_mt_params_t *params);
+
+/* ---- handle API ---- */
+typedef struct sfgpu_ctx sfgpu_ctx;
+
+enum { SFGPU_OK = 0, SFGPU_ERR_CUDA = 1, SFGPU_ERR_ARG = 2, SFGPU_ERR_NOMEM = 3, SFGPU_ERR_UNSUPPORTED = 4 };
+
+/* Create a context on `device`.  `stream` is a cudaStream_t passed as void* (NULL: the context
+ * creates its own non-blocking stream).  One context must only be used by one host thread at a time. */
+int sfgpu_create(int device, void *stream, sfgpu_ctx **out);
+void sfgpu_destroy(sfgpu_ctx *ctx);
+/* last error message of the calling thread ("" if none) */
+const char *sfgpu_last_error(void);
+/* number of usable CUDA devices (0 if none / driver missing) */
+int sfgpu_device_count(void);
+/* block until all work queued on the context's stream is done */
+int sfgpu_synchronize(sfgpu_ctx *ctx);
+
+/* solver selection: 0 = temporally blocked red-black SOR (default), 1 = one launch per half sweep
+ * (validation / tiny images).  Both are red-black and produce identical iterates. */
+int sfgpu_set_sor_variant(sfgpu_ctx *ctx, int variant);
+/* sweeps fused per HBM round trip of the blocked solver (1..8; default chosen per image size) */
+int sfgpu_set_sor_fuse(sfgpu_ctx *ctx, int sweeps_per_launch);
+
+/* two-frame refinement, host buffers (replaces variational.c:101; synchronous) */
+int sfgpu_variational(sfgpu_ctx *ctx, image_t *wx, image_t *wy, const color_image_t *im1,
+                      const color_image_t *im2, const variational_params_t *params);
+
+/* two-frame refinement on device-resident planes (asynchronous on the context's stream).
+ * d_wx, d_wy: stride*height floats, in/out.  d_im1, d_im2: 3*stride*height floats, planar. */
+int sfgpu_variational_dev(sfgpu_ctx *ctx, float *d_wx, float *d_wy, const float *d_im1, const float *d_im2,
+                          int width, int height, int stride, const variational_params_t *params);
+
+/* Pipelined sequence refinement (config 5; the shard loop of slow_flow.cpp:706 / adaptiveFR.cpp:496):
+ * n_pairs consecutive frame pairs (pair j = frames[j], frames[j+1]); wx[j], wy[j] in/out.
+ * Host buffers; uploads of pair j+1 and downloads of pair j-1 overlap the solve of pair j, and a
+ * frame shared by two pairs is uploaded once.  Pinned host memory is used as given if the buffers
+ * were registered with sfgpu_host_register, otherwise staged. */
+int sfgpu_variational_sequence(sfgpu_ctx *ctx, int n_pairs, const color_image_t *const *frames,
+                               image_t *const *wx, image_t *const *wy, const variational_params_t *params);
+
+/* page-lock / unlock a host range so transfers are asynchronous (cudaHostRegister) */
+int sfgpu_host_register(void *ptr, unsigned long long bytes);
+int sfgpu_host_unregister(void *ptr);
+
+/* multi-frame refinement (replaces Variational_MT::variational, variational_mt.cpp:526-784).
+ * im: F = 2*(S-1)+1 host colour images, reference frame at index S-1.  channel_w may be NULL (all
+ * ones, variational_mt.cpp:535-538).  occlusions_out may be NULL; otherwise receives the -1/0/+1
+ * labels of the finest level (Variational_MT::getOcclusions).  avg_change_out: the returned Point2f. */
+int sfgpu_variational_mt(sfgpu_ctx *ctx, image_t *wx, image_t *wy, const color_image_t *const *im,
+                         const sf_mt_params_t *params, const color_image_t *channel_w,
+                         image_t *occlusions_out, float avg_change_out[2]);
+
+/* normalize() of variational_mt.cpp:17-85: in place on F host frames; fills params->img_norm_* */
+int sfgpu_normalize(sfgpu_ctx *ctx, color_image_t *const *seq, int F, sf_mt_params_t *params);
+
+/* iteration statistics of the last sfgpu_variational_mt call on this context */
+typedef struct sfgpu_mt_stats_s {
+    int levels;            /* pyramid levels actually run */
+    int outer_iterations;  /* total outer iterations executed over all levels / alternations */
+    int sor_calls;         /* sor_coupled invocations */
+    int graphcut_calls;    /* optimizeOcc invocations */
+} sfgpu_mt_stats_t;
+int sfgpu_get_mt_stats(sfgpu_ctx *ctx, sfgpu_mt_stats_t *out);
+
+/* ---- per-kernel timing (CUDA events on the context's stream) for bench.py's roofline ---- */
+typedef struct sfgpu_profile_s {
+    double sor_ms;        /* sum of device time of all SOR launches since reset */
+    long long sor_launches;
+    long long sor_calls;   /* sor_coupled invocations */
+    long long sor_pixel_sweeps; /* sum over calls of width*height*niter_solver */
+    double data_ms;       /* fused derivative + data-term kernel */
+    long long data_launches;
+    long long data_pixels;
+    long long kernel_launches; /* every kernel launched by this context since reset */
+} sfgpu_profile_t;
+int sfgpu_profile_enable(sfgpu_ctx *ctx, int on);   /* on=1 brackets SOR / data-term launches with events */
+int sfgpu_profile_reset(sfgpu_ctx *ctx);
+int sfgpu_profile_get(sfgpu_ctx *ctx, sfgpu_profile_t *out); /* synchronises the stream */
+
+/* ---- operator-level twins (host buffers; test path).  Same argument meaning as the reference. ---- */
+/* variational_aux.c:18 / variational_aux_mt.cpp:722 (factor) ; mask may be NULL */
+int sfgpu_image_warp(sfgpu_ctx *ctx, color_image_t *dst, image_t *mask, const color_image_t *src,
+                     const image_t *wx, const image_t *wy, int factor);
+/* variational_aux.c:183 (coef = 5, deriv = 5-tap); result written into dst.
+ * MT variant (variational_aux_mt.cpp:673): avg/std/hbit de-normalisation; pass NULL for two-frame. */
+int sfgpu_compute_dpsis_weight(sfgpu_ctx *ctx, image_t *dst, const color_image_t *im, float coef,
+                               const float *avg3, const float *std3, int hbit);
+/* variational_aux.c:84 (robust_reg < 0) or variational_aux_mt.cpp:18 modes 0/1 with a penalty */
+int sfgpu_compute_smoothness(sfgpu_ctx *ctx, image_t *dst_horiz, image_t *dst_vert, const image_t *uu,
+                             const image_t *vv, const image_t *dpsis_weight, float alpha_factor,
+                             int robust_reg, float reg_eps, float reg_trunc, int mode);
+/* get_derivatives + compute_data_and_match (variational_aux.c:55,215) in one fused pass:
+ * im2w is the already warped second image. */
+int sfgpu_compute_data_and_match(sfgpu_ctx *ctx, image_t *a11, image_t *a12, image_t *a22, image_t *b1,
+                                 image_t *b2, const image_t *mask, const image_t *du, const image_t *dv,
+                                 const color_image_t *im1, const color_image_t *im2w,
+                                 float half_delta_over3, float half_gamma_over3);
+/* variational_aux.c:153 */
+int sfgpu_sub_laplacian(sfgpu_ctx *ctx, image_t *dst, const image_t *src, const image_t *weight_horiz,
+                        const image_t *weight_vert);
+/* solver.c:63 with red-black ordering.  Like the reference, a11/a12/a22 are overwritten with the
+ * inverted blocks. */
+int sfgpu_sor_coupled(sfgpu_ctx *ctx, image_t *du, image_t *dv, image_t *a11, image_t *a12, image_t *a22,
+                      const image_t *b1, const image_t *b2, const image_t *dpsis_horiz,
+                      const image_t *dpsis_vert, int iterations, float omega);
+
+/* library / build identification, e.g. "slowflow_gpu 0.1 sm_100a" */
+const char *sfgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLOWFLOW_GPU_H_ */

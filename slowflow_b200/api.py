@@ -1,0 +1,258 @@
+"""Host-side mirror of the reference entry points over the C ABI (include/slowflow_gpu.h).
+
+``variational(wx, wy, im1, im2, params)``   -> epic_flow_extended/variational.c:101
+``Variational_MT().variational(wx, wy, im, params)`` -> epic_flow_extended/variational_mt.cpp:526
+``Context`` wraps an ``sfgpu_ctx`` handle (one per host thread / device / stream).
+
+All compute goes through ``libslowflow_gpu.so``; a missing library or GPU raises ``RuntimeError``.
+"""
+import ctypes as C
+import os
+
+from .image import Image, ColorImage, image_t, color_image_t
+from .params import VariationalParams, MTParams, mt_params_default
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def library_path():
+    return os.path.join(_HERE, "lib", "libslowflow_gpu.so")
+
+
+class Profile(C.Structure):
+    _fields_ = [("sor_ms", C.c_double), ("sor_launches", C.c_longlong), ("sor_calls", C.c_longlong),
+                ("sor_pixel_sweeps", C.c_longlong), ("data_ms", C.c_double), ("data_launches", C.c_longlong),
+                ("data_pixels", C.c_longlong), ("kernel_launches", C.c_longlong)]
+
+
+class MTStats(C.Structure):
+    _fields_ = [("levels", C.c_int), ("outer_iterations", C.c_int), ("sor_calls", C.c_int),
+                ("graphcut_calls", C.c_int)]
+
+
+# every symbol include/slowflow_gpu.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "variational_params_default", "variational", "sf_mt_params_default", "sfgpu_create", "sfgpu_destroy",
+    "sfgpu_last_error", "sfgpu_device_count", "sfgpu_synchronize", "sfgpu_set_sor_variant", "sfgpu_set_sor_fuse",
+    "sfgpu_variational", "sfgpu_variational_dev", "sfgpu_variational_sequence", "sfgpu_host_register",
+    "sfgpu_host_unregister", "sfgpu_variational_mt", "sfgpu_normalize", "sfgpu_get_mt_stats", "sfgpu_profile_enable",
+    "sfgpu_profile_reset", "sfgpu_profile_get", "sfgpu_image_warp", "sfgpu_compute_dpsis_weight",
+    "sfgpu_compute_smoothness", "sfgpu_compute_data_and_match", "sfgpu_sub_laplacian", "sfgpu_sor_coupled",
+    "sfgpu_version",
+]
+
+
+def load_library(path=None):
+    """dlopen the CUDA library (RTLD_LOCAL: it exports ``variational`` like the reference does)."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or library_path()
+    if not os.path.exists(p):
+        raise RuntimeError(
+            "libslowflow_gpu.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback." % p)
+    lib = C.CDLL(p, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+    IP, CP, VP = C.POINTER(image_t), C.POINTER(color_image_t), C.POINTER(VariationalParams)
+    FP = C.POINTER(C.c_float)
+    lib.sfgpu_last_error.restype = C.c_char_p
+    lib.sfgpu_version.restype = C.c_char_p
+    lib.sfgpu_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.sfgpu_destroy.argtypes = [C.c_void_p]
+    lib.sfgpu_destroy.restype = None
+    lib.sfgpu_synchronize.argtypes = [C.c_void_p]
+    lib.sfgpu_set_sor_variant.argtypes = [C.c_void_p, C.c_int]
+    lib.sfgpu_set_sor_fuse.argtypes = [C.c_void_p, C.c_int]
+    lib.variational_params_default.argtypes = [VP]
+    lib.variational_params_default.restype = None
+    lib.variational.argtypes = [IP, IP, CP, CP, VP]
+    lib.variational.restype = None
+    lib.sf_mt_params_default.argtypes = [C.POINTER(MTParams)]
+    lib.sf_mt_params_default.restype = None
+    lib.sfgpu_variational.argtypes = [C.c_void_p, IP, IP, CP, CP, VP]
+    lib.sfgpu_variational_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_int, C.c_int, VP]
+    lib.sfgpu_variational_sequence.argtypes = [C.c_void_p, C.c_int, C.POINTER(CP), C.POINTER(IP), C.POINTER(IP), VP]
+    lib.sfgpu_host_register.argtypes = [C.c_void_p, C.c_ulonglong]
+    lib.sfgpu_host_unregister.argtypes = [C.c_void_p]
+    lib.sfgpu_variational_mt.argtypes = [C.c_void_p, IP, IP, C.POINTER(CP), C.POINTER(MTParams), CP, IP, FP]
+    lib.sfgpu_normalize.argtypes = [C.c_void_p, C.POINTER(CP), C.c_int, C.POINTER(MTParams)]
+    lib.sfgpu_get_mt_stats.argtypes = [C.c_void_p, C.POINTER(MTStats)]
+    lib.sfgpu_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    lib.sfgpu_profile_reset.argtypes = [C.c_void_p]
+    lib.sfgpu_profile_get.argtypes = [C.c_void_p, C.POINTER(Profile)]
+    lib.sfgpu_image_warp.argtypes = [C.c_void_p, CP, IP, CP, IP, IP, C.c_int]
+    lib.sfgpu_compute_dpsis_weight.argtypes = [C.c_void_p, IP, CP, C.c_float, FP, FP, C.c_int]
+    lib.sfgpu_compute_smoothness.argtypes = [C.c_void_p, IP, IP, IP, IP, IP, C.c_float, C.c_int, C.c_float,
+                                             C.c_float, C.c_int]
+    lib.sfgpu_compute_data_and_match.argtypes = [C.c_void_p, IP, IP, IP, IP, IP, IP, IP, IP, CP, CP, C.c_float,
+                                                 C.c_float]
+    lib.sfgpu_sub_laplacian.argtypes = [C.c_void_p, IP, IP, IP, IP]
+    lib.sfgpu_sor_coupled.argtypes = [C.c_void_p, IP, IP, IP, IP, IP, IP, IP, IP, IP, C.c_int, C.c_float]
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def _check(lib, rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (status %d): %s" % (what, rc, lib.sfgpu_last_error().decode()))
+
+
+def _ip(im):
+    return None if im is None else im.ptr()
+
+
+class Context:
+    """An ``sfgpu_ctx``: device + stream + workspace.  Not shareable between host threads."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib, self.lib.sfgpu_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)),
+               "sfgpu_create")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sfgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # --- configuration / timing
+    def synchronize(self):
+        _check(self.lib, self.lib.sfgpu_synchronize(self.h), "sfgpu_synchronize")
+
+    def set_sor_variant(self, v):
+        _check(self.lib, self.lib.sfgpu_set_sor_variant(self.h, int(v)), "sfgpu_set_sor_variant")
+
+    def set_sor_fuse(self, n):
+        _check(self.lib, self.lib.sfgpu_set_sor_fuse(self.h, int(n)), "sfgpu_set_sor_fuse")
+
+    def profile_enable(self, on=True):
+        _check(self.lib, self.lib.sfgpu_profile_enable(self.h, 1 if on else 0), "sfgpu_profile_enable")
+
+    def profile_reset(self):
+        _check(self.lib, self.lib.sfgpu_profile_reset(self.h), "sfgpu_profile_reset")
+
+    def profile_get(self):
+        p = Profile()
+        _check(self.lib, self.lib.sfgpu_profile_get(self.h, C.byref(p)), "sfgpu_profile_get")
+        return p
+
+    # --- two-frame
+    def variational(self, wx, wy, im1, im2, params=None):
+        _check(self.lib, self.lib.sfgpu_variational(self.h, wx.ptr(), wy.ptr(), im1.ptr(), im2.ptr(),
+                                                    C.byref(params) if params is not None else None),
+               "sfgpu_variational")
+
+    def variational_dev(self, d_wx, d_wy, d_im1, d_im2, width, height, stride, params=None):
+        """Device pointers (ints); asynchronous on the context's stream."""
+        _check(self.lib, self.lib.sfgpu_variational_dev(self.h, d_wx, d_wy, d_im1, d_im2, width, height, stride,
+                                                        C.byref(params) if params is not None else None),
+               "sfgpu_variational_dev")
+
+    def variational_sequence(self, frames, wxs, wys, params=None):
+        n = len(wxs)
+        assert len(frames) == n + 1 and len(wys) == n
+        CP, IP = C.POINTER(color_image_t), C.POINTER(image_t)
+        fa = (CP * (n + 1))(*[C.pointer(f.c) for f in frames])
+        xa = (IP * n)(*[C.pointer(w.c) for w in wxs])
+        ya = (IP * n)(*[C.pointer(w.c) for w in wys])
+        _check(self.lib, self.lib.sfgpu_variational_sequence(self.h, n, fa, xa, ya,
+                                                             C.byref(params) if params is not None else None),
+               "sfgpu_variational_sequence")
+
+    # --- multi-frame
+    def normalize(self, seq, params):
+        CP = C.POINTER(color_image_t)
+        arr = (CP * len(seq))(*[C.pointer(f.c) for f in seq])
+        _check(self.lib, self.lib.sfgpu_normalize(self.h, arr, len(seq), C.byref(params)), "sfgpu_normalize")
+
+    def variational_mt(self, wx, wy, im, params, channel_w=None, occlusions=None):
+        CP = C.POINTER(color_image_t)
+        arr = (CP * len(im))(*[C.pointer(f.c) for f in im])
+        out = (C.c_float * 2)()
+        _check(self.lib, self.lib.sfgpu_variational_mt(self.h, wx.ptr(), wy.ptr(), arr, C.byref(params),
+                                                       _ip(channel_w), _ip(occlusions), out),
+               "sfgpu_variational_mt")
+        return float(out[0]), float(out[1])
+
+    def mt_stats(self):
+        s = MTStats()
+        _check(self.lib, self.lib.sfgpu_get_mt_stats(self.h, C.byref(s)), "sfgpu_get_mt_stats")
+        return s
+
+    # --- operator twins (variational_aux.h:12-29, solver.h:11)
+    def image_warp(self, dst, mask, src, wx, wy, factor=1):
+        _check(self.lib, self.lib.sfgpu_image_warp(self.h, dst.ptr(), _ip(mask), src.ptr(), wx.ptr(), wy.ptr(),
+                                                   int(factor)), "sfgpu_image_warp")
+
+    def compute_dpsis_weight(self, dst, im, coef=5.0, avg=None, std=None, hbit=0):
+        a = (C.c_float * 3)(*avg) if avg is not None else None
+        s = (C.c_float * 3)(*std) if std is not None else None
+        _check(self.lib, self.lib.sfgpu_compute_dpsis_weight(self.h, dst.ptr(), im.ptr(), coef, a, s, int(hbit)),
+               "sfgpu_compute_dpsis_weight")
+
+    def compute_smoothness(self, dst_h, dst_v, uu, vv, w, alpha_factor, robust_reg=-1, eps=0.001, trunc=0.5, mode=1):
+        _check(self.lib, self.lib.sfgpu_compute_smoothness(self.h, dst_h.ptr(), dst_v.ptr(), uu.ptr(), vv.ptr(),
+                                                           w.ptr(), alpha_factor, int(robust_reg), eps, trunc,
+                                                           int(mode)), "sfgpu_compute_smoothness")
+
+    def compute_data_and_match(self, a11, a12, a22, b1, b2, mask, du, dv, im1, im2w, hd, hg):
+        _check(self.lib, self.lib.sfgpu_compute_data_and_match(self.h, a11.ptr(), a12.ptr(), a22.ptr(), b1.ptr(),
+                                                               b2.ptr(), mask.ptr(), du.ptr(), dv.ptr(), im1.ptr(),
+                                                               im2w.ptr(), hd, hg), "sfgpu_compute_data_and_match")
+
+    def sub_laplacian(self, dst, src, wh, wv):
+        _check(self.lib, self.lib.sfgpu_sub_laplacian(self.h, dst.ptr(), src.ptr(), wh.ptr(), wv.ptr()),
+               "sfgpu_sub_laplacian")
+
+    def sor_coupled(self, du, dv, a11, a12, a22, b1, b2, ph, pv, iterations, omega):
+        _check(self.lib, self.lib.sfgpu_sor_coupled(self.h, du.ptr(), dv.ptr(), a11.ptr(), a12.ptr(), a22.ptr(),
+                                                    b1.ptr(), b2.ptr(), ph.ptr(), pv.ptr(), int(iterations), omega),
+               "sfgpu_sor_coupled")
+
+
+def variational(wx, wy, im1, im2, params=None):
+    """Legacy drop-in entry (variational.c:101): refines wx, wy in place; aborts the process on error
+    exactly like the reference (fprintf + exit(1))."""
+    lib = load_library()
+    lib.variational(wx.ptr(), wy.ptr(), im1.ptr(), im2.ptr(), C.byref(params) if params is not None else None)
+
+
+class Variational_MT:
+    """Shape of the reference class (variational_mt.h:23-71) over ``sfgpu_variational_mt``."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or Context()
+        self.one_direction = False
+        self._channel_w = None
+        self._occlusions = None
+
+    def setChannelWeights(self, weights):
+        self._channel_w = weights
+
+    def getOcclusions(self):
+        return self._occlusions
+
+    def variational(self, wx, wy, im, params):
+        p = params
+        if self.one_direction and not p.one_direction:
+            p = MTParams.from_buffer_copy(bytes(params))
+            p.one_direction = 1
+        self._occlusions = Image(wx.width, wx.height)
+        return self.ctx.variational_mt(wx, wy, im, p, self._channel_w, self._occlusions)

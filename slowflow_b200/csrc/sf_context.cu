@@ -1,0 +1,629 @@
+// sf_context.cu -- context management, the two-frame driver and the C ABI of include/slowflow_gpu.h
+// (two-frame, sequence, operator twins, profiling).  The multi-frame driver lives in sf_mt.cu.
+#include "sf_context.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+namespace sf {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+bool cuda_ok(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+
+Penalty make_penalty(int type, float eps, float trunc) {
+    Penalty p;
+    p.type = type;
+    const float e2 = eps * eps; // the reference squares in float, then widens (modified_l1_norm.h:15)
+    p.eps_sq_f = e2;
+    p.eps_sq_d = (double)e2;
+    p.trunc = trunc;
+    return p;
+}
+
+} // namespace sf
+
+using namespace sf;
+
+// ------------------------------------------------------------------------------------------ context
+enum { PROF_SOR = 0, PROF_DATA = 1 };
+
+int sfgpu_ctx::ensure_workspace(Geom geom) {
+    if (geom.W < 5 || geom.H < 5) {
+        set_error("image must be at least 5x5 (5-tap derivative filter, image.c:425)");
+        return SFGPU_ERR_ARG;
+    }
+    const size_t P = geom.plane();
+    const size_t need = (size_t)(SP_COUNT + 3 + 1 + 2 + 1) * P;
+    if (need > ws_floats) {
+        if (ws) cudaFree(ws);
+        ws = nullptr;
+        ws_floats = 0;
+        SF_CUDA(cudaMalloc(&ws, need * sizeof(float)));
+        ws_floats = need;
+        g = Geom{0, 0, 0};
+    }
+    if (geom.W != g.W || geom.H != g.H || geom.S != g.S) {
+        g = geom;
+        float *p = ws;
+        float *arena = p; p += (size_t)SP_COUNT * P;
+        wim = p;   p += 3 * P;
+        mask = p;  p += P;
+        uu = p;    p += P;
+        vv = p;    p += P;
+        dpsis = p; p += P;
+        if (!sor_plan_init(sor, g, arena, num_sms)) {
+            // no TMA descriptor: only the per-half-sweep variant can run; report it loudly
+            return SFGPU_ERR_CUDA;
+        }
+    }
+    return SFGPU_OK;
+}
+
+int sfgpu_ctx::ensure_io(size_t floats) {
+    if (floats <= io_floats) return SFGPU_OK;
+    if (io) cudaFree(io);
+    io = nullptr;
+    io_floats = 0;
+    SF_CUDA(cudaMalloc(&io, floats * sizeof(float)));
+    io_floats = floats;
+    return SFGPU_OK;
+}
+
+cudaEvent_t sfgpu_ctx::get_event() {
+    if (!ev_free.empty()) {
+        cudaEvent_t e = ev_free.back();
+        ev_free.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void sfgpu_ctx::prof_begin(int kind, cudaEvent_t &a) {
+    a = nullptr;
+    if (!prof) return;
+    a = get_event();
+    cudaEventRecord(a, stream);
+}
+void sfgpu_ctx::prof_end(int kind, cudaEvent_t a) {
+    if (!prof || !a) return;
+    cudaEvent_t b = get_event();
+    cudaEventRecord(b, stream);
+    ev_pending.push_back(EvPair{a, b, kind});
+}
+int sfgpu_ctx::prof_collect() {
+    SF_CUDA(cudaStreamSynchronize(stream));
+    for (auto &p : ev_pending) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            if (p.kind == PROF_SOR) prof_acc.sor_ms += ms;
+            else prof_acc.data_ms += ms;
+        }
+        ev_free.push_back(p.a);
+        ev_free.push_back(p.b);
+    }
+    ev_pending.clear();
+    return SFGPU_OK;
+}
+
+static int auto_fuse(const sfgpu_ctx *c) { return c->sor_fuse > 0 ? c->sor_fuse : 5; }
+
+// ------------------------------------------------------------------------------------------ two-frame driver
+namespace sf {
+
+// shared by the two-frame and multi-frame drivers: one sor_coupled call on the context's arena
+int run_sor(sfgpu_ctx *c, int iterations, float omega, int *cur, bool zero_init) {
+    cudaEvent_t ev;
+    c->prof_begin(PROF_SOR, ev);
+    const int n = launch_sor(c->stream, c->sor, iterations, omega, c->sor_variant, auto_fuse(c), cur, zero_init);
+    c->prof_end(PROF_SOR, ev);
+    if (n < 0) return SFGPU_ERR_CUDA;
+    c->prof_acc.sor_launches += n;
+    c->prof_acc.kernel_launches += n;
+    c->prof_acc.sor_calls += 1;
+    c->prof_acc.sor_pixel_sweeps += (long long)c->g.W * c->g.H * iterations;
+    return SFGPU_OK;
+}
+
+int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d_im1, const float *d_im2,
+                  const variational_params_t *params) {
+    variational_params_t defaults;
+    if (!params) {
+        variational_params_default(&defaults);
+        params = &defaults;
+    }
+    int rc = c->ensure_workspace(g);
+    if (rc != SFGPU_OK) return rc;
+    cudaStream_t st = c->stream;
+    const size_t P = g.plane();
+    float *A = c->sor.arena;
+    // variational.c:114-116
+    const float half_alpha = 0.5f * params->alpha;
+    const float half_gamma_over3 = params->gamma * 0.5f / 3.0f;
+    const float half_delta_over3 = params->delta * 0.5f / 3.0f;
+    const float avg0[3] = {0.f, 0.f, 0.f}, std1[3] = {1.f, 1.f, 1.f};
+    Penalty two_frame_reg;
+    two_frame_reg.type = -1; two_frame_reg.eps_sq_f = 0.f; two_frame_reg.eps_sq_d = 0.0; two_frame_reg.trunc = 0.f;
+
+    launch_dpsis_weight(st, g, d_im1, c->dpsis, 5.0f, avg0, std1, 255.0f); // variational.c:34
+    c->prof_acc.kernel_launches++;
+
+    for (int outer = 0; outer < params->niter_outer; outer++) {
+        launch_warp(st, g, d_im2, d_wx, d_wy, 1, c->wim, c->mask); // variational.c:40
+        c->prof_acc.kernel_launches++;
+        int cur = 0;
+        for (int inner = 0; inner < params->niter_inner; inner++) {
+            const bool first = (inner == 0), last = (inner == params->niter_inner - 1);
+            const float *uu = first ? d_wx : c->uu, *vv = first ? d_wy : c->vv;
+            launch_smoothness(st, g, uu, vv, c->dpsis, half_alpha, two_frame_reg, 1, A + SP_PH * P, A + SP_PV * P);
+            const float *du = first ? nullptr : A + (size_t)(cur ? SP_DUB : SP_DUA) * P;
+            const float *dv = first ? nullptr : A + (size_t)(cur ? SP_DVB : SP_DVA) * P;
+            cudaEvent_t ev;
+            c->prof_begin(PROF_DATA, ev);
+            // variational.c:53-55 + the block inverse of solver.c:101-106, one pass
+            launch_data_two_frame(st, g, d_im1, c->wim, c->mask, du, dv, half_delta_over3, half_gamma_over3, true,
+                                  A + SP_PH * P, A + SP_PV * P, d_wx, d_wy, A + SP_A11 * P, A + SP_A12 * P,
+                                  A + SP_A22 * P, A + SP_B1 * P, A + SP_B2 * P);
+            c->prof_end(PROF_DATA, ev);
+            c->prof_acc.data_launches++;
+            c->prof_acc.data_pixels += (long long)g.W * g.H;
+            c->prof_acc.kernel_launches += 2;
+            rc = run_sor(c, params->niter_solver, params->sor_omega, &cur, first); // variational.c:57
+            if (rc != SFGPU_OK) return rc;
+            const float *ndu = A + (size_t)(cur ? SP_DUB : SP_DUA) * P, *ndv = A + (size_t)(cur ? SP_DVB : SP_DVA) * P;
+            if (last) { // variational.c:60-69 collapsed: wx = wx + du
+                launch_add(st, g, d_wx, d_wx, ndu);
+                launch_add(st, g, d_wy, d_wy, ndv);
+            } else {
+                launch_add(st, g, c->uu, d_wx, ndu);
+                launch_add(st, g, c->vv, d_wy, ndv);
+            }
+            c->prof_acc.kernel_launches += 2;
+        }
+    }
+    SF_CUDA(cudaGetLastError());
+    return SFGPU_OK;
+}
+
+} // namespace sf
+
+// ------------------------------------------------------------------------------------------ ABI: basics
+extern "C" {
+
+const char *sfgpu_version(void) { return "slowflow_gpu 0.1 (sm_100a)"; }
+const char *sfgpu_last_error(void) { return g_last_error.c_str(); }
+
+int sfgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int sfgpu_create(int device, void *stream, sfgpu_ctx **out) {
+    if (!out) {
+        set_error("sfgpu_create: out is NULL");
+        return SFGPU_ERR_ARG;
+    }
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("sfgpu_create: no CUDA device available (this library has no CPU fallback)");
+        return SFGPU_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) {
+        set_error("sfgpu_create: device index out of range");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("sfgpu_create: device is not sm_100 class (kernels are built for sm_100a only)");
+        return SFGPU_ERR_UNSUPPORTED;
+    }
+    sfgpu_ctx *c = new sfgpu_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    } else {
+        if (!cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+            delete c;
+            return SFGPU_ERR_CUDA;
+        }
+        c->own_stream = true;
+    }
+    *out = c;
+    return SFGPU_OK;
+}
+
+void sfgpu_destroy(sfgpu_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &p : c->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : c->ev_free) cudaEventDestroy(e);
+    if (c->ws) cudaFree(c->ws);
+    if (c->io) cudaFree(c->io);
+    if (c->h2d) cudaStreamDestroy(c->h2d);
+    if (c->d2h) cudaStreamDestroy(c->d2h);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int sfgpu_synchronize(sfgpu_ctx *c) {
+    if (!c) return SFGPU_ERR_ARG;
+    SF_CUDA(cudaStreamSynchronize(c->stream));
+    return SFGPU_OK;
+}
+
+int sfgpu_set_sor_variant(sfgpu_ctx *c, int variant) {
+    if (!c || variant < 0 || variant > 1) return SFGPU_ERR_ARG;
+    c->sor_variant = variant;
+    return SFGPU_OK;
+}
+int sfgpu_set_sor_fuse(sfgpu_ctx *c, int n) {
+    if (!c || n < 0 || n > 7) return SFGPU_ERR_ARG;
+    c->sor_fuse = n;
+    return SFGPU_OK;
+}
+
+int sfgpu_profile_enable(sfgpu_ctx *c, int on) {
+    if (!c) return SFGPU_ERR_ARG;
+    c->prof = on != 0;
+    return SFGPU_OK;
+}
+int sfgpu_profile_reset(sfgpu_ctx *c) {
+    if (!c) return SFGPU_ERR_ARG;
+    int rc = c->prof_collect();
+    memset(&c->prof_acc, 0, sizeof(c->prof_acc));
+    return rc;
+}
+int sfgpu_profile_get(sfgpu_ctx *c, sfgpu_profile_t *out) {
+    if (!c || !out) return SFGPU_ERR_ARG;
+    int rc = c->prof_collect();
+    *out = c->prof_acc;
+    return rc;
+}
+
+int sfgpu_host_register(void *ptr, unsigned long long bytes) {
+    SF_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return SFGPU_OK;
+}
+int sfgpu_host_unregister(void *ptr) {
+    SF_CUDA(cudaHostUnregister(ptr));
+    return SFGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------ ABI: two-frame
+void variational_params_default(variational_params_t *params) {
+    if (!params) {
+        fprintf(stderr, "Error optical_flow_params_default: argument is null\n");
+        exit(1);
+    }
+    params->alpha = 1.0f;
+    params->gamma = 0.71f;
+    params->delta = 0.0f;
+    params->sigma = 1.00f;
+    params->niter_outer = 5;
+    params->niter_inner = 1;
+    params->niter_solver = 30;
+    params->sor_omega = 1.9f;
+}
+
+static bool check_pair(const image_t *wx, const image_t *wy, const color_image_t *im1, const color_image_t *im2) {
+    if (!wx || !wy || !im1 || !im2 || !wx->data || !wy->data || !im1->c1 || !im2->c1) {
+        set_error("null image argument");
+        return false;
+    }
+    const int w = wx->width, h = wx->height, s = wx->stride;
+    if (s != ((w + 3) / 4) * 4) {
+        set_error("stride must be ceil4(width) (image.c:25)");
+        return false;
+    }
+    if (wy->width != w || wy->height != h || wy->stride != s || im1->width != w || im1->height != h ||
+        im1->stride != s || im2->width != w || im2->height != h || im2->stride != s) {
+        set_error("flow planes and images must share width/height/stride");
+        return false;
+    }
+    const size_t P = (size_t)s * h;
+    if (im1->c2 != im1->c1 + P || im1->c3 != im1->c2 + P || im2->c2 != im2->c1 + P || im2->c3 != im2->c2 + P) {
+        set_error("colour images must be planar and contiguous (image.c:80-87)");
+        return false;
+    }
+    return true;
+}
+
+int sfgpu_variational_dev(sfgpu_ctx *c, float *d_wx, float *d_wy, const float *d_im1, const float *d_im2, int width,
+                          int height, int stride, const variational_params_t *params) {
+    if (!c || !d_wx || !d_wy || !d_im1 || !d_im2) {
+        set_error("sfgpu_variational_dev: null argument");
+        return SFGPU_ERR_ARG;
+    }
+    if (stride != ((width + 3) / 4) * 4) {
+        set_error("stride must be ceil4(width)");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    return run_two_frame(c, Geom{width, height, stride}, d_wx, d_wy, d_im1, d_im2, params);
+}
+
+int sfgpu_variational(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_image_t *im1, const color_image_t *im2,
+                      const variational_params_t *params) {
+    if (!c) return SFGPU_ERR_ARG;
+    if (!check_pair(wx, wy, im1, im2)) return SFGPU_ERR_ARG;
+    SF_CUDA(cudaSetDevice(c->device));
+    const Geom g{wx->width, wx->height, wx->stride};
+    const size_t P = g.plane();
+    int rc = c->ensure_io(8 * P);
+    if (rc != SFGPU_OK) return rc;
+    float *d_im1 = c->io, *d_im2 = c->io + 3 * P, *d_wx = c->io + 6 * P, *d_wy = c->io + 7 * P;
+    cudaStream_t st = c->stream;
+    SF_CUDA(cudaMemcpyAsync(d_im1, im1->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st));
+    SF_CUDA(cudaMemcpyAsync(d_im2, im2->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st));
+    SF_CUDA(cudaMemcpyAsync(d_wx, wx->data, P * sizeof(float), cudaMemcpyHostToDevice, st));
+    SF_CUDA(cudaMemcpyAsync(d_wy, wy->data, P * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = run_two_frame(c, g, d_wx, d_wy, d_im1, d_im2, params);
+    if (rc != SFGPU_OK) return rc;
+    SF_CUDA(cudaMemcpyAsync(wx->data, d_wx, P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaMemcpyAsync(wy->data, d_wy, P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaStreamSynchronize(st));
+    return SFGPU_OK;
+}
+
+// legacy drop-in: thread-local default context on the current device, abort on error
+void variational(image_t *wx, image_t *wy, const color_image_t *im1, const color_image_t *im2,
+                 variational_params_t *params) {
+    struct Holder {
+        sfgpu_ctx *c = nullptr;
+        ~Holder() { if (c) sfgpu_destroy(c); }
+    };
+    static thread_local Holder holder;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    if (holder.c && holder.c->device != dev) {
+        sfgpu_destroy(holder.c);
+        holder.c = nullptr;
+    }
+    if (!holder.c && sfgpu_create(dev, nullptr, &holder.c) != SFGPU_OK) {
+        fprintf(stderr, "error in variational(): %s\n", sfgpu_last_error());
+        exit(1);
+    }
+    if (sfgpu_variational(holder.c, wx, wy, im1, im2, params) != SFGPU_OK) {
+        fprintf(stderr, "error in variational(): %s\n", sfgpu_last_error());
+        exit(1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ ABI: sequence
+int sfgpu_variational_sequence(sfgpu_ctx *c, int n_pairs, const color_image_t *const *frames, image_t *const *wx,
+                               image_t *const *wy, const variational_params_t *params) {
+    if (!c || n_pairs < 0 || !frames || !wx || !wy) {
+        set_error("sfgpu_variational_sequence: bad argument");
+        return SFGPU_ERR_ARG;
+    }
+    if (n_pairs == 0) return SFGPU_OK;
+    for (int j = 0; j < n_pairs; j++)
+        if (!check_pair(wx[j], wy[j], frames[j], frames[j + 1])) return SFGPU_ERR_ARG;
+    SF_CUDA(cudaSetDevice(c->device));
+    const Geom g{wx[0]->width, wx[0]->height, wx[0]->stride};
+    for (int j = 1; j < n_pairs; j++)
+        if (wx[j]->width != g.W || wx[j]->height != g.H) {
+            set_error("sfgpu_variational_sequence: all pairs must share one geometry");
+            return SFGPU_ERR_ARG;
+        }
+    const size_t P = g.plane();
+    // device ring: 3 frame slots (frame f -> slot f%3), 3 flow slots (pair j -> slot j%3)
+    int rc = c->ensure_io((3 * 3 + 3 * 2) * P);
+    if (rc != SFGPU_OK) return rc;
+    rc = c->ensure_workspace(g);
+    if (rc != SFGPU_OK) return rc;
+    if (!c->h2d) SF_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    if (!c->d2h) SF_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+    auto frame_slot = [&](int f) { return c->io + (size_t)(f % 3) * 3 * P; };
+    auto flow_slot = [&](int j) { return c->io + 9 * P + (size_t)(j % 3) * 2 * P; };
+
+    std::vector<cudaEvent_t> up(n_pairs + 1), done(n_pairs), down(n_pairs);
+    for (auto &e : up) SF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : done) SF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : down) SF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int status = SFGPU_OK;
+    auto upload = [&](int j) -> bool { // inputs of pair j: frame j+1 (and frame 0 for j == 0) + initial flow j
+        if (j >= 2 && !cuda_ok(cudaStreamWaitEvent(c->h2d, done[j - 2], 0), "wait done")) return false;   // frame slot (j+1)%3 last read by pair j-2
+        if (j >= 3 && !cuda_ok(cudaStreamWaitEvent(c->h2d, down[j - 3], 0), "wait down")) return false;   // flow slot j%3 last drained for pair j-3
+        if (j == 0 && !cuda_ok(cudaMemcpyAsync(frame_slot(0), frames[0]->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, c->h2d), "h2d frame")) return false;
+        if (!cuda_ok(cudaMemcpyAsync(frame_slot(j + 1), frames[j + 1]->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, c->h2d), "h2d frame")) return false;
+        if (!cuda_ok(cudaMemcpyAsync(flow_slot(j), wx[j]->data, P * sizeof(float), cudaMemcpyHostToDevice, c->h2d), "h2d wx")) return false;
+        if (!cuda_ok(cudaMemcpyAsync(flow_slot(j) + P, wy[j]->data, P * sizeof(float), cudaMemcpyHostToDevice, c->h2d), "h2d wy")) return false;
+        return cuda_ok(cudaEventRecord(up[j], c->h2d), "record up");
+    };
+    auto download = [&](int j) -> bool {
+        if (!cuda_ok(cudaStreamWaitEvent(c->d2h, done[j], 0), "wait done")) return false;
+        if (!cuda_ok(cudaMemcpyAsync(wx[j]->data, flow_slot(j), P * sizeof(float), cudaMemcpyDeviceToHost, c->d2h), "d2h wx")) return false;
+        if (!cuda_ok(cudaMemcpyAsync(wy[j]->data, flow_slot(j) + P, P * sizeof(float), cudaMemcpyDeviceToHost, c->d2h), "d2h wy")) return false;
+        return cuda_ok(cudaEventRecord(down[j], c->d2h), "record down");
+    };
+    // the previous work on the compute stream may still use the io ring
+    {
+        cudaEvent_t e0;
+        if (cuda_ok(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming), "event")) {
+            cudaEventRecord(e0, c->stream);
+            cudaStreamWaitEvent(c->h2d, e0, 0);
+            cudaEventDestroy(e0);
+        }
+    }
+    if (!upload(0)) status = SFGPU_ERR_CUDA;
+    for (int j = 0; j < n_pairs && status == SFGPU_OK; j++) {
+        if (!cuda_ok(cudaStreamWaitEvent(c->stream, up[j], 0), "wait up")) { status = SFGPU_ERR_CUDA; break; }
+        status = run_two_frame(c, g, flow_slot(j), flow_slot(j) + P, frame_slot(j), frame_slot(j + 1), params);
+        if (status != SFGPU_OK) break;
+        if (!cuda_ok(cudaEventRecord(done[j], c->stream), "record done")) { status = SFGPU_ERR_CUDA; break; }
+        if (j + 1 < n_pairs && !upload(j + 1)) { status = SFGPU_ERR_CUDA; break; }
+        if (!download(j)) { status = SFGPU_ERR_CUDA; break; }
+    }
+    cudaStreamSynchronize(c->h2d);
+    cudaStreamSynchronize(c->stream);
+    if (!cuda_ok(cudaStreamSynchronize(c->d2h), "sync d2h") && status == SFGPU_OK) status = SFGPU_ERR_CUDA;
+    for (auto e : up) cudaEventDestroy(e);
+    for (auto e : done) cudaEventDestroy(e);
+    for (auto e : down) cudaEventDestroy(e);
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------ ABI: operator twins
+static bool same_geom(const image_t *a, int w, int h, int s) { return a && a->data && a->width == w && a->height == h && a->stride == s; }
+
+struct DevPlanes { // scratch device planes for the operator twins
+    float *p = nullptr;
+    ~DevPlanes() { if (p) cudaFree(p); }
+    int alloc(size_t floats) { SF_CUDA(cudaMalloc(&p, floats * sizeof(float))); return SFGPU_OK; }
+};
+#define H2D(dst, src, n) SF_CUDA(cudaMemcpyAsync((dst), (src), (n) * sizeof(float), cudaMemcpyHostToDevice, st))
+#define D2H(dst, src, n) SF_CUDA(cudaMemcpyAsync((dst), (src), (n) * sizeof(float), cudaMemcpyDeviceToHost, st))
+
+int sfgpu_image_warp(sfgpu_ctx *c, color_image_t *dst, image_t *mask, const color_image_t *src, const image_t *wx,
+                     const image_t *wy, int factor) {
+    if (!c || !dst || !src || !wx || !wy) return SFGPU_ERR_ARG;
+    SF_CUDA(cudaSetDevice(c->device));
+    const Geom g{src->width, src->height, src->stride};
+    const size_t P = g.plane();
+    cudaStream_t st = c->stream;
+    DevPlanes d;
+    int rc = d.alloc(9 * P);
+    if (rc) return rc;
+    float *s3 = d.p, *fx = d.p + 3 * P, *fy = d.p + 4 * P, *o3 = d.p + 5 * P, *m = d.p + 8 * P;
+    H2D(s3, src->c1, 3 * P); H2D(fx, wx->data, P); H2D(fy, wy->data, P);
+    launch_warp(st, g, s3, fx, fy, factor, o3, mask ? m : nullptr);
+    D2H(dst->c1, o3, 3 * P);
+    if (mask) D2H(mask->data, m, P);
+    SF_CUDA(cudaStreamSynchronize(st));
+    SF_CUDA(cudaGetLastError());
+    return SFGPU_OK;
+}
+
+int sfgpu_compute_dpsis_weight(sfgpu_ctx *c, image_t *dst, const color_image_t *im, float coef, const float *avg3,
+                               const float *std3, int hbit) {
+    if (!c || !dst || !im) return SFGPU_ERR_ARG;
+    SF_CUDA(cudaSetDevice(c->device));
+    const Geom g{im->width, im->height, im->stride};
+    const size_t P = g.plane();
+    cudaStream_t st = c->stream;
+    DevPlanes d;
+    int rc = d.alloc(4 * P);
+    if (rc) return rc;
+    const float a0[3] = {0.f, 0.f, 0.f}, s1[3] = {1.f, 1.f, 1.f};
+    H2D(d.p, im->c1, 3 * P);
+    launch_dpsis_weight(st, g, d.p, d.p + 3 * P, coef, avg3 ? avg3 : a0, std3 ? std3 : s1, hbit ? 65535.0f : 255.0f);
+    D2H(dst->data, d.p + 3 * P, P);
+    SF_CUDA(cudaStreamSynchronize(st));
+    SF_CUDA(cudaGetLastError());
+    return SFGPU_OK;
+}
+
+int sfgpu_compute_smoothness(sfgpu_ctx *c, image_t *dst_horiz, image_t *dst_vert, const image_t *uu, const image_t *vv,
+                             const image_t *w, float alpha_factor, int robust_reg, float reg_eps, float reg_trunc,
+                             int mode) {
+    if (!c || !dst_horiz || !dst_vert || !uu || !vv || !w) return SFGPU_ERR_ARG;
+    if (mode < 0 || mode > 1) {
+        set_error("smoothing modes >= 2 are not supported (reference bug Q6)");
+        return SFGPU_ERR_UNSUPPORTED;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    const Geom g{uu->width, uu->height, uu->stride};
+    const size_t P = g.plane();
+    cudaStream_t st = c->stream;
+    DevPlanes d;
+    int rc = d.alloc(5 * P);
+    if (rc) return rc;
+    H2D(d.p, uu->data, P); H2D(d.p + P, vv->data, P); H2D(d.p + 2 * P, w->data, P);
+    Penalty reg = make_penalty(robust_reg, reg_eps, reg_trunc);
+    launch_smoothness(st, g, d.p, d.p + P, d.p + 2 * P, alpha_factor, reg, mode, d.p + 3 * P, d.p + 4 * P);
+    D2H(dst_horiz->data, d.p + 3 * P, P); D2H(dst_vert->data, d.p + 4 * P, P);
+    SF_CUDA(cudaStreamSynchronize(st));
+    SF_CUDA(cudaGetLastError());
+    return SFGPU_OK;
+}
+
+int sfgpu_compute_data_and_match(sfgpu_ctx *c, image_t *a11, image_t *a12, image_t *a22, image_t *b1, image_t *b2,
+                                 const image_t *mask, const image_t *du, const image_t *dv, const color_image_t *im1,
+                                 const color_image_t *im2w, float half_delta_over3, float half_gamma_over3) {
+    if (!c || !a11 || !a12 || !a22 || !b1 || !b2 || !mask || !du || !dv || !im1 || !im2w) return SFGPU_ERR_ARG;
+    SF_CUDA(cudaSetDevice(c->device));
+    const Geom g{im1->width, im1->height, im1->stride};
+    if (g.W < 5 || g.H < 5) return SFGPU_ERR_ARG;
+    const size_t P = g.plane();
+    cudaStream_t st = c->stream;
+    DevPlanes d;
+    int rc = d.alloc(14 * P);
+    if (rc) return rc;
+    float *i1 = d.p, *i2 = d.p + 3 * P, *m = d.p + 6 * P, *u = d.p + 7 * P, *v = d.p + 8 * P, *o = d.p + 9 * P;
+    H2D(i1, im1->c1, 3 * P); H2D(i2, im2w->c1, 3 * P); H2D(m, mask->data, P); H2D(u, du->data, P); H2D(v, dv->data, P);
+    launch_data_two_frame(st, g, i1, i2, m, u, v, half_delta_over3, half_gamma_over3, false, nullptr, nullptr, nullptr,
+                          nullptr, o, o + P, o + 2 * P, o + 3 * P, o + 4 * P);
+    D2H(a11->data, o, P); D2H(a12->data, o + P, P); D2H(a22->data, o + 2 * P, P); D2H(b1->data, o + 3 * P, P);
+    D2H(b2->data, o + 4 * P, P);
+    SF_CUDA(cudaStreamSynchronize(st));
+    SF_CUDA(cudaGetLastError());
+    return SFGPU_OK;
+}
+
+int sfgpu_sub_laplacian(sfgpu_ctx *c, image_t *dst, const image_t *src, const image_t *wh, const image_t *wv) {
+    if (!c || !dst || !src || !wh || !wv) return SFGPU_ERR_ARG;
+    SF_CUDA(cudaSetDevice(c->device));
+    const Geom g{src->width, src->height, src->stride};
+    const size_t P = g.plane();
+    cudaStream_t st = c->stream;
+    DevPlanes d;
+    int rc = d.alloc(4 * P);
+    if (rc) return rc;
+    H2D(d.p, dst->data, P); H2D(d.p + P, src->data, P); H2D(d.p + 2 * P, wh->data, P); H2D(d.p + 3 * P, wv->data, P);
+    launch_sub_laplacian(st, g, d.p, d.p + P, d.p + 2 * P, d.p + 3 * P);
+    D2H(dst->data, d.p, P);
+    SF_CUDA(cudaStreamSynchronize(st));
+    SF_CUDA(cudaGetLastError());
+    return SFGPU_OK;
+}
+
+int sfgpu_sor_coupled(sfgpu_ctx *c, image_t *du, image_t *dv, image_t *a11, image_t *a12, image_t *a22,
+                      const image_t *b1, const image_t *b2, const image_t *ph, const image_t *pv, int iterations,
+                      float omega) {
+    if (!c || !du || !dv || !a11 || !a12 || !a22 || !b1 || !b2 || !ph || !pv) return SFGPU_ERR_ARG;
+    const int w = du->width, h = du->height, s = du->stride;
+    if (!same_geom(dv, w, h, s) || !same_geom(a11, w, h, s) || !same_geom(a12, w, h, s) || !same_geom(a22, w, h, s) ||
+        !same_geom(b1, w, h, s) || !same_geom(b2, w, h, s) || !same_geom(ph, w, h, s) || !same_geom(pv, w, h, s)) {
+        set_error("sfgpu_sor_coupled: geometry mismatch");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    const Geom g{w, h, s};
+    int rc = c->ensure_workspace(g);
+    if (rc != SFGPU_OK) return rc;
+    const size_t P = g.plane();
+    cudaStream_t st = c->stream;
+    float *A = c->sor.arena;
+    H2D(A + SP_A11 * P, a11->data, P); H2D(A + SP_A12 * P, a12->data, P); H2D(A + SP_A22 * P, a22->data, P);
+    H2D(A + SP_B1 * P, b1->data, P); H2D(A + SP_B2 * P, b2->data, P); H2D(A + SP_PH * P, ph->data, P);
+    H2D(A + SP_PV * P, pv->data, P); H2D(A + SP_DUA * P, du->data, P); H2D(A + SP_DVA * P, dv->data, P);
+    launch_invert_blocks(st, g, A + SP_A11 * P, A + SP_A12 * P, A + SP_A22 * P, A + SP_PH * P, A + SP_PV * P);
+    int cur = 0;
+    rc = run_sor(c, iterations, omega, &cur, false);
+    if (rc != SFGPU_OK) return rc;
+    D2H(du->data, A + (size_t)(cur ? SP_DUB : SP_DUA) * P, P);
+    D2H(dv->data, A + (size_t)(cur ? SP_DVB : SP_DVA) * P, P);
+    D2H(a11->data, A + SP_A11 * P, P); D2H(a12->data, A + SP_A12 * P, P); D2H(a22->data, A + SP_A22 * P, P);
+    SF_CUDA(cudaStreamSynchronize(st));
+    SF_CUDA(cudaGetLastError());
+    return SFGPU_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,57 @@
+// sf_context.cuh -- the per-thread / per-device context behind sfgpu_ctx.
+#pragma once
+#include <vector>
+
+#include "sf_internal.cuh"
+
+struct sfgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+
+    int sor_variant = 0; // 0 tiled, 1 per-half-sweep launches
+    int sor_fuse = 0;    // 0 = auto
+
+    // ---- level workspace (one allocation, re-made when the geometry grows)
+    sf::Geom g{0, 0, 0};
+    float *ws = nullptr;
+    size_t ws_floats = 0;
+    sf::SorPlan sor;
+    float *wim = nullptr;   // 3 planes: warped second image (two-frame)
+    float *mask = nullptr;  // 1 plane
+    float *uu = nullptr, *vv = nullptr;
+    float *dpsis = nullptr;
+
+    // ---- host-API staging (device copies of caller buffers)
+    float *io = nullptr; // im1(3) im2(3) wx wy   [+ ring for the sequence API]
+    size_t io_floats = 0;
+
+    // ---- sequence pipeline
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+
+    // ---- profiling
+    bool prof = false;
+    struct EvPair { cudaEvent_t a, b; int kind; };
+    std::vector<EvPair> ev_pending;
+    std::vector<cudaEvent_t> ev_free;
+    sfgpu_profile_t prof_acc{};
+
+    sfgpu_mt_stats_t mt_stats{};
+
+    // helpers
+    int ensure_workspace(sf::Geom geom);
+    int ensure_io(size_t floats);
+    cudaEvent_t get_event();
+    void prof_begin(int kind, cudaEvent_t &a);
+    void prof_end(int kind, cudaEvent_t a);
+    int prof_collect();
+};
+
+namespace sf {
+// two-frame refinement on device planes (variational.c:19-82 + :101-143)
+int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d_im1, const float *d_im2,
+                  const variational_params_t *params);
+// one sor_coupled call on the context's SOR arena (profiled)
+int run_sor(sfgpu_ctx *c, int iterations, float omega, int *cur, bool zero_init);
+} // namespace sf

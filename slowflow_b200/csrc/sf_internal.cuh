@@ -1,0 +1,91 @@
+// sf_internal.cuh -- internal declarations shared by the CUDA translation units of libslowflow_gpu.so.
+// Nothing here is part of the ABI (see include/slowflow_gpu.h).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "slowflow_gpu.h"
+
+namespace sf {
+
+// ---------------------------------------------------------------------------------------------
+// geometry of one pyramid level: W valid columns, H rows, S = ceil4(W) floats per row (image.c:25).
+// Device planes use exactly the host layout, so a plane moves with one cudaMemcpyAsync.
+struct Geom {
+    int W, H, S;
+    __host__ __device__ size_t plane() const { return (size_t)S * H; }
+};
+static inline Geom make_geom(int w, int h) { return Geom{w, h, ((w + 3) / 4) * 4}; }
+
+// thread-local error string behind sfgpu_last_error()
+void set_error(const std::string &msg);
+bool cuda_ok(cudaError_t e, const char *what);
+#define SF_CUDA(call)                                         \
+    do {                                                      \
+        if (!::sf::cuda_ok((call), #call)) return SFGPU_ERR_CUDA; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// robust penalties (penalty_functions/*.h), selected at run time inside the kernels by a small POD
+struct Penalty {
+    int type;        // SF_ROBUST_*
+    float eps_sq_f;  // epsilon_vec_sq / float epsilon_sq
+    double eps_sq_d; // double epsilon_sq (ModL1, Lorentzian, Geman-McClure keep it in double)
+    float trunc;     // TruncModifiedL1Norm::truncation
+};
+Penalty make_penalty(int type, float eps, float trunc);
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers (all asynchronous on `st`)
+
+// K0: smoothness weight 0.5*exp(-coef*|grad lum|) (variational_aux.c:183 ; variational_aux_mt.cpp:673)
+void launch_dpsis_weight(cudaStream_t st, Geom g, const float *im3, float *out, float coef, const float avg[3],
+                         const float stdv[3], float divisor);
+// K1: bilinear warp with integer time factor (variational_aux.c:18 ; variational_aux_mt.cpp:722)
+void launch_warp(cudaStream_t st, Geom g, const float *src3, const float *wx, const float *wy, int factor,
+                 float *dst3, float *mask /*nullable*/);
+// K3: smoothness diffusivities.  reg.type < 0: two-frame form (variational_aux.c:84), else MT modes 0/1.
+void launch_smoothness(cudaStream_t st, Geom g, const float *uu, const float *vv, const float *w, float alpha_factor,
+                       Penalty reg, int mode, float *ph, float *pv);
+// K2 (two-frame): derivatives + data term [+ laplacian + 2x2 block inverse when fuse_system]
+//   fuse_system = false: writes the raw a11,a12,a22,b1,b2 of compute_data_and_match (variational_aux.c:215)
+//   fuse_system = true : also adds div(psi grad lap_u/lap_v) (variational_aux.c:153) and stores the inverted
+//                        blocks exactly as sor_coupled's first sweep would (solver.c:101-106).
+void launch_data_two_frame(cudaStream_t st, Geom g, const float *im1, const float *im2w, const float *mask,
+                           const float *du, const float *dv, float half_delta_over3, float half_gamma_over3,
+                           bool fuse_system, const float *ph, const float *pv, const float *lap_u,
+                           const float *lap_v, float *a11, float *a12, float *a22, float *b1, float *b2);
+// sub_laplacian as a gather (operator twin)
+void launch_sub_laplacian(cudaStream_t st, Geom g, float *dst, const float *src, const float *ph, const float *pv);
+// in-place inverse of the 2x2 blocks (operator twin of the first SOR sweep's prologue)
+void launch_invert_blocks(cudaStream_t st, Geom g, float *a11, float *a12, float *a22, const float *ph, const float *pv);
+// K5: dst = a + b over the whole plane (variational.c:60-65)
+void launch_add(cudaStream_t st, Geom g, float *dst, const float *a, const float *b);
+void launch_fill(cudaStream_t st, float *dst, size_t n, float v);
+
+// ---------------------------------------------------------------------------------------------
+// K4: red-black SOR on the coupled 2x2-block 5-point system (solver.c:63, re-ordered).
+// The SOR arena is 11 consecutive planes: a11' a12' a22' b1 b2 psi_h psi_v duA dvA duB dvB.
+enum SorPlane { SP_A11 = 0, SP_A12, SP_A22, SP_B1, SP_B2, SP_PH, SP_PV, SP_DUA, SP_DVA, SP_DUB, SP_DVB, SP_COUNT };
+
+struct SorPlan {
+    Geom g{0, 0, 0};
+    float *arena = nullptr; // SP_COUNT planes
+    CUtensorMap tmap;       // 3-D (x, y, plane) view of the arena
+    bool tmap_valid = false;
+    int num_sms = 0;
+};
+// Encode the TMA descriptor for an arena.  Returns false (and sets the error) on failure.
+bool sor_plan_init(SorPlan &plan, Geom g, float *arena, int num_sms);
+// Runs `iterations` sweeps; the iterate starts in (duA,dvA) when *cur==0 or (duB,dvB) when *cur==1 and
+// *cur is updated to the buffer holding the result.  zero_init: treat the initial iterate as 0.
+// variant 0: tiled / temporally blocked (fuse sweeps per launch), variant 1: one launch per half sweep.
+// Returns the number of kernel launches issued (negative on error).
+int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int variant, int fuse, int *cur,
+               bool zero_init);
+
+} // namespace sf

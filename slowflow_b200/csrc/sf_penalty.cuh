@@ -1,0 +1,75 @@
+// sf_penalty.cuh -- the robust penalties of penalty_functions/*.h as device functions.
+//
+// The reference has two code paths per penalty with different rounding: the v4sf overloads (fp32,
+// used by the data terms, variational_aux_mt.cpp:166-634, and the occlusion costs :815-824) and the
+// scalar overloads (computed in double where epsilon_sq is a double member, used by
+// compute_smoothness :65,90).  Both are reproduced as written, including the unmatched
+// Geman-McClure psi / psi' pair (geman_mcclure.h:20-38) and the truncated-L1 compare of
+// sqrt(s^2) against tau (trunc_modified_l1_norm.h:20-54).
+#pragma once
+#include "sf_internal.cuh"
+
+namespace sf {
+
+// psi'(s^2), v4sf overloads (fp32)
+__device__ __forceinline__ float penalty_deriv_v(const Penalty &p, float xsq) {
+    switch (p.type) {
+    case SF_ROBUST_QUADRATIC: return 1.0f;
+    case SF_ROBUST_LORENTZIAN: return 1.0f / (2.0f * p.eps_sq_f + xsq);
+    case SF_ROBUST_GEMAN_MCCLURE: {
+        float t = p.eps_sq_f + xsq;
+        t = t * t;
+        return (p.eps_sq_f + 2.0f * xsq) / t;
+    }
+    case SF_ROBUST_TRUNC_MODL1: {
+        if (sqrtf(xsq) > p.trunc) return 0.0f;
+        return 1.0f / (2.0f * sqrtf(xsq + p.eps_sq_f));
+    }
+    default: return 1.0f / (2.0f * sqrtf(xsq + p.eps_sq_f)); // ModifiedL1Norm
+    }
+}
+
+// psi'(s^2), scalar overloads (double inside where the reference's member is double)
+__device__ __forceinline__ float penalty_deriv_s(const Penalty &p, float xsq) {
+    switch (p.type) {
+    case SF_ROBUST_QUADRATIC: return 1.0f;
+    case SF_ROBUST_LORENTZIAN: return (float)(1.0 / (2.0 * p.eps_sq_d + (double)xsq));
+    case SF_ROBUST_GEMAN_MCCLURE: {
+        float t = (float)(p.eps_sq_d + (double)xsq);
+        t = t * t;
+        return (float)((p.eps_sq_d + 2.0 * (double)xsq) / (double)t);
+    }
+    case SF_ROBUST_TRUNC_MODL1: {
+        if (sqrtf(xsq) > p.trunc) return 0.0f;
+        return 1.0f / (2.0f * sqrtf(xsq + p.eps_sq_f));
+    }
+    default: return (float)(1.0 / (2.0 * sqrt((double)xsq + p.eps_sq_d)));
+    }
+}
+
+// psi(s^2), v4sf overloads (occlusion data costs)
+__device__ __forceinline__ float penalty_apply_v(const Penalty &p, float xsq) {
+    switch (p.type) {
+    case SF_ROBUST_QUADRATIC: return xsq;
+    case SF_ROBUST_LORENTZIAN: return (float)log(1.0 + 0.5 * (double)xsq / p.eps_sq_d);
+    case SF_ROBUST_GEMAN_MCCLURE: return xsq / ((xsq + 1.0f) * (xsq + 1.0f));
+    case SF_ROBUST_TRUNC_MODL1: {
+        if (sqrtf(xsq) > p.trunc) return sqrtf(p.trunc + p.eps_sq_f);
+        return sqrtf(xsq + p.eps_sq_f);
+    }
+    default: return sqrtf(xsq + p.eps_sq_f);
+    }
+}
+
+// smoothness diffusivity of one edge.
+//   type < 0 : two-frame form (w+w')*half_alpha / sqrt(s^2 + 1e-6), sqrt and divide in double (variational_aux.c:124)
+//   else     : (w+w')*alpha * psi'_reg(s^2) through the scalar overload (variational_aux_mt.cpp:65)
+__device__ __forceinline__ float smooth_weight(const Penalty &reg, float ww, float alpha_factor, float ssq) {
+    if (reg.type < 0) {
+        const float eps_smooth = 0.001f * 0.001f;
+        return (float)((double)(ww * alpha_factor) / sqrt((double)(ssq + eps_smooth)));
+    }
+    return ww * alpha_factor * penalty_deriv_s(reg, ssq);
+}
+
+} // namespace sf
