@@ -15,7 +15,7 @@
 //     vertical neighbours across warps through a 16 KB double-buffered exchange area.
 //   * T sweeps (2T half sweeps) run per HBM round trip; the outer 2T pixels of the tile are halo that
 //     is recomputed by the neighbouring tile.  HBM traffic per sweep drops from 44 B/px to
-//     (36/f + 8)/T B/px with f = ((64-4T)/64)^2.
+//     (36/f + 8)/T B/px with f = the interior fraction of the tile (e.g. 56x56/64x64 for T = 2).
 //   * du,dv ping-pong between two arena buffers (a tile's halo is another tile's interior).
 // Variant 1 (validation, tiny images): one launch per half sweep straight from global memory.
 #include "sf_internal.cuh"
@@ -74,18 +74,25 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// bounded spin: a TMA that never completes (bad descriptor) traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
     asm volatile(
@@ -146,8 +153,10 @@ __global__ void __launch_bounds__(SOR_NW * 32, 1) k_sor_tiled(const __grid_const
     uint64_t *mbar = reinterpret_cast<uint64_t *>(base + SOR_STAGE_BYTES + SOR_EXCH_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int halo = 2 * a.T;
-    const int IW = SOR_TW - 2 * halo, IH = SOR_TH - 2 * halo;
+    // halo: 2T pixels per side.  TMA needs the box origin 16-byte aligned along x, so the horizontal
+    // halo is rounded up to a multiple of 4 floats (tile origins stay multiples of 4).
+    const int hy = 2 * a.T, hx = (2 * a.T + 3) & ~3;
+    const int IW = SOR_TW - 2 * hx, IH = SOR_TH - 2 * hy;
     const int ntiles = a.tiles_x * a.tiles_y;
     const int nload = a.zero_init ? 7 : 9;
 
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(SOR_NW * 32, 1) k_sor_tiled(const __grid_const
 
     auto issue = [&](int tile) {
         const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-        const int x0 = tx * IW - halo, y0 = ty * IH - halo;
+        const int x0 = tx * IW - hx, y0 = ty * IH - hy;
         mbar_expect_tx(mbar, (uint32_t)(nload * SOR_PLANE_FLOATS * 4));
 #pragma unroll 1
         for (int pl = 0; pl < nload; pl++) {
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(SOR_NW * 32, 1) k_sor_tiled(const __grid_const
 
     while (tile < ntiles) {
         const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-        const int x0 = tx * IW - halo, y0 = ty * IH - halo;
+        const int x0 = tx * IW - hx, y0 = ty * IH - hy;
 
         mbar_wait(mbar, phase);
         phase ^= 1u;
@@ -244,11 +253,11 @@ __global__ void __launch_bounds__(SOR_NW * 32, 1) k_sor_tiled(const __grid_const
 
         // ---- interior of the tile -> global (float2 per lane and row: 256 B per warp row)
         const int cx = 2 * lane, gx = x0 + cx;
-        if (cx >= halo && cx < SOR_TW - halo && gx < a.g.W) {
+        if (cx >= hx && cx < SOR_TW - hx && gx < a.g.W) {
 #pragma unroll
             for (int r = 0; r < SOR_R; r++) {
                 const int tr = warp * SOR_R + r, gy = y0 + tr;
-                if (tr >= halo && tr < SOR_TH - halo && gy < a.g.H) {
+                if (tr >= hy && tr < SOR_TH - hy && gy < a.g.H) {
                     const size_t o = (size_t)gy * a.g.S + gx;
                     *reinterpret_cast<float2 *>(a.out_du + o) = make_float2(q.du[r][0], q.du[r][1]);
                     *reinterpret_cast<float2 *>(a.out_dv + o) = make_float2(q.dv[r][0], q.dv[r][1]);
@@ -344,7 +353,7 @@ int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int 
         SorTiledArgs a;
         a.g = g;
         a.T = T;
-        const int IW = SOR_TW - 4 * T, IH = SOR_TH - 4 * T;
+        const int IW = SOR_TW - 2 * ((2 * T + 3) & ~3), IH = SOR_TH - 4 * T;
         a.tiles_x = (g.W + IW - 1) / IW;
         a.tiles_y = (g.H + IH - 1) / IH;
         a.omega = omega;

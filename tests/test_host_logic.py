@@ -1,0 +1,61 @@
+"""Host-side logic that needs no GPU: containers, synthetic inputs, sharding (world_size 2, gloo)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from slowflow_b200 import ColorImage, Image, synth
+from slowflow_b200.shard import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_image_layout_matches_reference_rules():
+    im = Image(61, 7)
+    assert im.stride == 64 and im.buf.ctypes.data % 16 == 0 and im.full.shape == (7, 64)
+    c = ColorImage(2073, 3)
+    assert c.stride == 2076
+    base = C_addr(c.c.c1)
+    assert C_addr(c.c.c2) - base == 4 * c.stride * c.height and C_addr(c.c.c3) - base == 8 * c.stride * c.height
+
+
+def C_addr(p):
+    import ctypes as C
+    return C.cast(p, C.c_void_p).value
+
+
+def test_synth_is_deterministic_and_in_range():
+    a = synth.frame(97, 53, 1)
+    b = synth.frame(97, 53, 1)
+    assert np.array_equal(a, b) and a.dtype == np.float32
+    assert a.min() >= 0.0 and a.max() <= 255.0 and a.std() > 10
+    u0, v0 = synth.initial_flow(97, 53)
+    u, v = synth.gt_flow(97, 53)
+    assert np.abs(u0 - u).max() <= 0.25 + 1e-6 and np.abs(v0 - v).max() <= 0.25 + 1e-6
+    assert np.array_equal(u0, synth.initial_flow(97, 53)[0])
+    z = synth.initial_flow(9, 9, zero=True)
+    assert not z[0].any() and not z[1].any()
+
+
+def test_shard_range_partitions_everything():
+    for n in (0, 1, 7, 240, 241):
+        for world in (1, 2, 3, 4, 8):
+            got = []
+            for r in range(world):
+                lo, hi = shard_range(n, r, world)
+                assert 0 <= lo <= hi <= n
+                got += list(range(lo, hi))
+            assert got == list(range(n))
+            sizes = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_gloo_sharding_and_max_time():
+    """The N>1 bench path on CPU: 2 ranks (gloo) shard 7 units, agree on max-over-ranks time and total."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29581",
+                          os.path.join(ROOT, "tests", "_gloo_worker.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "rank=0:ok:0:4" in out.stdout and "rank=1:ok:4:7" in out.stdout
