@@ -111,7 +111,7 @@ int sfgpu_ctx::prof_collect() {
     return SFGPU_OK;
 }
 
-static int auto_fuse(const sfgpu_ctx *c) { return c->sor_fuse > 0 ? c->sor_fuse : 5; }
+static int auto_fuse(const sfgpu_ctx *c) { return c->sor_fuse > 0 ? c->sor_fuse : 4; }
 
 // ------------------------------------------------------------------------------------------ two-frame driver
 namespace sf {
@@ -166,9 +166,14 @@ int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d
             cudaEvent_t ev;
             c->prof_begin(PROF_DATA, ev);
             // variational.c:53-55 + the block inverse of solver.c:101-106, one pass
-            launch_data_two_frame(st, g, d_im1, c->wim, c->mask, du, dv, half_delta_over3, half_gamma_over3, true,
-                                  A + SP_PH * P, A + SP_PV * P, d_wx, d_wy, A + SP_A11 * P, A + SP_A12 * P,
-                                  A + SP_A22 * P, A + SP_B1 * P, A + SP_B2 * P);
+            DataTermDesc term{d_im1, c->wim, +1, c->mask, DK_TWO_FRAME, half_delta_over3, half_gamma_over3, 1.0f, -1};
+            DataCommon cm{};
+            cm.du = du; cm.dv = dv; cm.chw = nullptr; cm.occ = nullptr; cm.data_norm = 1.0f; cm.dt_norm = 1;
+            cm.pc = two_frame_reg; cm.pg = two_frame_reg; cm.accumulate = false; cm.fuse_system = true;
+            cm.ph = A + SP_PH * P; cm.pv = A + SP_PV * P; cm.lap_u = d_wx; cm.lap_v = d_wy;
+            cm.a11 = A + SP_A11 * P; cm.a12 = A + SP_A12 * P; cm.a22 = A + SP_A22 * P; cm.b1 = A + SP_B1 * P;
+            cm.b2 = A + SP_B2 * P;
+            launch_data_term(st, g, term, cm);
             c->prof_end(PROF_DATA, ev);
             c->prof_acc.data_launches++;
             c->prof_acc.data_pixels += (long long)g.W * g.H;
@@ -568,8 +573,12 @@ int sfgpu_compute_data_and_match(sfgpu_ctx *c, image_t *a11, image_t *a12, image
     if (rc) return rc;
     float *i1 = d.p, *i2 = d.p + 3 * P, *m = d.p + 6 * P, *u = d.p + 7 * P, *v = d.p + 8 * P, *o = d.p + 9 * P;
     H2D(i1, im1->c1, 3 * P); H2D(i2, im2w->c1, 3 * P); H2D(m, mask->data, P); H2D(u, du->data, P); H2D(v, dv->data, P);
-    launch_data_two_frame(st, g, i1, i2, m, u, v, half_delta_over3, half_gamma_over3, false, nullptr, nullptr, nullptr,
-                          nullptr, o, o + P, o + 2 * P, o + 3 * P, o + 4 * P);
+    DataTermDesc term{i1, i2, +1, m, DK_TWO_FRAME, half_delta_over3, half_gamma_over3, 1.0f, -1};
+    DataCommon cm{};
+    cm.du = u; cm.dv = v; cm.data_norm = 1.0f; cm.dt_norm = 1; cm.pc = make_penalty(1, 0.001f, 0.5f); cm.pg = cm.pc;
+    cm.accumulate = false; cm.fuse_system = false;
+    cm.a11 = o; cm.a12 = o + P; cm.a22 = o + 2 * P; cm.b1 = o + 3 * P; cm.b2 = o + 4 * P;
+    launch_data_term(st, g, term, cm);
     D2H(a11->data, o, P); D2H(a12->data, o + P, P); D2H(a22->data, o + 2 * P, P); D2H(b1->data, o + 3 * P, P);
     D2H(b2->data, o + 4 * P, P);
     SF_CUDA(cudaStreamSynchronize(st));

@@ -1,0 +1,429 @@
+// sf_data.cu -- K2: image derivatives + robust data term in one fused pass (sm_100a).
+//
+// Replaces, per data term, the reference's chain
+//     mean / temporal difference  (variational_aux.c:63-69 ; variational_mt.cpp:118-161)
+//     7 separable 5-tap convolutions per colour image -> 24 derivative planes (variational_aux.c:71-77)
+//     compute_data_and_match      (variational_aux.c:215-302)            kind DK_TWO_FRAME
+//     add_data_and_match          (variational_aux_mt.cpp:166-403)       kind DK_MT_SUCC
+//     add_data_and_match_ref      (variational_aux_mt.cpp:408-634)       kind DK_MT_REF
+//   [+ sub_laplacian (variational_aux.c:153-180) and the 2x2 block inverse of sor_coupled's first
+//      sweep (solver.c:101-106) when fuse_system is set on the last term]
+// Nothing but the two input images, the mask and the 5 system planes touches HBM: the derivative
+// planes live in shared memory / registers.
+//
+// CTA = 256 threads (32 x 8), output tile 32 x 32, 4 pixels per thread.
+//   stage 1  m = 0.5*(B + A), z = +-(B - A) on the tile + 4 px halo   (float4 loads on interior tiles)
+//   stage 2  Ix = d/dx m on tile+2, Iy = d/dy m on tile columns x (tile rows + 2)
+//   stage 3  per pixel: Ixx Ixy Iyy Ixz Iyz (+ Ix Iy Iz), robust weights, 2x2 system contribution
+// Border semantics follow image.c:400-526 (clamped columns, folded vertical taps); tiles that do not
+// touch the image border take a branch-free path.
+#include "sf_internal.cuh"
+#include "sf_penalty.cuh"
+#include "sf_stencil.cuh"
+
+namespace sf {
+
+constexpr int DT_TW = 32, DT_TH = 32, DT_HALO = 4;
+constexpr int DT_MW = DT_TW + 2 * DT_HALO; // 40 columns of m / z (multiple of 4: float4 staging)
+constexpr int DT_MH = DT_TH + 2 * DT_HALO; // 40 rows
+constexpr int DT_XW = DT_TW + 4;           // Ix columns (x-2 .. x+2)
+constexpr int DT_XH = DT_TH + 4;           // Ix / Iy rows (y-2 .. y+2)
+constexpr size_t DT_SMEM_FLOATS = 3 * (2 * DT_MH * DT_MW + DT_XH * DT_XW + DT_XH * DT_TW);
+
+struct Derivs {
+    float ix[3], iy[3], iz[3], ixx[3], ixy[3], iyy[3], ixz[3], iyz[3];
+};
+struct Acc {
+    float a11, a12, a22, b1, b2;
+};
+
+// ---- two-frame data term (variational_aux.c:241-296).  Quotients x/n are evaluated as x * rcp(n) with a
+// correctly rounded reciprocal and 1/sqrt through rsqrtf (<= 2 ulp from the reference's divps / sqrtps).
+__device__ __forceinline__ void term_two_frame(const Derivs &d, float u, float v, float m, float hd, float hg, Acc &acc) {
+    const float dnorm = 0.1f * 0.1f, eps_color = 0.001f * 0.001f, eps_grad = 0.001f * 0.001f;
+    if (hd != 0.0f) {
+        float r[3], inv[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            r[c] = d.iz[c] + d.ix[c] * u + d.iy[c] * v;
+            inv[c] = __frcp_rn(d.ix[c] * d.ix[c] + d.iy[c] * d.iy[c] + dnorm);
+        }
+        const float t = m * hd * rsqrtf(r[0] * r[0] * inv[0] + r[1] * r[1] * inv[1] + r[2] * r[2] * inv[2] + eps_color);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float gc = t * inv[c];
+            acc.a11 += gc * d.ix[c] * d.ix[c];
+            acc.a12 += gc * d.ix[c] * d.iy[c];
+            acc.a22 += gc * d.iy[c] * d.iy[c];
+            acc.b1 -= gc * d.iz[c] * d.ix[c];
+            acc.b2 -= gc * d.iz[c] * d.iy[c];
+        }
+    }
+    float rx[3], ry[3], ivx[3], ivy[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        ivx[c] = __frcp_rn(d.ixx[c] * d.ixx[c] + d.ixy[c] * d.ixy[c] + dnorm);
+        ivy[c] = __frcp_rn(d.iyy[c] * d.iyy[c] + d.ixy[c] * d.ixy[c] + dnorm);
+        rx[c] = d.ixz[c] + d.ixx[c] * u + d.ixy[c] * v;
+        ry[c] = d.iyz[c] + d.ixy[c] * u + d.iyy[c] * v;
+    }
+    const float t = m * hg * rsqrtf(rx[0] * rx[0] * ivx[0] + ry[0] * ry[0] * ivy[0] + rx[1] * rx[1] * ivx[1] +
+                                    ry[1] * ry[1] * ivy[1] + rx[2] * rx[2] * ivx[2] + ry[2] * ry[2] * ivy[2] + eps_grad);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float gx = t * ivx[c], gy = t * ivy[c];
+        acc.a11 += gx * d.ixx[c] * d.ixx[c] + gy * d.ixy[c] * d.ixy[c];
+        acc.a12 += gx * d.ixx[c] * d.ixy[c] + gy * d.ixy[c] * d.iyy[c];
+        acc.a22 += gy * d.iyy[c] * d.iyy[c] + gx * d.ixy[c] * d.ixy[c];
+        acc.b1 -= gx * d.ixx[c] * d.ixz[c] + gy * d.ixy[c] * d.iyz[c];
+        acc.b2 -= gy * d.iyy[c] * d.iyz[c] + gx * d.ixy[c] * d.ixz[c];
+    }
+}
+
+// ---- multi-frame successive term (variational_aux_mt.cpp:186-363): warped frames s and s+1, effective
+// gradient s*I - (s+1)*I evaluated exactly as written; wc = channel weights; psi' pluggable.
+__device__ __forceinline__ void term_mt_succ(const Derivs &d, float u, float v, float m, float wd, float wg, float s,
+                                             const float wc[3], int dt_norm, const Penalty &pc, const Penalty &pg, Acc &acc) {
+    const float dnorm = 0.1f * 0.1f;
+    const float f = s, f1 = s + 1.0f;
+    if (wd != 0.0f) {
+        float r[3], gx[3], gy[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            r[c] = wc[c] * (d.iz[c] + d.ix[c] * f * u + d.iy[c] * f * v - d.ix[c] * f1 * u - d.iy[c] * f1 * v);
+            gx[c] = f * d.ix[c] - f1 * d.ix[c];
+            gy[c] = f * d.iy[c] - f1 * d.iy[c];
+        }
+        if (!dt_norm) {
+            const float t = m * wd * penalty_deriv_v(pc, r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float g = t * wc[c];
+                acc.a11 += g * gx[c] * gx[c];
+                acc.a12 += g * gx[c] * gy[c];
+                acc.a22 += g * gy[c] * gy[c];
+                acc.b1 -= g * d.iz[c] * gx[c];
+                acc.b2 -= g * d.iz[c] * gy[c];
+            }
+        } else {
+            float inv[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) inv[c] = __frcp_rn(gx[c] * gx[c] + gy[c] * gy[c] + dnorm);
+            const float t = m * wd * penalty_deriv_v(pc, r[0] * r[0] * inv[0] + r[1] * r[1] * inv[1] + r[2] * r[2] * inv[2]);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float g = t * inv[c] * wc[c];
+                acc.a11 += g * gx[c] * gx[c];
+                acc.a12 += g * gx[c] * gy[c];
+                acc.a22 += g * gy[c] * gy[c];
+                acc.b1 -= g * d.iz[c] * gx[c];
+                acc.b2 -= g * d.iz[c] * gy[c];
+            }
+        }
+    }
+    float rx[3], ry[3], gxx[3], gyy[3], gxy[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        rx[c] = wc[c] * (d.ixz[c] + d.ixx[c] * f * u + d.ixy[c] * f * v - d.ixx[c] * f1 * u - d.ixy[c] * f1 * v);
+        ry[c] = wc[c] * (d.iyz[c] + d.ixy[c] * f * u + d.iyy[c] * f * v - d.ixy[c] * f1 * u - d.iyy[c] * f1 * v);
+        gxx[c] = f * d.ixx[c] - f1 * d.ixx[c];
+        gyy[c] = f * d.iyy[c] - f1 * d.iyy[c];
+        gxy[c] = f * d.ixy[c] - f1 * d.ixy[c];
+    }
+    if (!dt_norm) {
+        const float t = m * wg * penalty_deriv_v(pg, rx[0] * rx[0] + ry[0] * ry[0] + rx[1] * rx[1] + ry[1] * ry[1] +
+                                                         rx[2] * rx[2] + ry[2] * ry[2]);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float g = t * wc[c];
+            acc.a11 += g * gxx[c] * gxx[c] + g * gxy[c] * gxy[c];
+            acc.a12 += g * gxx[c] * gxy[c] + g * gxy[c] * gyy[c];
+            acc.a22 += g * gyy[c] * gyy[c] + g * gxy[c] * gxy[c];
+            acc.b1 -= g * d.ixz[c] * gxx[c] + g * d.iyz[c] * gxy[c];
+            acc.b2 -= g * d.iyz[c] * gyy[c] + g * d.ixz[c] * gxy[c];
+        }
+    } else {
+        float ivx[3], ivy[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            ivx[c] = __frcp_rn(gxx[c] * gxx[c] + gxy[c] * gxy[c] + dnorm);
+            ivy[c] = __frcp_rn(gyy[c] * gyy[c] + gxy[c] * gxy[c] + dnorm);
+        }
+        const float t = m * wg * penalty_deriv_v(pg, rx[0] * rx[0] * ivx[0] + ry[0] * ry[0] * ivy[0] + rx[1] * rx[1] * ivx[1] +
+                                                         ry[1] * ry[1] * ivy[1] + rx[2] * rx[2] * ivx[2] + ry[2] * ry[2] * ivy[2]);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float g1 = t * ivx[c] * wc[c], g2 = t * ivy[c] * wc[c];
+            acc.a11 += g1 * gxx[c] * gxx[c] + g2 * gxy[c] * gxy[c];
+            acc.a12 += g1 * gxx[c] * gxy[c] + g2 * gxy[c] * gyy[c];
+            acc.a22 += g2 * gyy[c] * gyy[c] + g1 * gxy[c] * gxy[c];
+            acc.b1 -= g1 * d.ixz[c] * gxx[c] + g2 * d.iyz[c] * gxy[c];
+            acc.b2 -= g2 * d.iyz[c] * gyy[c] + g1 * d.ixz[c] * gxy[c];
+        }
+    }
+}
+
+// ---- multi-frame reference term (variational_aux_mt.cpp:416-592): frame vs. unwarped reference frame with
+// time factor s (sign flipped for s >= 0, :424-425).  The un-normalised branch reproduces the reference
+// literally, including its copy-paste slips (:458-471 channel 3, :527-530 channel 1).
+__device__ __forceinline__ void term_mt_ref(const Derivs &d, float u, float v, float m, float wd, float wg, float s,
+                                            const float wc[3], int dt_norm, const Penalty &pc, const Penalty &pg, Acc &acc) {
+    const float dnorm = 0.1f * 0.1f;
+    const float fsq = s * s;
+    const float f = (s >= 0.0f) ? -s : s;
+    if (wd != 0.0f) {
+        float r[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) r[c] = wc[c] * (d.iz[c] + d.ix[c] * f * u + d.iy[c] * f * v);
+        if (!dt_norm) {
+            float t = m * wd * penalty_deriv_v(pc, r[0] * r[0] / fsq + r[1] * r[1] / fsq + r[2] * r[2] / fsq);
+            t /= fsq;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float g = (c == 0) ? t * wc[0] * f : t * f * wc[c];
+                acc.b1 -= g * d.iz[c] * d.ix[c];
+                acc.b2 -= g * d.iz[c] * d.iy[c];
+                g = (c == 2) ? t * f : g * f; // channel 3 drops the weight and one factor (as written, :469)
+                acc.a11 += g * d.ix[c] * d.ix[c];
+                acc.a12 += g * d.ix[c] * d.iy[c];
+                acc.a22 += g * d.iy[c] * d.iy[c];
+            }
+        } else {
+            float inv[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) inv[c] = __frcp_rn(fsq * d.ix[c] * d.ix[c] + fsq * d.iy[c] * d.iy[c] + dnorm);
+            const float t = m * wd * penalty_deriv_v(pc, r[0] * r[0] * inv[0] + r[1] * r[1] * inv[1] + r[2] * r[2] * inv[2]);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float g = t * inv[c] * wc[c] * f;
+                acc.b1 -= g * d.iz[c] * d.ix[c];
+                acc.b2 -= g * d.iz[c] * d.iy[c];
+                g = g * f;
+                acc.a11 += g * d.ix[c] * d.ix[c];
+                acc.a12 += g * d.ix[c] * d.iy[c];
+                acc.a22 += g * d.iy[c] * d.iy[c];
+            }
+        }
+    }
+    float rx[3], ry[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        rx[c] = wc[c] * (d.ixz[c] + d.ixx[c] * f * u + d.ixy[c] * f * v);
+        ry[c] = wc[c] * (d.iyz[c] + d.ixy[c] * f * u + d.iyy[c] * f * v);
+    }
+    if (!dt_norm) {
+        float t = m * wg * penalty_deriv_v(pg, rx[0] * rx[0] / fsq + ry[0] * ry[0] / fsq + rx[1] * rx[1] / fsq +
+                                                   ry[1] * ry[1] / fsq + rx[2] * rx[2] / fsq + ry[2] * ry[2] / fsq);
+        t /= fsq;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float g = t * wc[c] * f;
+            acc.b1 -= g * d.ixx[c] * d.ixz[c] + g * d.ixy[c] * d.iyz[c];
+            acc.b2 -= g * d.iyy[c] * d.iyz[c] + g * d.ixy[c] * d.ixz[c];
+            g = g * f;
+            if (c == 0) g = g * fsq; // channel 1 carries an extra factorsq (as written, :528-530)
+            acc.a11 += g * d.ixx[c] * d.ixx[c] + g * d.ixy[c] * d.ixy[c];
+            acc.a12 += g * d.ixx[c] * d.ixy[c] + g * d.ixy[c] * d.iyy[c];
+            acc.a22 += g * d.iyy[c] * d.iyy[c] + g * d.ixy[c] * d.ixy[c];
+        }
+    } else {
+        float ivx[3], ivy[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            ivx[c] = __frcp_rn(fsq * d.ixx[c] * d.ixx[c] + fsq * d.ixy[c] * d.ixy[c] + dnorm);
+            ivy[c] = __frcp_rn(fsq * d.iyy[c] * d.iyy[c] + fsq * d.ixy[c] * d.ixy[c] + dnorm);
+        }
+        const float t = m * wg * penalty_deriv_v(pg, rx[0] * rx[0] * ivx[0] + ry[0] * ry[0] * ivy[0] + rx[1] * rx[1] * ivx[1] +
+                                                         ry[1] * ry[1] * ivy[1] + rx[2] * rx[2] * ivx[2] + ry[2] * ry[2] * ivy[2]);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float g1 = t * ivx[c] * wc[c] * f, g2 = t * ivy[c] * wc[c] * f;
+            acc.b1 -= g1 * d.ixx[c] * d.ixz[c] + g2 * d.ixy[c] * d.iyz[c];
+            acc.b2 -= g2 * d.iyy[c] * d.iyz[c] + g1 * d.ixy[c] * d.ixz[c];
+            g1 = g1 * f;
+            g2 = g2 * f;
+            acc.a11 += g1 * d.ixx[c] * d.ixx[c] + g2 * d.ixy[c] * d.ixy[c];
+            acc.a12 += g1 * d.ixx[c] * d.ixy[c] + g2 * d.ixy[c] * d.iyy[c];
+            acc.a22 += g2 * d.iyy[c] * d.iyy[c] + g1 * d.ixy[c] * d.ixy[c];
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_data_term(Geom g, DataTermDesc t, DataCommon cm) {
+    extern __shared__ float smem[];
+    float *sm_m = smem;                       // [3][DT_MH][DT_MW]
+    float *sm_z = sm_m + 3 * DT_MH * DT_MW;   // [3][DT_MH][DT_MW]
+    float *sm_ix = sm_z + 3 * DT_MH * DT_MW;  // [3][DT_XH][DT_XW]
+    float *sm_iy = sm_ix + 3 * DT_XH * DT_XW; // [3][DT_XH][DT_TW]
+
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int x0 = blockIdx.x * DT_TW, y0 = blockIdx.y * DT_TH;
+    const int W1 = g.W - 1, H1 = g.H - 1;
+    const size_t P = g.plane();
+    // tile (with its halo) strictly inside the image: no clamping, no folded vertical taps anywhere
+    const bool interior = (x0 - DT_HALO >= 0) && (x0 + DT_TW + DT_HALO <= g.W) && (y0 - DT_HALO >= 0) &&
+                          (y0 + DT_TH + DT_HALO <= g.H);
+    const float zs = (t.zsign > 0) ? 1.0f : -1.0f;
+
+    // ---- stage 1
+    if (interior) {
+        constexpr int Q = DT_MW / 4; // float4 per row
+        for (int idx = tid; idx < 3 * DT_MH * Q; idx += 256) {
+            const int c = idx / (DT_MH * Q);
+            const int rem = idx - c * (DT_MH * Q);
+            const int ry = rem / Q, q = rem - ry * Q;
+            const size_t o = (size_t)c * P + (size_t)(y0 - DT_HALO + ry) * g.S + (x0 - DT_HALO + 4 * q);
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(t.A + o));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(t.B + o));
+            const int so = (c * DT_MH + ry) * DT_MW + 4 * q;
+            *reinterpret_cast<float4 *>(sm_m + so) =
+                make_float4(0.5f * (b.x + a.x), 0.5f * (b.y + a.y), 0.5f * (b.z + a.z), 0.5f * (b.w + a.w));
+            *reinterpret_cast<float4 *>(sm_z + so) =
+                make_float4(zs * (b.x - a.x), zs * (b.y - a.y), zs * (b.z - a.z), zs * (b.w - a.w));
+        }
+    } else {
+        for (int idx = tid; idx < 3 * DT_MH * DT_MW; idx += 256) {
+            const int c = idx / (DT_MH * DT_MW);
+            const int rem = idx - c * (DT_MH * DT_MW);
+            const int ry = rem / DT_MW, rx = rem - ry * DT_MW;
+            const int gx = clampi(x0 - DT_HALO + rx, 0, W1), gy = clampi(y0 - DT_HALO + ry, 0, H1);
+            const size_t o = (size_t)c * P + (size_t)gy * g.S + gx;
+            const float a = __ldg(t.A + o), b = __ldg(t.B + o);
+            sm_m[(c * DT_MH + ry) * DT_MW + rx] = 0.5f * (b + a);
+            sm_z[(c * DT_MH + ry) * DT_MW + rx] = zs * (b - a);
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 2: Ix on (tile+2)^2 -- columns outside the image take the value at the clamped column
+    // (the reference convolves Ix itself with replicate borders, image.c:475-516) -- and Iy on tile columns.
+    for (int idx = tid; idx < 3 * DT_XH * DT_XW; idx += 256) {
+        const int c = idx / (DT_XH * DT_XW);
+        const int rem = idx - c * (DT_XH * DT_XW);
+        const int ry = rem / DT_XW, rx = rem - ry * DT_XW;
+        const int gx = interior ? (x0 - 2 + rx) : clampi(x0 - 2 + rx, 0, W1);
+        const int mx = gx - (x0 - DT_HALO);
+        const float *row = sm_m + (c * DT_MH + (ry + 2)) * DT_MW;
+        sm_ix[(c * DT_XH + ry) * DT_XW + rx] = hconv5(row[mx - 2], row[mx - 1], row[mx], row[mx + 1], row[mx + 2]);
+    }
+    for (int idx = tid; idx < 3 * DT_XH * DT_TW; idx += 256) {
+        const int c = idx / (DT_XH * DT_TW);
+        const int rem = idx - c * (DT_XH * DT_TW);
+        const int ry = rem / DT_TW, rx = rem - ry * DT_TW;
+        const float *col = sm_m + (c * DT_MH + (ry + 2)) * DT_MW + (rx + DT_HALO);
+        sm_iy[(c * DT_XH + ry) * DT_TW + rx] =
+            interior ? hconv5(col[-2 * DT_MW], col[-DT_MW], col[0], col[DT_MW], col[2 * DT_MW])
+                     : vconv5(col[-2 * DT_MW], col[-DT_MW], col[0], col[DT_MW], col[2 * DT_MW], y0 - 2 + ry, g.H);
+    }
+    __syncthreads();
+
+    // ---- stage 3
+    const int lx = threadIdx.x;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        const int ly = threadIdx.y + 8 * k;
+        const int i = x0 + lx, j = y0 + ly;
+        if (i >= g.S || j >= g.H) continue;
+        const size_t o = (size_t)j * g.S + i;
+        if (i >= g.W) { // padding columns: defined zeros (the reference leaves garbage there)
+            cm.a11[o] = 0.0f; cm.a12[o] = 0.0f; cm.a22[o] = 0.0f; cm.b1[o] = 0.0f; cm.b2[o] = 0.0f;
+            continue;
+        }
+        Derivs d;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float *pix = sm_ix + (c * DT_XH + (ly + 2)) * DT_XW + (lx + 2);
+            const float *piy = sm_iy + (c * DT_XH + (ly + 2)) * DT_TW + lx;
+            const float *pz = sm_z + (c * DT_MH + (ly + DT_HALO)) * DT_MW + (lx + DT_HALO);
+            d.ix[c] = pix[0];
+            d.iy[c] = piy[0];
+            d.iz[c] = pz[0];
+            d.ixx[c] = hconv5(pix[-2], pix[-1], pix[0], pix[1], pix[2]);
+            d.ixz[c] = hconv5(pz[-2], pz[-1], pz[0], pz[1], pz[2]);
+            if (interior) {
+                d.ixy[c] = hconv5(pix[-2 * DT_XW], pix[-DT_XW], pix[0], pix[DT_XW], pix[2 * DT_XW]);
+                d.iyy[c] = hconv5(piy[-2 * DT_TW], piy[-DT_TW], piy[0], piy[DT_TW], piy[2 * DT_TW]);
+                d.iyz[c] = hconv5(pz[-2 * DT_MW], pz[-DT_MW], pz[0], pz[DT_MW], pz[2 * DT_MW]);
+            } else {
+                d.ixy[c] = vconv5(pix[-2 * DT_XW], pix[-DT_XW], pix[0], pix[DT_XW], pix[2 * DT_XW], j, g.H);
+                d.iyy[c] = vconv5(piy[-2 * DT_TW], piy[-DT_TW], piy[0], piy[DT_TW], piy[2 * DT_TW], j, g.H);
+                d.iyz[c] = vconv5(pz[-2 * DT_MW], pz[-DT_MW], pz[0], pz[DT_MW], pz[2 * DT_MW], j, g.H);
+            }
+        }
+        const float u = cm.du ? cm.du[o] : 0.0f, v = cm.dv ? cm.dv[o] : 0.0f;
+        float m = t.mask[o];
+        Acc acc;
+        if (cm.accumulate) {
+            acc.a11 = cm.a11[o]; acc.a12 = cm.a12[o]; acc.a22 = cm.a22[o]; acc.b1 = cm.b1[o]; acc.b2 = cm.b2[o];
+        } else {
+            acc.a11 = acc.a12 = acc.a22 = acc.b1 = acc.b2 = 0.0f;
+        }
+        if (KIND == DK_TWO_FRAME) {
+            term_two_frame(d, u, v, m, t.wd, t.wg, acc);
+        } else {
+            // occlusion / window factor of variational_mt.cpp:293-320, applied on the fly to the raw mask
+            if (t.dir >= 0 && cm.occ) {
+                const float oc = cm.occ[o];
+                const float fac = (1.0f + ((oc == 0.0f) ? 1.0f : 0.0f)) * cm.data_norm;
+                const float sel = (t.dir == 0) ? ((oc >= 0.0f) ? 1.0f : 0.0f) : ((oc <= 0.0f) ? 1.0f : 0.0f);
+                m = (1.0f * (sel / fac)) * m;
+            }
+            float wc[3] = {1.0f, 1.0f, 1.0f};
+            if (cm.chw) {
+                wc[0] = cm.chw[o]; wc[1] = cm.chw[o + P]; wc[2] = cm.chw[o + 2 * P];
+            }
+            if (KIND == DK_MT_SUCC) term_mt_succ(d, u, v, m, t.wd, t.wg, t.s, wc, cm.dt_norm, cm.pc, cm.pg, acc);
+            else term_mt_ref(d, u, v, m, t.wd, t.wg, t.s, wc, cm.dt_norm, cm.pc, cm.pg, acc);
+        }
+        if (cm.fuse_system) {
+            // b += div(psi grad w): gather form of sub_laplacian with its accumulation order (left edge, right
+            // edge, upper edge, lower edge; variational_aux.c:158-179)
+            const float hl = (i > 0) ? cm.ph[o - 1] : 0.0f, hr = cm.ph[o];
+            const float vt = (j > 0) ? cm.pv[o - g.S] : 0.0f, vb = cm.pv[o];
+            const size_t ol = (i > 0) ? o - 1 : o, orr = (i < W1) ? o + 1 : o;
+            const size_t ot = (j > 0) ? o - g.S : o, ob = (j < H1) ? o + g.S : o;
+            {
+                const float wcn = cm.lap_u[o];
+                acc.b1 -= hl * (wcn - cm.lap_u[ol]);
+                acc.b1 += hr * (cm.lap_u[orr] - wcn);
+                acc.b1 -= vt * (wcn - cm.lap_u[ot]);
+                acc.b1 += vb * (cm.lap_u[ob] - wcn);
+            }
+            {
+                const float wcn = cm.lap_v[o];
+                acc.b2 -= hl * (wcn - cm.lap_v[ol]);
+                acc.b2 += hr * (cm.lap_v[orr] - wcn);
+                acc.b2 -= vt * (wcn - cm.lap_v[ot]);
+                acc.b2 += vb * (cm.lap_v[ob] - wcn);
+            }
+            // inverse of [[a11 + sum psi, a12], [a12, a22 + sum psi]] (solver.c:101-106)
+            const float sp = ((hl + hr) + vt) + vb;
+            const float D11 = acc.a22 + sp, D22 = acc.a11 + sp;
+            const float det = D11 * D22 - acc.a12 * acc.a12;
+            acc.a11 = D11 / det;
+            acc.a22 = D22 / det;
+            acc.a12 = acc.a12 / -det;
+        }
+        cm.a11[o] = acc.a11; cm.a12[o] = acc.a12; cm.a22[o] = acc.a22; cm.b1[o] = acc.b1; cm.b2[o] = acc.b2;
+    }
+}
+
+void launch_data_term(cudaStream_t st, Geom g, const DataTermDesc &t, const DataCommon &cm) {
+    dim3 b(32, 8), grid((g.S + DT_TW - 1) / DT_TW, (g.H + DT_TH - 1) / DT_TH);
+    const size_t smem = DT_SMEM_FLOATS * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_data_term<DK_TWO_FRAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_data_term<DK_MT_SUCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_data_term<DK_MT_REF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    switch (t.kind) {
+    case DK_MT_SUCC: k_data_term<DK_MT_SUCC><<<grid, b, smem, st>>>(g, t, cm); break;
+    case DK_MT_REF: k_data_term<DK_MT_REF><<<grid, b, smem, st>>>(g, t, cm); break;
+    default: k_data_term<DK_TWO_FRAME><<<grid, b, smem, st>>>(g, t, cm); break;
+    }
+}
+
+} // namespace sf

@@ -51,14 +51,33 @@ void launch_warp(cudaStream_t st, Geom g, const float *src3, const float *wx, co
 // K3: smoothness diffusivities.  reg.type < 0: two-frame form (variational_aux.c:84), else MT modes 0/1.
 void launch_smoothness(cudaStream_t st, Geom g, const float *uu, const float *vv, const float *w, float alpha_factor,
                        Penalty reg, int mode, float *ph, float *pv);
-// K2 (two-frame): derivatives + data term [+ laplacian + 2x2 block inverse when fuse_system]
-//   fuse_system = false: writes the raw a11,a12,a22,b1,b2 of compute_data_and_match (variational_aux.c:215)
-//   fuse_system = true : also adds div(psi grad lap_u/lap_v) (variational_aux.c:153) and stores the inverted
-//                        blocks exactly as sor_coupled's first sweep would (solver.c:101-106).
-void launch_data_two_frame(cudaStream_t st, Geom g, const float *im1, const float *im2w, const float *mask,
-                           const float *du, const float *dv, float half_delta_over3, float half_gamma_over3,
-                           bool fuse_system, const float *ph, const float *pv, const float *lap_u,
-                           const float *lap_v, float *a11, float *a12, float *a22, float *b1, float *b2);
+// K2: derivatives + robust data term of ONE term, fused (sf_data.cu).  A term pairs two colour images:
+//   m = 0.5*(B + A) (spatial derivatives are taken on it), z = zsign>0 ? B - A : A - B (temporal difference).
+enum DataKind { DK_TWO_FRAME = 0, DK_MT_SUCC = 1, DK_MT_REF = 2 };
+struct DataTermDesc {
+    const float *A, *B; // 3-plane images
+    int zsign;
+    const float *mask;  // raw in-bounds mask of the warp
+    int kind;           // DataKind
+    float wd, wg;       // weights of the colour / gradient constancy parts (already scaled by rho/omega for MT)
+    float s;            // MT time factor
+    int dir;            // MT occlusion handling: 0 past term, 1 future term, -1 none
+};
+struct DataCommon {
+    const float *du, *dv; // current increment (nullable: 0)
+    const float *chw;     // channel weights, 3 planes (nullable: 1)
+    const float *occ;     // occlusion labels -1/0/+1 (nullable)
+    float data_norm;      // sum_s rho_s + omega_s (variational_mt.cpp:223-226)
+    int dt_norm;          // slow_flow_dataterm
+    Penalty pc, pg;       // psi_color, psi_grad
+    bool accumulate;      // add to the existing a11..b2 instead of starting from 0
+    // fuse_system: also add div(psi grad lap_u/lap_v) (variational_aux.c:153) and store the inverted 2x2
+    // blocks exactly as sor_coupled's first sweep would (solver.c:101-106)
+    bool fuse_system;
+    const float *ph, *pv, *lap_u, *lap_v;
+    float *a11, *a12, *a22, *b1, *b2;
+};
+void launch_data_term(cudaStream_t st, Geom g, const DataTermDesc &t, const DataCommon &cm);
 // sub_laplacian as a gather (operator twin)
 void launch_sub_laplacian(cudaStream_t st, Geom g, float *dst, const float *src, const float *ph, const float *pv);
 // in-place inverse of the 2x2 blocks (operator twin of the first SOR sweep's prologue)

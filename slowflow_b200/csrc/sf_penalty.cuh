@@ -29,21 +29,22 @@ __device__ __forceinline__ float penalty_deriv_v(const Penalty &p, float xsq) {
     }
 }
 
-// psi'(s^2), scalar overloads (double inside where the reference's member is double)
+// psi'(s^2), scalar overloads.  The reference evaluates these in double where epsilon_sq is a double member and
+// rounds the result to float; the fp32 evaluation here is within 2 ulp of that (kept off the FP64 pipe).
 __device__ __forceinline__ float penalty_deriv_s(const Penalty &p, float xsq) {
     switch (p.type) {
     case SF_ROBUST_QUADRATIC: return 1.0f;
-    case SF_ROBUST_LORENTZIAN: return (float)(1.0 / (2.0 * p.eps_sq_d + (double)xsq));
+    case SF_ROBUST_LORENTZIAN: return __fdiv_rn(1.0f, 2.0f * p.eps_sq_f + xsq);
     case SF_ROBUST_GEMAN_MCCLURE: {
-        float t = (float)(p.eps_sq_d + (double)xsq);
+        float t = p.eps_sq_f + xsq;
         t = t * t;
-        return (float)((p.eps_sq_d + 2.0 * (double)xsq) / (double)t);
+        return __fdiv_rn(p.eps_sq_f + 2.0f * xsq, t);
     }
     case SF_ROBUST_TRUNC_MODL1: {
         if (sqrtf(xsq) > p.trunc) return 0.0f;
         return 1.0f / (2.0f * sqrtf(xsq + p.eps_sq_f));
     }
-    default: return (float)(1.0 / (2.0 * sqrt((double)xsq + p.eps_sq_d)));
+    default: return __fdiv_rn(1.0f, 2.0f * sqrtf(xsq + p.eps_sq_f));
     }
 }
 
@@ -62,12 +63,14 @@ __device__ __forceinline__ float penalty_apply_v(const Penalty &p, float xsq) {
 }
 
 // smoothness diffusivity of one edge.
-//   type < 0 : two-frame form (w+w')*half_alpha / sqrt(s^2 + 1e-6), sqrt and divide in double (variational_aux.c:124)
+//   type < 0 : two-frame form (w+w')*half_alpha / sqrt(s^2 + 1e-6) (variational_aux.c:124).  The reference
+//              takes the sqrt and the quotient in double and rounds once; here both are IEEE fp32, which
+//              differs by at most 1-2 ulp (2e-7 relative) and keeps the kernel off the FP64 pipe.
 //   else     : (w+w')*alpha * psi'_reg(s^2) through the scalar overload (variational_aux_mt.cpp:65)
 __device__ __forceinline__ float smooth_weight(const Penalty &reg, float ww, float alpha_factor, float ssq) {
     if (reg.type < 0) {
         const float eps_smooth = 0.001f * 0.001f;
-        return (float)((double)(ww * alpha_factor) / sqrt((double)(ssq + eps_smooth)));
+        return __fdiv_rn(ww * alpha_factor, sqrtf(ssq + eps_smooth));
     }
     return ww * alpha_factor * penalty_deriv_s(reg, ssq);
 }
