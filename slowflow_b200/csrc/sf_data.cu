@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(256) k_data_term(Geom g, DataTermDesc t, DataC
             }
             float wc[3] = {1.0f, 1.0f, 1.0f};
             if (cm.chw) {
-                wc[0] = cm.chw[o]; wc[1] = cm.chw[o + P]; wc[2] = cm.chw[o + 2 * P];
+                wc[0] = cm.chw[o]; wc[1] = cm.chw[o + cm.chw_pstride]; wc[2] = cm.chw[o + 2 * cm.chw_pstride];
             }
             if (KIND == DK_MT_SUCC) term_mt_succ(d, u, v, m, t.wd, t.wg, t.s, wc, cm.dt_norm, cm.pc, cm.pg, acc);
             else term_mt_ref(d, u, v, m, t.wd, t.wg, t.s, wc, cm.dt_norm, cm.pc, cm.pg, acc);

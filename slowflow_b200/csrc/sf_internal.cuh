@@ -66,6 +66,7 @@ struct DataTermDesc {
 struct DataCommon {
     const float *du, *dv; // current increment (nullable: 0)
     const float *chw;     // channel weights, 3 planes (nullable: 1)
+    size_t chw_pstride;   // floats between the channel-weight planes (full-resolution plane size)
     const float *occ;     // occlusion labels -1/0/+1 (nullable)
     float data_norm;      // sum_s rho_s + omega_s (variational_mt.cpp:223-226)
     int dt_norm;          // slow_flow_dataterm

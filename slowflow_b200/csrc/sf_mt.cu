@@ -1,8 +1,477 @@
-// sf_mt.cu -- multi-frame driver (Variational_MT).  PLACEHOLDER until the MT kernels land.
+// sf_mt.cu -- the multi-frame, occlusion-aware refinement: device-side restatement of
+//   Variational_MT::variational        epic_flow_extended/variational_mt.cpp:526-784 (pyramid, coarse-to-fine)
+//   Variational_MT::compute_one_level  :169-493 (alternation / outer / inner loops, early exits)
+//   Variational_MT::get_derivatives    :87-166  (here: only the warps; derivatives are fused into K2, sf_data.cu)
+//   Variational_AUX_MT::optimizeOcc    variational_aux_mt.cpp:758-887 (data costs on device, min-cut on host)
+//   normalize                          variational_mt.cpp:17-85
+//   cv::GaussianBlur / cv::resize      as used at variational_mt.cpp:607-611, 672-673, 711-712
+//
+// Frame f of the window (f = 0 .. 2*ref, reference frame at f = ref) is warped once per outer iteration with the
+// integer time factor f - ref (variational_aux_mt.cpp:735); the reference warps most frames twice to identical
+// results.  mask_f is the in-bounds mask of that warp; the reference's mask[s] is mask_s for s < ref and
+// mask_{s+1} for s >= ref (variational_mt.cpp:98-110).  The occlusion / window factors of :293-320 are applied
+// on the fly inside the data-term kernel, so the raw masks survive for optimizeOcc.
 #include "sf_context.cuh"
+
+#include <math.h>
 #include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "sf_gridcut.hpp"
+#include "sf_penalty.cuh"
+#include "sf_stencil.cuh"
+
 using namespace sf;
+
+namespace sf {
+
+// ------------------------------------------------------------------------------------------ small kernels
+// uu = wx + du, vv = wy + dv; block partial sums of |old_du - du|, |old_dv - dv| over valid pixels
+// (variational_mt.cpp:371-399) and, when finalize, of |uu - wx|, |vv - wy| followed by wx = uu, wy = vv
+// (:412-429).  Partials go to part[block*4 + k]; the host adds them in double (deterministic).
+__global__ void __launch_bounds__(256) k_mt_update(Geom g, float *__restrict__ wx, float *__restrict__ wy,
+                                                   const float *__restrict__ du, const float *__restrict__ dv,
+                                                   const float *__restrict__ odu, const float *__restrict__ odv,
+                                                   float *__restrict__ uu, float *__restrict__ vv, int finalize,
+                                                   float *__restrict__ part) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    for (int j = blockIdx.y * 8 + threadIdx.y; j < g.H; j += gridDim.y * 8) {
+        if (i < g.W) {
+            const size_t o = (size_t)j * g.S + i;
+            const float a = du[o], b = dv[o];
+            s0 += fabsf((odu ? odu[o] : 0.0f) - a);
+            s1 += fabsf((odv ? odv[o] : 0.0f) - b);
+            const float x = wx[o], y = wy[o];
+            const float nu = x + a, nv = y + b;
+            if (finalize) {
+                s2 += fabsf(nu - x);
+                s3 += fabsf(nv - y);
+                wx[o] = nu;
+                wy[o] = nv;
+            }
+            if (uu) { uu[o] = nu; vv[o] = nv; }
+        }
+    }
+    __shared__ float red[4][256];
+    const int t = threadIdx.y * 32 + threadIdx.x;
+    red[0][t] = s0; red[1][t] = s1; red[2][t] = s2; red[3][t] = s3;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (t < k) {
+            red[0][t] += red[0][t + k]; red[1][t] += red[1][t + k]; red[2][t] += red[2][t + k]; red[3][t] += red[3][t + k];
+        }
+        __syncthreads();
+    }
+    if (t < 4) part[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 4 + t] = red[t][0];
+}
+
+// per-pixel data costs of the binary occlusion labelling (variational_aux_mt.cpp:786-848).
+// W[f]: warped frame f (W[ref] = reference frame), mk[f]: raw mask of frame f.
+struct OccArgs {
+    const float *W[2 * SF_MT_MAX_REF + 1];
+    const float *mk[2 * SF_MT_MAX_REF + 1];
+    float rho[SF_MT_MAX_REF], omega[SF_MT_MAX_REF];
+    int ref;
+    float delta_over3, gamma_over3, penalty;
+    Penalty pc, pg;
+};
+__global__ void __launch_bounds__(256) k_occ_costs(Geom g, OccArgs a, float *__restrict__ d0, float *__restrict__ d1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.W || j >= g.H) return;
+    const size_t P = g.plane();
+    const size_t o = (size_t)j * g.S + i;
+    const int W1 = g.W - 1, H1 = g.H - 1;
+    float e[2] = {0.f, 0.f}, nrm[2] = {0.f, 0.f};
+    for (int s = 0; s < 2 * a.ref; s++) {
+        const int idx = max(a.ref - s - 1, s - a.ref);
+        const float m = a.mk[s < a.ref ? s : s + 1][o];
+        float term = 0.f;
+        for (int kind = 0; kind < 2; kind++) { // 0: successive pair (s, s+1); 1: frame vs reference
+            const float *A, *B;
+            if (kind == 0) { A = a.W[s]; B = a.W[s + 1]; }
+            else if (s < a.ref) { A = a.W[s]; B = a.W[a.ref]; }
+            else { A = a.W[a.ref]; B = a.W[s + 1]; }
+            float sz = 0.f, sx = 0.f, sy = 0.f;
+            for (int c = 0; c < 3; c++) {
+                const float *pa = A + c * P, *pb = B + c * P;
+                auto Z = [&](int x, int y) { const size_t q = (size_t)clampi(y, 0, H1) * g.S + clampi(x, 0, W1); return pa[q] - pb[q]; };
+                const float z0 = Z(i, j);
+                const float zx = hconv5(Z(i - 2, j), Z(i - 1, j), z0, Z(i + 1, j), Z(i + 2, j));
+                const float zy = vconv5(Z(i, j - 2), Z(i, j - 1), z0, Z(i, j + 1), Z(i, j + 2), j, g.H);
+                sz += z0 * z0;
+                sx += zx * zx;
+                sy += zy * zy;
+            }
+            const float w = (kind == 0) ? a.rho[idx] : a.omega[idx];
+            const float part = w * a.delta_over3 * m * penalty_apply_v(a.pc, sz) + w * a.gamma_over3 * m * penalty_apply_v(a.pg, sx + sy);
+            term += part;
+        }
+        const int l = (s >= a.ref) ? 0 : 1;
+        e[l] += term;
+        nrm[l] += m * (a.rho[idx] + a.rho[idx] + a.omega[idx] + a.omega[idx]);
+    }
+    if (nrm[0] == 0.f) nrm[0] = 1.f;
+    if (nrm[1] == 0.f) nrm[1] = 1.f;
+    d0[o] = 0.01f * e[0] / nrm[0] + a.penalty * 0.0f;
+    d1[o] = 0.01f * e[1] / nrm[1] + a.penalty * 1.0f;
+}
+
+// separable Gaussian (replicate border), symmetric-sum evaluation like cv::GaussianBlur's float path
+struct BlurTaps { int r; float k[17]; }; // k[0] centre, k[i] at distance i
+__global__ void __launch_bounds__(256) k_blur(Geom g, const float *__restrict__ src, float *__restrict__ dst, BlurTaps t,
+                                              int vertical, int planes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.W || j >= g.H) return;
+    const size_t P = g.plane();
+    for (int c = 0; c < planes; c++) {
+        const float *s = src + c * P;
+        float acc = t.k[0] * s[(size_t)j * g.S + i];
+        for (int k = 1; k <= t.r; k++) {
+            const float a = vertical ? s[(size_t)clampi(j - k, 0, g.H - 1) * g.S + i] : s[(size_t)j * g.S + clampi(i - k, 0, g.W - 1)];
+            const float b = vertical ? s[(size_t)clampi(j + k, 0, g.H - 1) * g.S + i] : s[(size_t)j * g.S + clampi(i + k, 0, g.W - 1)];
+            acc += t.k[k] * (a + b);
+        }
+        dst[c * P + (size_t)j * g.S + i] = acc;
+    }
+}
+// bilinear resize with pixel-centre mapping (cv::resize INTER_LINEAR), optional scale of the values
+__global__ void __launch_bounds__(256) k_resize(Geom gs, const float *__restrict__ src, Geom gd, float *__restrict__ dst,
+                                                double scale_x, double scale_y, float mul, int planes) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= gd.S || y >= gd.H) return;
+    const size_t Ps = gs.plane(), Pd = gd.plane();
+    if (x >= gd.W) {
+        for (int c = 0; c < planes; c++) dst[c * Pd + (size_t)y * gd.S + x] = 0.0f;
+        return;
+    }
+    float fx = (float)((x + 0.5) * scale_x - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    if (sx >= gs.W - 1) { sx = gs.W - 1; fx = 0.f; }
+    float fy = (float)((y + 0.5) * scale_y - 0.5);
+    int sy = (int)floorf(fy);
+    fy -= sy;
+    if (sy < 0) { sy = 0; fy = 0.f; }
+    if (sy >= gs.H - 1) { sy = gs.H - 1; fy = 0.f; }
+    const int x1 = min(sx + 1, gs.W - 1), y1 = min(sy + 1, gs.H - 1);
+    const float a1 = fx, a0 = 1.f - fx, b1 = fy, b0 = 1.f - fy;
+    for (int c = 0; c < planes; c++) {
+        const float *s = src + c * Ps;
+        const float r0 = s[(size_t)sy * gs.S + sx] * a0 + s[(size_t)sy * gs.S + x1] * a1;
+        const float r1 = s[(size_t)y1 * gs.S + sx] * a0 + s[(size_t)y1 * gs.S + x1] * a1;
+        float v = r0 * b0 + r1 * b1;
+        if (mul != 1.0f) v *= mul; // image_mul_scalar (image.c:49-57)
+        dst[c * Pd + (size_t)y * gd.S + x] = v;
+    }
+}
+
+// normalize(): per-channel sums in double (variational_mt.cpp:27-46), then (I - avg) / std (:61-69)
+__global__ void __launch_bounds__(256) k_norm_sums(Geom g, const float *__restrict__ im, double *__restrict__ sums /*6*/) {
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    const size_t P = g.plane();
+    for (int j = blockIdx.x; j < g.H; j += gridDim.x)
+        for (int i = threadIdx.x; i < g.W; i += blockDim.x)
+            for (int c = 0; c < 3; c++) {
+                const double v = im[c * P + (size_t)j * g.S + i];
+                s[c] += v;
+                s[3 + c] += v * v;
+            }
+    __shared__ double red[6][256];
+    for (int k = 0; k < 6; k++) red[k][threadIdx.x] = s[k];
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k)
+            for (int q = 0; q < 6; q++) red[q][threadIdx.x] += red[q][threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x < 6) atomicAdd(&sums[threadIdx.x], red[threadIdx.x][0]);
+}
+__global__ void __launch_bounds__(256) k_norm_apply(Geom g, float *__restrict__ im, double a0, double a1, double a2, double s0,
+                                                    double s1, double s2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.W || j >= g.H) return;
+    const size_t P = g.plane(), o = (size_t)j * g.S + i;
+    if (s0 > 0) im[o] = (float)(((double)im[o] - a0) / s0);
+    if (s1 > 0) im[o + P] = (float)(((double)im[o + P] - a1) / s1);
+    if (s2 > 0) im[o + 2 * P] = (float)(((double)im[o + 2 * P] - a2) / s2);
+}
+
+static dim3 grid2d(int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); }
+
+// ------------------------------------------------------------------------------------------ level state
+struct MtLevel {
+    Geom g;
+    std::vector<float *> frames; // F colour images (3 planes each)
+};
+
+struct MtWork {
+    float *pool = nullptr;
+    size_t pool_floats = 0;
+    float *part_dev = nullptr;
+    float *part_host = nullptr; // pinned
+    size_t part_cap = 0;
+    ~MtWork() {
+        if (pool) cudaFree(pool);
+        if (part_dev) cudaFree(part_dev);
+        if (part_host) cudaFreeHost(part_host);
+    }
+};
+
+static BlurTaps make_taps(double sigma) {
+    // cv::getGaussianKernel: n = cvRound(8 sigma + 1) | 1 for CV_32F, exp(-x^2 / 2 sigma^2) normalised
+    BlurTaps t;
+    int n = ((int)lrint(sigma * 8 + 1)) | 1;
+    if (n > 33) n = 33;
+    t.r = n / 2;
+    std::vector<double> v(n);
+    double sum = 0;
+    for (int i = 0; i < n; i++) {
+        const double x = i - (n - 1) * 0.5;
+        v[i] = exp(-0.5 / (sigma * sigma) * x * x);
+        sum += v[i];
+    }
+    for (int k = 0; k <= t.r; k++) t.k[k] = (float)(v[t.r + k] / sum);
+    for (int k = t.r + 1; k < 17; k++) t.k[k] = 0.f;
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------ one level
+struct LevelCtx {
+    sfgpu_ctx *c;
+    const sf_mt_params_t *p;
+    Geom g;
+    int ref;
+    bool one_direction;
+    float alpha, gamma_over3, delta_over3;
+    Penalty pc, pg, preg;
+    std::vector<float *> frames;  // level frames
+    std::vector<float *> warped;  // per frame (warped[ref] == frames[ref])
+    std::vector<float *> masks;   // per frame (masks[ref] unused)
+    float *wx, *wy, *uu, *vv, *odu, *odv, *dpsis, *occ, *d0, *d1;
+    const float *chw;             // channel weights (level-0 planes; Q14: not rescaled per level)
+    size_t chw_pstride;
+    MtWork *work;
+};
+
+static int read_partials(LevelCtx &L, dim3 grid, double out[4]) {
+    const size_t n = (size_t)grid.x * grid.y * 4;
+    SF_CUDA(cudaMemcpyAsync(L.work->part_host, L.work->part_dev, n * sizeof(float), cudaMemcpyDeviceToHost, L.c->stream));
+    SF_CUDA(cudaStreamSynchronize(L.c->stream));
+    out[0] = out[1] = out[2] = out[3] = 0.0;
+    for (size_t b = 0; b < n; b += 4)
+        for (int k = 0; k < 4; k++) out[k] += L.work->part_host[b + k];
+    return SFGPU_OK;
+}
+
+static void warp_all(LevelCtx &L) { // Variational_MT::get_derivatives, warping part (variational_mt.cpp:96-110)
+    const int F = 2 * L.ref + 1;
+    for (int f = (L.one_direction ? L.ref + 1 : 0); f < F; f++) {
+        if (f == L.ref) continue;
+        launch_warp(L.c->stream, L.g, L.frames[f], L.wx, L.wy, f - L.ref, L.warped[f], L.masks[f]);
+        L.c->prof_acc.kernel_launches++;
+    }
+}
+
+static int optimize_occ(LevelCtx &L) { // variational_aux_mt.cpp:758-887
+    const Geom g = L.g;
+    OccArgs a;
+    memset(&a, 0, sizeof(a));
+    const int F = 2 * L.ref + 1;
+    for (int f = 0; f < F; f++) { a.W[f] = L.warped[f]; a.mk[f] = L.masks[f]; }
+    for (int s = 0; s < L.ref; s++) { a.rho[s] = L.p->rho[s]; a.omega[s] = L.p->omega[s]; }
+    a.ref = L.ref;
+    a.delta_over3 = L.delta_over3;
+    a.gamma_over3 = L.gamma_over3;
+    a.penalty = L.p->occlusion_penalty;
+    a.pc = L.pc;
+    a.pg = L.pg;
+    k_occ_costs<<<grid2d(g.W, g.H), dim3(32, 8), 0, L.c->stream>>>(g, a, L.d0, L.d1);
+    L.c->prof_acc.kernel_launches++;
+    const size_t P = g.plane();
+    std::vector<float> h0(P), h1(P), hocc(P, 0.0f);
+    SF_CUDA(cudaMemcpyAsync(h0.data(), L.d0, P * sizeof(float), cudaMemcpyDeviceToHost, L.c->stream));
+    SF_CUDA(cudaMemcpyAsync(h1.data(), L.d1, P * sizeof(float), cudaMemcpyDeviceToHost, L.c->stream));
+    SF_CUDA(cudaStreamSynchronize(L.c->stream));
+    // binary Potts labelling = one min-cut (gco stand-in semantics; int EnergyTermType optional)
+    const bool int_terms = L.p->graphcut_int_terms != 0;
+    auto q = [&](double e) -> int64_t { return (int64_t)llround((int_terms ? (double)(int)e : e) * 16777216.0); };
+    GridCut gc(g.W, g.H);
+    const int64_t pair = q((double)L.p->occlusion_alpha);
+    for (int y = 0; y < g.H; y++)
+        for (int x = 0; x < g.W; x++) {
+            const int pnode = y * g.W + x;
+            const size_t o = (size_t)y * g.S + x;
+            gc.set_terminal(pnode, q((double)h1[o]), q((double)h0[o]));
+            if (x + 1 < g.W) gc.set_edge_right(pnode, pair);
+            if (y + 1 < g.H) gc.set_edge_down(pnode, pair);
+        }
+    gc.maxflow();
+    for (int y = 0; y < g.H; y++)
+        for (int x = 0; x < g.W; x++) hocc[(size_t)y * g.S + x] = (float)(2 * gc.label(y * g.W + x) - 1); // :879
+    SF_CUDA(cudaMemcpyAsync(L.occ, hocc.data(), P * sizeof(float), cudaMemcpyHostToDevice, L.c->stream));
+    SF_CUDA(cudaStreamSynchronize(L.c->stream));
+    L.c->mt_stats.graphcut_calls++;
+    return SFGPU_OK;
+}
+
+static int compute_one_level(LevelCtx &L, float avg_change[2]) { // variational_mt.cpp:169-493
+    sfgpu_ctx *c = L.c;
+    const sf_mt_params_t *p = L.p;
+    const Geom g = L.g;
+    const size_t P = g.plane();
+    cudaStream_t st = c->stream;
+    float *A = c->sor.arena;
+    const int ref = L.ref;
+
+    // occlusion labels: 0, or -1 everywhere ("occluded in the past") when reasoning / one direction (:213-220)
+    launch_fill(st, L.occ, P, (L.one_direction || p->occlusion_reasoning) ? -1.0f : 0.0f);
+    float data_norm = 0.f;
+    for (int s = 0; s < ref; s++) data_norm += p->rho[s] + p->omega[s];
+    launch_dpsis_weight(st, g, L.frames[ref], L.dpsis, 5.0f, p->img_norm_avg, p->img_norm_std, p->hbit ? 65535.0f : 255.0f);
+    c->prof_acc.kernel_launches += 2;
+
+    // ordered term list of :343-361
+    std::vector<DataTermDesc> terms;
+    auto pair_imgs = [&](int q, int kind, const float *&Aimg, const float *&Bimg) {
+        if (kind == DK_MT_SUCC) { Aimg = L.warped[q]; Bimg = L.warped[q + 1]; }
+        else if (q < ref) { Aimg = L.warped[q]; Bimg = L.frames[ref]; }
+        else { Aimg = L.frames[ref]; Bimg = L.warped[q + 1]; }
+    };
+    auto add_term = [&](int q, int kind, float w, float time, int dir) {
+        DataTermDesc t;
+        pair_imgs(q, kind, t.A, t.B);
+        t.zsign = -1; // Iz = im1 - im2 (variational_mt.cpp:127,152)
+        t.mask = L.masks[q < ref ? q : q + 1];
+        t.kind = kind;
+        t.wd = w * L.delta_over3;
+        t.wg = w * L.gamma_over3;
+        t.s = time;
+        t.dir = dir;
+        terms.push_back(t);
+    };
+    for (int s = 0; s < ref; s++) {
+        if (!L.one_direction) {
+            if (p->rho[ref - 1 - s] > 0) add_term(s, DK_MT_SUCC, p->rho[ref - 1 - s], (float)(s - ref), 0);
+            if (p->omega[ref - 1 - s] > 0) add_term(s, DK_MT_REF, p->omega[ref - 1 - s], (float)(s - ref), 0);
+        }
+        if (p->rho[s] > 0) add_term(ref + s, DK_MT_SUCC, p->rho[s], (float)s, 1);
+        if (p->omega[s] > 0) add_term(ref + s, DK_MT_REF, p->omega[s], (float)(s + 1), 1);
+    }
+
+    const dim3 ugrid((g.W + 31) / 32, std::min((g.H + 7) / 8, 64));
+    avg_change[0] = avg_change[1] = 0.f;
+    const double inv_n = 1.0 / ((double)g.H * g.W);
+
+    for (int alter = 0; alter < p->niter_alter; alter++) {
+        warp_all(L); // :266
+        if (alter > 0 && p->occlusion_reasoning && !L.one_direction) { // :269-272
+            int rc = optimize_occ(L);
+            if (rc != SFGPU_OK) return rc;
+        }
+        for (int outer = 0; outer < p->niter_outer; outer++) {
+            if (outer > 0) warp_all(L); // :289-290
+            c->mt_stats.outer_iterations++;
+            int cur = 0;
+            bool broke_inner = false;
+            int inner_done = 0;
+            for (int inner = 0; inner < p->niter_inner; inner++) {
+                const bool first = (inner == 0);
+                const float *uu = first ? L.wx : L.uu, *vv = first ? L.wy : L.vv; // uu == wx at the start of an outer iteration
+                float *du_cur = A + (size_t)(cur ? SP_DUB : SP_DUA) * P, *dv_cur = A + (size_t)(cur ? SP_DVB : SP_DVA) * P;
+                if (!first) { // :329-330 old_du = du
+                    SF_CUDA(cudaMemcpyAsync(L.odu, du_cur, P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                    SF_CUDA(cudaMemcpyAsync(L.odv, dv_cur, P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                }
+                launch_smoothness(st, g, uu, vv, L.dpsis, L.alpha, L.preg, p->smoothing, A + SP_PH * P, A + SP_PV * P); // :333
+                c->prof_acc.kernel_launches++;
+                DataCommon cm{};
+                cm.du = first ? nullptr : du_cur;
+                cm.dv = first ? nullptr : dv_cur;
+                cm.chw = L.chw;
+                cm.chw_pstride = L.chw_pstride;
+                cm.occ = L.occ;
+                cm.data_norm = data_norm;
+                cm.dt_norm = p->dataterm;
+                cm.pc = L.pc;
+                cm.pg = L.pg;
+                cm.ph = A + SP_PH * P; cm.pv = A + SP_PV * P;
+                cm.lap_u = uu; cm.lap_v = vv; // MT passes uu, vv to sub_laplacian (:364-365)
+                cm.a11 = A + SP_A11 * P; cm.a12 = A + SP_A12 * P; cm.a22 = A + SP_A22 * P;
+                cm.b1 = A + SP_B1 * P; cm.b2 = A + SP_B2 * P;
+                cudaEvent_t ev;
+                c->prof_begin(1, ev);
+                if (terms.empty()) { // no active data term: the system is the smoothness term alone
+                    launch_fill(st, cm.a11, 5 * P, 0.0f);
+                    launch_sub_laplacian(st, g, cm.b1, uu, cm.ph, cm.pv);
+                    launch_sub_laplacian(st, g, cm.b2, vv, cm.ph, cm.pv);
+                    launch_invert_blocks(st, g, cm.a11, cm.a12, cm.a22, cm.ph, cm.pv);
+                    c->prof_acc.kernel_launches += 4;
+                }
+                for (size_t k = 0; k < terms.size(); k++) {
+                    cm.accumulate = (k > 0);
+                    cm.fuse_system = (k + 1 == terms.size());
+                    launch_data_term(st, g, terms[k], cm);
+                    c->prof_acc.kernel_launches++;
+                    c->prof_acc.data_launches++;
+                    c->prof_acc.data_pixels += (long long)g.W * g.H;
+                }
+                c->prof_end(1, ev);
+                int rc = run_sor(c, p->niter_solver, p->sor_omega, &cur, first); // :368
+                if (rc != SFGPU_OK) return rc;
+                c->mt_stats.sor_calls++;
+                inner_done = inner + 1;
+                const float *ndu = A + (size_t)(cur ? SP_DUB : SP_DUA) * P, *ndv = A + (size_t)(cur ? SP_DVB : SP_DVA) * P;
+                const bool last_possible = (inner == p->niter_inner - 1);
+                // :371-399; when this is certainly the last inner iteration the outer update (:412-429) is fused in
+                k_mt_update<<<ugrid, dim3(32, 8), 0, st>>>(g, L.wx, L.wy, ndu, ndv, first ? nullptr : L.odu, first ? nullptr : L.odv,
+                                                           last_possible ? nullptr : L.uu, last_possible ? nullptr : L.vv,
+                                                           last_possible ? 1 : 0, L.work->part_dev);
+                c->prof_acc.kernel_launches++;
+                double sums[4];
+                rc = read_partials(L, ugrid, sums);
+                if (rc != SFGPU_OK) return rc;
+                const float ch_du = (float)(sums[0] * inv_n), ch_dv = (float)(sums[1] * inv_n);
+                if (last_possible) {
+                    avg_change[0] = (float)(sums[2] * inv_n);
+                    avg_change[1] = (float)(sums[3] * inv_n);
+                } else if (std::max(ch_du, ch_dv) < p->thres_inner) { // :407-408
+                    broke_inner = true;
+                    break;
+                }
+            }
+            if (p->niter_inner <= 0) avg_change[0] = avg_change[1] = 0.f;
+            else if (broke_inner || inner_done < p->niter_inner) {
+                // left the inner loop early: uu, vv hold wx + du; do the outer update now (:412-429)
+                const float *ndu = A + (size_t)(cur ? SP_DUB : SP_DUA) * P, *ndv = A + (size_t)(cur ? SP_DVB : SP_DVA) * P;
+                k_mt_update<<<ugrid, dim3(32, 8), 0, st>>>(g, L.wx, L.wy, ndu, ndv, nullptr, nullptr, nullptr, nullptr, 1,
+                                                           L.work->part_dev);
+                c->prof_acc.kernel_launches++;
+                double sums[4];
+                int rc = read_partials(L, ugrid, sums);
+                if (rc != SFGPU_OK) return rc;
+                avg_change[0] = (float)(sums[2] * inv_n);
+                avg_change[1] = (float)(sums[3] * inv_n);
+            }
+            if (std::max(avg_change[0], avg_change[1]) < p->thres_outer) break; // :436-437
+        }
+    }
+    SF_CUDA(cudaGetLastError());
+    return SFGPU_OK;
+}
+
+} // namespace sf
+
+// ------------------------------------------------------------------------------------------ ABI
 extern "C" {
+
 void sf_mt_params_default(sf_mt_params_t *p) { // slow_flow.cpp:64-128 (setDefault)
     if (!p) return;
     memset(p, 0, sizeof(*p));
@@ -20,18 +489,223 @@ void sf_mt_params_default(sf_mt_params_t *p) { // slow_flow.cpp:64-128 (setDefau
     p->graphcut_int_terms = 0; p->hbit = 1;
     for (int k = 0; k < 3; k++) { p->img_norm_avg[k] = 0.0f; p->img_norm_std[k] = 1.0f; }
 }
-int sfgpu_variational_mt(sfgpu_ctx *, image_t *, image_t *, const color_image_t *const *, const sf_mt_params_t *,
-                         const color_image_t *, image_t *, float *) {
-    set_error("sfgpu_variational_mt: not built yet");
-    return SFGPU_ERR_UNSUPPORTED;
-}
-int sfgpu_normalize(sfgpu_ctx *, color_image_t *const *, int, sf_mt_params_t *) {
-    set_error("sfgpu_normalize: not built yet");
-    return SFGPU_ERR_UNSUPPORTED;
-}
+
 int sfgpu_get_mt_stats(sfgpu_ctx *c, sfgpu_mt_stats_t *out) {
     if (!c || !out) return SFGPU_ERR_ARG;
     *out = c->mt_stats;
     return SFGPU_OK;
 }
+
+int sfgpu_normalize(sfgpu_ctx *c, color_image_t *const *seq, int F, sf_mt_params_t *params) {
+    if (!c || !seq || F < 1 || !params) {
+        set_error("sfgpu_normalize: bad argument");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const Geom g{seq[0]->width, seq[0]->height, seq[0]->stride};
+    const size_t P = g.plane();
+    float *dev = nullptr;
+    double *dsum = nullptr;
+    SF_CUDA(cudaMalloc(&dev, (size_t)F * 3 * P * sizeof(float)));
+    if (!cuda_ok(cudaMalloc(&dsum, (size_t)F * 6 * sizeof(double)), "cudaMalloc")) { cudaFree(dev); return SFGPU_ERR_CUDA; }
+    cudaMemsetAsync(dsum, 0, (size_t)F * 6 * sizeof(double), st);
+    for (int f = 0; f < F; f++) {
+        cudaMemcpyAsync(dev + (size_t)f * 3 * P, seq[f]->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st);
+        k_norm_sums<<<std::min(g.H, 592), 256, 0, st>>>(g, dev + (size_t)f * 3 * P, dsum + f * 6);
+    }
+    std::vector<double> hs((size_t)F * 6);
+    cudaMemcpyAsync(hs.data(), dsum, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (!cuda_ok(cudaStreamSynchronize(st), "normalize sums")) { cudaFree(dev); cudaFree(dsum); return SFGPU_ERR_CUDA; }
+    double avg[3] = {0, 0, 0}, sd[3] = {0, 0, 0};
+    const double n = (double)g.H * g.W;
+    for (int f = 0; f < F; f++)
+        for (int k = 0; k < 3; k++) { avg[k] += hs[f * 6 + k] / n; sd[k] += hs[f * 6 + 3 + k] / n; }
+    for (int k = 0; k < 3; k++) {
+        avg[k] /= F;
+        sd[k] = sqrt((sd[k] / F) - avg[k] * avg[k]) / 255.0f; // :48-51
+    }
+    for (int f = 0; f < F; f++) {
+        k_norm_apply<<<grid2d(g.W, g.H), dim3(32, 8), 0, st>>>(g, dev + (size_t)f * 3 * P, avg[0], avg[1], avg[2], sd[0], sd[1], sd[2]);
+        cudaMemcpyAsync(seq[f]->c1, dev + (size_t)f * 3 * P, 3 * P * sizeof(float), cudaMemcpyDeviceToHost, st);
+    }
+    const bool ok = cuda_ok(cudaStreamSynchronize(st), "normalize apply");
+    cudaFree(dev);
+    cudaFree(dsum);
+    if (!ok) return SFGPU_ERR_CUDA;
+    for (int k = 0; k < 3; k++) {
+        // the reference publishes the values through a stringstream with 6 significant digits (:72-84)
+        char buf[64];
+        snprintf(buf, sizeof(buf), "%.6g", avg[k]);
+        params->img_norm_avg[k] = (float)atof(buf);
+        snprintf(buf, sizeof(buf), "%.6g", sd[k]);
+        params->img_norm_std[k] = (float)atof(buf);
+    }
+    c->prof_acc.kernel_launches += 2 * F;
+    return SFGPU_OK;
 }
+
+int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_image_t *const *im,
+                         const sf_mt_params_t *p, const color_image_t *channel_w, image_t *occlusions_out,
+                         float avg_change_out[2]) {
+    if (!c || !wx || !wy || !im || !p) {
+        set_error("sfgpu_variational_mt: null argument");
+        return SFGPU_ERR_ARG;
+    }
+    const int ref = p->S - 1, F = 2 * ref + 1;
+    if (ref < 1 || ref > SF_MT_MAX_REF) {
+        set_error("sfgpu_variational_mt: slow_flow_S out of range");
+        return SFGPU_ERR_ARG;
+    }
+    if (p->smoothing < 0 || p->smoothing > 1) {
+        set_error("sfgpu_variational_mt: slow_flow_smoothing >= 2 is not supported (reference bug, SURVEY Q6)");
+        return SFGPU_ERR_UNSUPPORTED;
+    }
+    if (p->layers < 1 || (p->layers > 1 && !(p->p_scale > 0.f && p->p_scale < 1.f))) {
+        set_error("sfgpu_variational_mt: bad pyramid parameters");
+        return SFGPU_ERR_ARG;
+    }
+    const int W0 = wx->width, H0 = wx->height;
+    for (int f = 0; f < F; f++)
+        if (!im[f] || !im[f]->c1 || im[f]->width != W0 || im[f]->height != H0 || im[f]->stride != wx->stride) {
+            set_error("sfgpu_variational_mt: frames and flow must share one geometry");
+            return SFGPU_ERR_ARG;
+        }
+    if (wy->width != W0 || wy->height != H0 || wx->stride != ((W0 + 3) / 4) * 4) {
+        set_error("sfgpu_variational_mt: bad flow planes");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    memset(&c->mt_stats, 0, sizeof(c->mt_stats));
+    if (avg_change_out) avg_change_out[0] = avg_change_out[1] = 0.f;
+
+    // ---- pyramid geometry (variational_mt.cpp:583-652): floor((float)w * p_scale); a level is dropped when
+    // the NEXT one would be <= order+1 = floor(3 sigma)+2 pixels (:647-651)
+    const float sigma = 1.0f / sqrtf(2.0f * p->p_scale);
+    const int order = (int)floorf(3.0f * sigma) + 1;
+    std::vector<Geom> geoms;
+    int L = p->layers;
+    for (int l = 0; l < L; l++) {
+        if (l == 0) geoms.push_back(make_geom(W0, H0));
+        else geoms.push_back(make_geom((int)floorf((float)geoms[l - 1].W * p->p_scale), (int)floorf((float)geoms[l - 1].H * p->p_scale)));
+        if (floorf((float)geoms[l].W * p->p_scale) <= order + 1 || floorf((float)geoms[l].H * p->p_scale) <= order + 1) {
+            L = l;
+            break;
+        }
+    }
+    if (L == 0) return SFGPU_OK; // the reference computes nothing in this case
+    geoms.resize(L);
+    c->mt_stats.levels = L;
+
+    // ---- device memory: frames of all levels + per-level work planes sized for level 0
+    const Geom g0 = geoms[0];
+    const size_t P0 = g0.plane();
+    size_t frame_floats = 0;
+    for (int l = 0; l < L; l++) frame_floats += (size_t)F * 3 * geoms[l].plane();
+    const size_t work_planes = (size_t)(F - 1) * 3 + (F - 1) + 2 /*wx wy*/ + 2 /*wx,wy of next level*/ + 2 /*uu vv*/ + 2 /*odu odv*/ + 1 /*dpsis*/ +
+                               1 /*occ*/ + 2 /*d0 d1*/ + 3 /*blur tmp*/ + (channel_w ? 3 : 0);
+    MtWork work;
+    work.pool_floats = frame_floats + work_planes * P0;
+    SF_CUDA(cudaMalloc(&work.pool, work.pool_floats * sizeof(float)));
+    work.part_cap = (size_t)((g0.W + 31) / 32) * 64 * 4;
+    SF_CUDA(cudaMalloc(&work.part_dev, work.part_cap * sizeof(float)));
+    SF_CUDA(cudaMallocHost(&work.part_host, work.part_cap * sizeof(float)));
+    float *ptr = work.pool;
+    std::vector<MtLevel> levels(L);
+    for (int l = 0; l < L; l++) {
+        levels[l].g = geoms[l];
+        for (int f = 0; f < F; f++) { levels[l].frames.push_back(ptr); ptr += 3 * geoms[l].plane(); }
+    }
+    auto take = [&](size_t planes) { float *r = ptr; ptr += planes * P0; return r; };
+    std::vector<float *> warped(F, nullptr), masks(F, nullptr);
+    for (int f = 0; f < F; f++)
+        if (f != ref) { warped[f] = take(3); masks[f] = take(1); }
+    float *wxa = take(1), *wya = take(1), *wxb = take(1), *wyb = take(1);
+    float *uu = take(1), *vv = take(1), *odu = take(1), *odv = take(1), *dpsis = take(1), *occ = take(1), *d0 = take(1), *d1 = take(1);
+    float *blur_tmp = take(3);
+    float *chw = channel_w ? take(3) : nullptr;
+
+    // ---- upload
+    for (int f = 0; f < F; f++)
+        SF_CUDA(cudaMemcpyAsync(levels[0].frames[f], im[f]->c1, 3 * P0 * sizeof(float), cudaMemcpyHostToDevice, st));
+    SF_CUDA(cudaMemcpyAsync(wxa, wx->data, P0 * sizeof(float), cudaMemcpyHostToDevice, st));
+    SF_CUDA(cudaMemcpyAsync(wya, wy->data, P0 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (chw) SF_CUDA(cudaMemcpyAsync(chw, channel_w->c1, 3 * P0 * sizeof(float), cudaMemcpyHostToDevice, st));
+
+    // ---- pyramid: GaussianBlur(sigma) + resize per frame and level (:604-614)
+    if (L > 1) {
+        const BlurTaps taps = make_taps((double)sigma);
+        for (int l = 1; l < L; l++) {
+            const Geom gs = geoms[l - 1], gd = geoms[l];
+            for (int f = 0; f < F; f++) {
+                k_blur<<<grid2d(gs.W, gs.H), dim3(32, 8), 0, st>>>(gs, levels[l - 1].frames[f], blur_tmp, taps, 0, 3);
+                // vertical pass writes into the (not yet used) warp scratch of frame slot 0/1
+                float *tmp2 = warped[ref == 0 ? 1 : 0];
+                k_blur<<<grid2d(gs.W, gs.H), dim3(32, 8), 0, st>>>(gs, blur_tmp, tmp2, taps, 1, 3);
+                k_resize<<<grid2d(gd.S, gd.H), dim3(32, 8), 0, st>>>(gs, tmp2, gd, levels[l].frames[f], (double)gs.W / gd.W,
+                                                                     (double)gs.H / gd.H, 1.0f, 3);
+                c->prof_acc.kernel_launches += 3;
+            }
+        }
+    }
+
+    // ---- coarse-to-fine (:662-762)
+    float *cur_x = wxa, *cur_y = wya, *oth_x = wxb, *oth_y = wyb;
+    Geom cur_g = g0;
+    if (L > 1) {
+        const Geom gd = geoms[L - 1];
+        const float fx = (1.0f * gd.W) / g0.W, fy = (1.0f * gd.H) / g0.H;
+        k_resize<<<grid2d(gd.S, gd.H), dim3(32, 8), 0, st>>>(g0, cur_x, gd, oth_x, (double)g0.W / gd.W, (double)g0.H / gd.H, fx, 1);
+        k_resize<<<grid2d(gd.S, gd.H), dim3(32, 8), 0, st>>>(g0, cur_y, gd, oth_y, (double)g0.W / gd.W, (double)g0.H / gd.H, fy, 1);
+        std::swap(cur_x, oth_x);
+        std::swap(cur_y, oth_y);
+        cur_g = gd;
+        c->prof_acc.kernel_launches += 2;
+    }
+    float avg_change[2] = {0.f, 0.f};
+    int rc = c->ensure_workspace(g0); // size the level workspace once for the finest level
+    for (int l = L - 1; l >= 0 && rc == SFGPU_OK; l--) {
+        const Geom g = geoms[l];
+        if (l < L - 1) { // up-sample the flow of level l+1 and scale the vectors (:687-722)
+            const float fx = (1.0f * g.W) / cur_g.W, fy = (1.0f * g.H) / cur_g.H;
+            k_resize<<<grid2d(g.S, g.H), dim3(32, 8), 0, st>>>(cur_g, cur_x, g, oth_x, (double)cur_g.W / g.W, (double)cur_g.H / g.H, fx, 1);
+            k_resize<<<grid2d(g.S, g.H), dim3(32, 8), 0, st>>>(cur_g, cur_y, g, oth_y, (double)cur_g.W / g.W, (double)cur_g.H / g.H, fy, 1);
+            std::swap(cur_x, oth_x);
+            std::swap(cur_y, oth_y);
+            cur_g = g;
+            c->prof_acc.kernel_launches += 2;
+        }
+        rc = c->ensure_workspace(g);
+        if (rc != SFGPU_OK) break;
+        LevelCtx Lc;
+        Lc.c = c; Lc.p = p; Lc.g = g; Lc.ref = ref;
+        Lc.one_direction = p->one_direction != 0;
+        Lc.alpha = p->alpha;
+        Lc.gamma_over3 = p->gamma / 3.0f;
+        Lc.delta_over3 = p->delta / 3.0f;
+        Lc.pc = make_penalty(p->robust_color, p->robust_color_eps, p->robust_color_truncation);
+        Lc.pg = (p->robust_grad >= 0) ? make_penalty(p->robust_grad, p->robust_grad_eps, p->robust_grad_truncation) : Lc.pc; // Q8
+        Lc.preg = make_penalty(p->robust_reg, p->robust_reg_eps, p->robust_reg_truncation);
+        Lc.frames = levels[l].frames;
+        Lc.warped = warped;
+        Lc.warped[ref] = levels[l].frames[ref];
+        Lc.masks = masks;
+        Lc.wx = cur_x; Lc.wy = cur_y; Lc.uu = uu; Lc.vv = vv; Lc.odu = odu; Lc.odv = odv;
+        Lc.dpsis = dpsis; Lc.occ = occ; Lc.d0 = d0; Lc.d1 = d1;
+        Lc.chw = chw; Lc.chw_pstride = P0;
+        Lc.work = &work;
+        rc = compute_one_level(Lc, avg_change);
+    }
+    if (rc != SFGPU_OK) return rc;
+
+    SF_CUDA(cudaMemcpyAsync(wx->data, cur_x, P0 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaMemcpyAsync(wy->data, cur_y, P0 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (occlusions_out && occlusions_out->data && occlusions_out->width == W0 && occlusions_out->height == H0)
+        SF_CUDA(cudaMemcpyAsync(occlusions_out->data, occ, P0 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaStreamSynchronize(st));
+    if (avg_change_out) { avg_change_out[0] = avg_change[0]; avg_change_out[1] = avg_change[1]; }
+    return SFGPU_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,125 @@
+"""Multi-frame (Variational_MT) parity on the GPU.
+
+Checker: the reference's own unmodified driver (oracle/_ref: variational_mt.cpp + variational_aux_mt.cpp built
+against header shims) in its CPU red-black mode, and the C++ restatement oracle/sf_oracle_mt.cpp where
+built.  Gate: mean endpoint difference <= 0.01 px, max <= 0.1 px, >= 8 px from the borders.  Non-convex penalties
+are gated at eps = 0.5 (full iteration count) and over a short horizon at small eps (the reference iteration is
+chaotic there, SURVEY 8d 'stability')."""
+import numpy as np
+import pytest
+
+import mt_helpers as mh
+from slowflow_b200.metrics import epe
+from oracle.pyoracle import SOR_LEX, SOR_REDBLACK
+
+pytestmark = pytest.mark.gpu
+MEAN_TOL, MAX_TOL = 0.01, 0.1
+
+
+def check(g, r, what, occ_frac_tol=0.002):
+    mean, mx = epe(g["wx"].array, g["wy"].array, r["wx"].array, r["wy"].array, border=8)
+    occ_diff = float((g["occ"].array != r["occ"].array).mean())
+    print("%s: GPU vs CPU-RB mean %.3e max %.3e | occlusion labels differing %.4f%% | outer its gpu %d | avg change gpu %s cpu %s"
+          % (what, mean, mx, 100 * occ_diff, g["stats"].outer_iterations, g["avg"], r["avg"]))
+    assert mean <= MEAN_TOL and mx <= MAX_TOL, what
+    assert occ_diff <= occ_frac_tol, what
+    return mean, mx
+
+
+def test_normalize_matches_reference(ctx, reference):
+    ims, wx, wy = mh.window(200, 120, 3)
+    p = mh.params(3)
+    r = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, mh.params(3, niter_alter=1, niter_outer=1), SOR_REDBLACK)
+    g_ims = [f.copy() for f in ims]
+    ctx.normalize(g_ims, p)
+    for k in range(3):
+        assert abs(p.img_norm_avg[k] - r["params"].img_norm_avg[k]) <= 1e-4 * abs(r["params"].img_norm_avg[k])
+        assert abs(p.img_norm_std[k] - r["params"].img_norm_std[k]) <= 1e-5
+    for a, b in zip(g_ims, r["frames"]):
+        assert np.abs(a.array - b.array).max() < 5e-4  # values ~ +-500 after normalisation
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("modl1_default_occ", dict(niter_alter=2, niter_outer=4)),
+    ("modl1_no_occ", dict(niter_alter=2, niter_outer=4, occlusion_reasoning=0)),
+    ("geman_mcclure_eps0.5", dict(niter_alter=2, niter_outer=4, robust_color=4, robust_color_eps=0.5)),
+    ("lorentzian_eps0.5_no_occ", dict(niter_alter=2, niter_outer=4, robust_color=2, robust_color_eps=0.5, occlusion_reasoning=0)),
+    ("trunc_modl1_short", dict(niter_alter=1, niter_outer=2, robust_color=3, robust_color_eps=0.001, robust_color_truncation=5.0)),
+    # quadratic data penalty: the reference iteration is unstable at the motion discontinuity (its own lex vs
+    # red-black orderings differ by > 10 px after 3 outer iterations) -> gate the arithmetic over one iteration
+    ("quadratic_reg_lorentzian_short", dict(niter_alter=1, niter_outer=1, robust_color=0, robust_reg=2, robust_reg_eps=0.5)),
+    ("geman_mcclure_small_eps_short_horizon", dict(niter_alter=1, niter_outer=2, robust_color=4, robust_color_eps=0.001)),
+    ("forward_only", dict(niter_alter=1, niter_outer=3, one_direction=1)),
+    # slow_flow_dataterm = 0: the reference-term branch carries copy-paste slips (reproduced literally)
+    # that make the reference itself blow up after 2 outer iterations -> one iteration with them, two without
+    ("unnormalised_dataterm_short", dict(niter_alter=1, niter_outer=1, dataterm=0)),
+    ("unnormalised_dataterm_succ_only", dict(niter_alter=1, niter_outer=2, dataterm=0, omega=[0, 0])),
+    ("smoothing0_inner2", dict(niter_alter=1, niter_outer=2, niter_inner=2, smoothing=0)),
+    ("separate_grad_penalty", dict(niter_alter=1, niter_outer=2, robust_grad=2, robust_grad_eps=0.5)),
+])
+def test_mt_parity_small(ctx, reference, name, kw):
+    ims, wx, wy = mh.window(256, 160, 3)
+    p = mh.params(3, **kw)
+    r = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, p, SOR_REDBLACK)
+    g = mh.run_gpu(ctx, ims, wx, wy, p)
+    check(g, r, name)
+
+
+def test_mt_parity_S2_and_S4(ctx, reference):
+    for S in (2, 4):
+        ims, wx, wy = mh.window(192, 128, S)
+        p = mh.params(S, niter_alter=2, niter_outer=3, rho=[1, 1, 1], omega=[0, 2, 1])
+        r = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, p, SOR_REDBLACK)
+        g = mh.run_gpu(ctx, ims, wx, wy, p)
+        check(g, r, "S=%d" % S)
+
+
+def test_mt_pyramid_three_layers_zero_init(ctx, reference):
+    """Config 4 in small: layers = 3, p_scale = 0.9, zero initial flow, odd level widths (stride != width)."""
+    ims, wx, wy = mh.window(250, 163, 3, zero_flow=True)
+    p = mh.params(3, layers=3, niter_alter=1, niter_outer=3)
+    r = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, p, SOR_REDBLACK)
+    g = mh.run_gpu(ctx, ims, wx, wy, p)
+    assert g["stats"].levels == 3
+    check(g, r, "pyramid 3 layers")
+
+
+def test_mt_config3_1280x1024(ctx, reference):
+    """BASELINE config 3 geometry (1280x1024, S=3, 5 frames) with Geman-McClure eps=0.5, occlusion reasoning on,
+    bounded to 2 alternations x 3 outer iterations so the CPU reference finishes in about a minute."""
+    ims, wx, wy = mh.window(1280, 1024, 3)
+    p = mh.params(3, niter_alter=2, niter_outer=3, robust_color=4, robust_color_eps=0.5)
+    r = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, p, SOR_REDBLACK)
+    g = mh.run_gpu(ctx, ims, wx, wy, p)
+    check(g, r, "config 3 (bounded)")
+    lex = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, p, SOR_LEX)
+    print("reported: GPU vs CPU-lex mean %.3e max %.3e" % epe(g["wx"].array, g["wy"].array, lex["wx"].array, lex["wy"].array))
+
+
+def test_mt_early_exit_iteration_counts(ctx, reference):
+    """Convergent setting: the early exits (variational_mt.cpp:407,436) must fire on the GPU as on the CPU."""
+    ims, wx, wy = mh.window(160, 120, 2)
+    p = mh.params(2, niter_alter=3, niter_outer=10, thres_outer=5e-3, occlusion_reasoning=0)
+    r = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, p, SOR_REDBLACK)
+    g = mh.run_gpu(ctx, ims, wx, wy, p)
+    check(g, r, "early exit")
+    assert g["stats"].outer_iterations < 30
+    assert abs(g["avg"][0] - r["avg"][0]) < 1e-4 and abs(g["avg"][1] - r["avg"][1]) < 1e-4
+
+
+def test_mt_class_shape(ctx):
+    """Variational_MT mirror (variational_mt.h:23-71): setChannelWeights / getOcclusions / one_direction."""
+    from slowflow_b200 import ColorImage, Variational_MT
+    ims, wx, wy = mh.window(128, 96, 2)
+    p = mh.params(2, niter_alter=1, niter_outer=2)
+    solver = Variational_MT(ctx)
+    w = ColorImage(128, 96)
+    w.buf[:] = 1.0
+    solver.setChannelWeights(w)
+    a, b = wx.copy(), wy.copy()
+    r1 = solver.variational(a, b, ims, p)
+    plain = Variational_MT(ctx)
+    c, d = wx.copy(), wy.copy()
+    r2 = plain.variational(c, d, ims, p)
+    assert np.array_equal(a.array, c.array) and r1 == r2  # all-ones weights == no weights
+    assert solver.getOcclusions() is not None and set(np.unique(solver.getOcclusions().array)) <= {-1.0, 0.0, 1.0}
