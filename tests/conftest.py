@@ -40,3 +40,13 @@ def ctx(built):
     c = Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture(scope="session")
+def mt_checker(built):
+    """(library, symbol prefix) of the CPU checker for the multi-frame path: the reference's own unmodified driver
+    (oracle/_ref) where it was built, else the bit-identical restatement (oracle/sf_oracle_mt.cpp)."""
+    from oracle.pyoracle import Oracle, Reference, have_reference
+    if have_reference():
+        return Reference().lib, "sf_ref_"
+    return Oracle().lib, "sfo_"

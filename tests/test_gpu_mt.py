@@ -26,10 +26,10 @@ def check(g, r, what, occ_frac_tol=0.002):
     return mean, mx
 
 
-def test_normalize_matches_reference(ctx, reference):
+def test_normalize_matches_reference(ctx, mt_checker):
     ims, wx, wy = mh.window(200, 120, 3)
     p = mh.params(3)
-    r = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, mh.params(3, niter_alter=1, niter_outer=1), SOR_REDBLACK)
+    r = mh.run_cpu(*mt_checker, ims, wx, wy, mh.params(3, niter_alter=1, niter_outer=1), SOR_REDBLACK)
     g_ims = [f.copy() for f in ims]
     ctx.normalize(g_ims, p)
     for k in range(3):
@@ -57,50 +57,50 @@ def test_normalize_matches_reference(ctx, reference):
     ("smoothing0_inner2", dict(niter_alter=1, niter_outer=2, niter_inner=2, smoothing=0)),
     ("separate_grad_penalty", dict(niter_alter=1, niter_outer=2, robust_grad=2, robust_grad_eps=0.5)),
 ])
-def test_mt_parity_small(ctx, reference, name, kw):
+def test_mt_parity_small(ctx, mt_checker, name, kw):
     ims, wx, wy = mh.window(256, 160, 3)
     p = mh.params(3, **kw)
-    r = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, p, SOR_REDBLACK)
+    r = mh.run_cpu(*mt_checker, ims, wx, wy, p, SOR_REDBLACK)
     g = mh.run_gpu(ctx, ims, wx, wy, p)
     check(g, r, name)
 
 
-def test_mt_parity_S2_and_S4(ctx, reference):
+def test_mt_parity_S2_and_S4(ctx, mt_checker):
     for S in (2, 4):
         ims, wx, wy = mh.window(192, 128, S)
         p = mh.params(S, niter_alter=2, niter_outer=3, rho=[1, 1, 1], omega=[0, 2, 1])
-        r = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, p, SOR_REDBLACK)
+        r = mh.run_cpu(*mt_checker, ims, wx, wy, p, SOR_REDBLACK)
         g = mh.run_gpu(ctx, ims, wx, wy, p)
         check(g, r, "S=%d" % S)
 
 
-def test_mt_pyramid_three_layers_zero_init(ctx, reference):
+def test_mt_pyramid_three_layers_zero_init(ctx, mt_checker):
     """Config 4 in small: layers = 3, p_scale = 0.9, zero initial flow, odd level widths (stride != width)."""
     ims, wx, wy = mh.window(250, 163, 3, zero_flow=True)
     p = mh.params(3, layers=3, niter_alter=1, niter_outer=3)
-    r = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, p, SOR_REDBLACK)
+    r = mh.run_cpu(*mt_checker, ims, wx, wy, p, SOR_REDBLACK)
     g = mh.run_gpu(ctx, ims, wx, wy, p)
     assert g["stats"].levels == 3
     check(g, r, "pyramid 3 layers")
 
 
-def test_mt_config3_1280x1024(ctx, reference):
+def test_mt_config3_1280x1024(ctx, mt_checker):
     """BASELINE config 3 geometry (1280x1024, S=3, 5 frames) with Geman-McClure eps=0.5, occlusion reasoning on,
     bounded to 2 alternations x 3 outer iterations so the CPU reference finishes in about a minute."""
     ims, wx, wy = mh.window(1280, 1024, 3)
     p = mh.params(3, niter_alter=2, niter_outer=3, robust_color=4, robust_color_eps=0.5)
-    r = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, p, SOR_REDBLACK)
+    r = mh.run_cpu(*mt_checker, ims, wx, wy, p, SOR_REDBLACK)
     g = mh.run_gpu(ctx, ims, wx, wy, p)
     check(g, r, "config 3 (bounded)")
-    lex = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, p, SOR_LEX)
+    lex = mh.run_cpu(*mt_checker, ims, wx, wy, p, SOR_LEX)
     print("reported: GPU vs CPU-lex mean %.3e max %.3e" % epe(g["wx"].array, g["wy"].array, lex["wx"].array, lex["wy"].array))
 
 
-def test_mt_early_exit_iteration_counts(ctx, reference):
+def test_mt_early_exit_iteration_counts(ctx, mt_checker):
     """Convergent setting: the early exits (variational_mt.cpp:407,436) must fire on the GPU as on the CPU."""
     ims, wx, wy = mh.window(160, 120, 2)
     p = mh.params(2, niter_alter=3, niter_outer=10, thres_outer=5e-3, occlusion_reasoning=0)
-    r = mh.run_cpu(reference.lib, "sf_ref_", ims, wx, wy, p, SOR_REDBLACK)
+    r = mh.run_cpu(*mt_checker, ims, wx, wy, p, SOR_REDBLACK)
     g = mh.run_gpu(ctx, ims, wx, wy, p)
     check(g, r, "early exit")
     assert g["stats"].outer_iterations < 30
@@ -123,3 +123,12 @@ def test_mt_class_shape(ctx):
     r2 = plain.variational(c, d, ims, p)
     assert np.array_equal(a.array, c.array) and r1 == r2  # all-ones weights == no weights
     assert solver.getOcclusions() is not None and set(np.unique(solver.getOcclusions().array)) <= {-1.0, 0.0, 1.0}
+
+
+def test_mt_gpu_vs_restatement(ctx, oracle):
+    """Same gate against the C++ restatement (the checker that always travels as source)."""
+    ims, wx, wy = mh.window(200, 144, 3)
+    p = mh.params(3, niter_alter=2, niter_outer=3, robust_color=2, robust_color_eps=0.5)
+    r = mh.run_cpu(oracle.lib, "sfo_", ims, wx, wy, p, SOR_REDBLACK)
+    g = mh.run_gpu(ctx, ims, wx, wy, p)
+    check(g, r, "vs restatement")
