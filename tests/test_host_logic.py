@@ -59,3 +59,17 @@ def test_two_rank_gloo_sharding_and_max_time():
                           os.path.join(ROOT, "tests", "_gloo_worker.py")], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "rank=0:ok:0:4" in out.stdout and "rank=1:ok:4:7" in out.stdout
+
+
+def test_cpp_call_sites_compile_against_the_shim(built, tmp_path):
+    """include/variational_mt_gpu.hpp keeps the shape of the reference class: the slow_flow.cpp / adaptiveFR.cpp call
+    sites compile, link against libslowflow_gpu.so and the ParameterList -> POD mapping runs (no GPU needed)."""
+    from slowflow_b200.api import library_path
+    exe = str(tmp_path / "callsite")
+    lib_dir = os.path.dirname(library_path())
+    cmd = ["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp_shim_callsite.cpp"),
+           "-o", exe, "-L", lib_dir, "-lslowflow_gpu", "-Wl,-rpath," + lib_dir]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
