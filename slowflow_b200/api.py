@@ -17,7 +17,8 @@ _LIB = None
 
 
 def library_path():
-    return os.path.join(_HERE, "lib", "libslowflow_gpu.so")
+    """Path of the CUDA library; SLOWFLOW_GPU_LIB overrides it (used to A/B kernel build variants)."""
+    return os.environ.get("SLOWFLOW_GPU_LIB") or os.path.join(_HERE, "lib", "libslowflow_gpu.so")
 
 
 class Profile(C.Structure):

@@ -95,7 +95,9 @@ enum SorPlane { SP_A11 = 0, SP_A12, SP_A22, SP_B1, SP_B2, SP_PH, SP_PV, SP_DUA, 
 struct SorPlan {
     Geom g{0, 0, 0};
     float *arena = nullptr; // SP_COUNT planes
-    CUtensorMap tmap;       // 3-D (x, y, plane) view of the arena
+    CUtensorMap tmap;       // 3-D (x, y, plane) views of the arena: box = a warp's strip of the 7 coefficient planes,
+    CUtensorMap tmap_iter;  //   ... of a du,dv plane pair,
+    CUtensorMap tmap_row;   //   ... one row of one plane
     bool tmap_valid = false;
     int num_sms = 0;
 };

@@ -20,6 +20,10 @@
 // Variant 1 (validation, tiny images): one launch per half sweep straight from global memory.
 #include "sf_internal.cuh"
 
+#ifndef SF_SOR_NW
+#define SF_SOR_NW 8
+#endif
+
 namespace sf {
 
 // ------------------------------------------------------------------------------------------ variant 1
@@ -46,15 +50,34 @@ __global__ void __launch_bounds__(256) k_sor_half_global(Geom g, const float *__
 }
 
 // ------------------------------------------------------------------------------------------ variant 0
-constexpr int SOR_R = 4;                    // rows per warp (must be even: row parity == r parity)
-constexpr int SOR_NW = 16;                  // warps per CTA
+#ifndef SF_SOR_R
+#define SF_SOR_R 8
+#endif
+#ifndef SF_SOR_SKIP
+#define SF_SOR_SKIP 0
+#endif
+#ifndef SF_SOR_SYNC
+#define SF_SOR_SYNC 0 // 0: one CTA barrier per half sweep; 1: neighbour-to-neighbour publication counters
+#endif
+constexpr int SOR_R = SF_SOR_R;             // rows per lane (4 or 8); rows p and p + SOR_R/2 form one packed-fp32 pair
+constexpr int SOR_HP = SOR_R / 2;           // row pairs per lane and column
+constexpr int SOR_NW = SF_SOR_NW;           // warps per CTA
 constexpr int SOR_TW = 64;                  // tile width: 2 pixels per lane
 constexpr int SOR_TH = SOR_R * SOR_NW;      // tile height
 constexpr int SOR_STAGED = 9;               // a11' a12' a22' b1 b2 psi_h psi_v du dv
-constexpr int SOR_PLANE_FLOATS = SOR_TW * SOR_TH;
-constexpr int SOR_STAGE_BYTES = SOR_STAGED * SOR_PLANE_FLOATS * 4;
-constexpr int SOR_EXCH_BYTES = 2 /*buffers*/ * 2 /*top,bottom*/ * SOR_NW * 32 * 8;
-constexpr int SOR_SMEM_BYTES = SOR_STAGE_BYTES + SOR_EXCH_BYTES + 64 + 1024 /*alignment slack*/;
+constexpr int SOR_BLOCK_BYTES = (SOR_STAGED * SOR_R + 1) * SOR_TW * 4; // one warp's staging block (+ the psi_v row above)
+constexpr int SOR_EXCH_BYTES = 2 /*slots*/ * 2 /*top,bottom*/ * SOR_NW * 32 * 8;
+constexpr int SOR_SMEM_BYTES = SOR_NW * SOR_BLOCK_BYTES + SOR_EXCH_BYTES + 128 /*pub*/ + SOR_NW * 8 /*mbarriers*/ + 1024 /*alignment slack*/;
+
+#ifdef SF_SOR_CLOCKS
+__device__ unsigned long long g_sor_clk[8]; // tma-wait, load, sweeps, barrier-wait, store, -, -, tiles (warp 0 of every CTA)
+#define SOR_CLK(var) const long long var = clock64()
+#ifndef SF_SOR_CLOCK_THREAD
+#define SF_SOR_CLOCK_THREAD 0
+#endif
+#else
+#define SOR_CLK(var)
+#endif
 
 struct SorTiledArgs {
     Geom g;
@@ -64,6 +87,7 @@ struct SorTiledArgs {
     int tiles_x, tiles_y;
     float omega;
     int zero_init;  // initial iterate is 0: du,dv are not loaded
+    float one;      // 1.0f, opaque to the compiler (see ldp in k_sor_tiled)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,6 +97,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -101,177 +128,333 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 
+// Per-lane register tile: pixel columns {2l, 2l+1} of the warp's 8 rows.  Every quantity is held as a
+// packed pair (row p, row p+4) of one column in ONE 64-bit register so that the whole relaxation runs on
+// packed-fp32 FFMA2 (fma.rn.f32x2, sm_100): both rows of a pair have the same colour in a given column.
+// (64-bit inline-asm operands make ptxas keep the pairs in aligned register pairs; with float2 values it
+// re-assembled every operand with MOVs.)
+typedef unsigned long long p64;
+__device__ __forceinline__ p64 pk(float lo, float hi) {
+    p64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ p64 pkv(float lo, float hi) {
+    p64 r;
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo_of(p64 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float hi_of(p64 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+__device__ __forceinline__ p64 fma2(p64 a, p64 b, p64 c) {
+    p64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ p64 shfl_up2(p64 v) {
+    return pk(__shfl_up_sync(0xffffffffu, lo_of(v), 1), __shfl_up_sync(0xffffffffu, hi_of(v), 1));
+}
+__device__ __forceinline__ p64 shfl_down2(p64 v) {
+    return pk(__shfl_down_sync(0xffffffffu, lo_of(v), 1), __shfl_down_sync(0xffffffffu, hi_of(v), 1));
+}
+
 struct SorRegs {
-    float a11[SOR_R][2], a12[SOR_R][2], a22[SOR_R][2], b1[SOR_R][2], b2[SOR_R][2];
-    float phl[SOR_R], phm[SOR_R], phr[SOR_R]; // psi_h at columns 2l-1, 2l, 2l+1
-    float pv[SOR_R][2], pvt[2];               // psi_v of the rows, and of the row above the strip
-    float du[SOR_R][2], dv[SOR_R][2];
+    p64 na11[2][SOR_HP], na12[2][SOR_HP], na22[2][SOR_HP]; // NEGATED inverse blocks, [column][pair]
+    p64 b1[2][SOR_HP], b2[2][SOR_HP];
+    p64 du[2][SOR_HP], dv[2][SOR_HP];
+    p64 phl[SOR_HP], phm[SOR_HP], phr[SOR_HP]; // psi_h at columns 2l-1, 2l, 2l+1
+    p64 pv[2][SOR_HP];                         // psi_v of the rows
+    p64 pvt[2];                                // psi_v of (row -1, row 3): the rows above pair 0
 };
 
-template <int C>
-__device__ __forceinline__ void sor_half_sweep(SorRegs &q, const float2 up, const float2 dn, const float omega) {
-    constexpr unsigned FULL = 0xffffffffu;
-#pragma unroll
-    for (int r = 0; r < SOR_R; r++) {
-        const int e = (C + r) & 1; // column of the pair that has colour C in this row (tile origin is even/even)
-        float ul, vl, ur, vr, psl, psr;
-        if (e == 0) {
-            ul = __shfl_up_sync(FULL, q.du[r][1], 1);
-            vl = __shfl_up_sync(FULL, q.dv[r][1], 1);
-            ur = q.du[r][1];
-            vr = q.dv[r][1];
-            psl = q.phl[r];
-            psr = q.phm[r];
-        } else {
-            ul = q.du[r][0];
-            vl = q.dv[r][0];
-            ur = __shfl_down_sync(FULL, q.du[r][0], 1);
-            vr = __shfl_down_sync(FULL, q.dv[r][0], 1);
-            psl = q.phm[r];
-            psr = q.phr[r];
-        }
-        float ut, vt, pst, ub, vb;
-        if (r == 0) { ut = up.x; vt = up.y; pst = q.pvt[e]; }
-        else { ut = q.du[r - 1][e]; vt = q.dv[r - 1][e]; pst = q.pv[r - 1][e]; }
-        if (r == SOR_R - 1) { ub = dn.x; vb = dn.y; }
-        else { ub = q.du[r + 1][e]; vb = q.dv[r + 1][e]; }
-        const float psb = q.pv[r][e];
-        // B = b + sum_nb psi_nb*d_nb as one FMA chain (bottom, top, right, left); the reference's
-        // left-to-right sum differs from this only in rounding (tests gate at 2e-4 after 30 sweeps)
-        const float B1 = fmaf(psl, ul, fmaf(psr, ur, fmaf(pst, ut, fmaf(psb, ub, q.b1[r][e]))));
-        const float B2 = fmaf(psl, vl, fmaf(psr, vr, fmaf(pst, vt, fmaf(psb, vb, q.b2[r][e]))));
-        const float ru = fmaf(q.a11[r][e], B1, fmaf(q.a12[r][e], B2, -q.du[r][e]));
-        const float rv = fmaf(q.a12[r][e], B1, fmaf(q.a22[r][e], B2, -q.dv[r][e]));
-        q.du[r][e] = fmaf(omega, ru, q.du[r][e]);
-        q.dv[r][e] = fmaf(omega, rv, q.dv[r][e]);
+// Relax the colour-C pixels of row pair P (rows P and P+4).  up = (du,dv) of the row above the warp's strip
+// (used by P == 0), dn = of the row below (P == SOR_HP-1).  Same FMA chain per component as the scalar form
+//   B = psl*dl + (psr*dr + (pst*dt + (psb*db + b)));  d += omega*(a1*B1 + (a2*B2 - d))
+// written with negated a and omega (fma(-a,B,d) = -fma(a,B,-d) exactly), which needs no negation op:
+//   n = (-a1)*B1 + ((-a2)*B2 + d);  d += (-omega)*n
+template <int C, int P>
+__device__ __forceinline__ void sor_relax_pair(SorRegs &q, const float2 up, const float2 dn, const p64 nomega2) {
+    constexpr int e = (C + P) & 1; // column of the lane's pair that has colour C in these rows (tile origin is even/even)
+    p64 ul, vl, ur, vr, psl, psr;
+    if (e == 0) {
+        ul = shfl_up2(q.du[1][P]);
+        vl = shfl_up2(q.dv[1][P]);
+        ur = q.du[1][P];
+        vr = q.dv[1][P];
+        psl = q.phl[P];
+        psr = q.phm[P];
+    } else {
+        ul = q.du[0][P];
+        vl = q.dv[0][P];
+        ur = shfl_down2(q.du[0][P]);
+        vr = shfl_down2(q.dv[0][P]);
+        psl = q.phm[P];
+        psr = q.phr[P];
+    }
+    p64 ut, vt, pst, ub, vb;
+    if (P == 0) {
+        ut = pk(up.x, lo_of(q.du[e][SOR_HP - 1]));
+        vt = pk(up.y, lo_of(q.dv[e][SOR_HP - 1]));
+        pst = q.pvt[e];
+    } else {
+        ut = q.du[e][P - 1];
+        vt = q.dv[e][P - 1];
+        pst = q.pv[e][P - 1];
+    }
+    if (P == SOR_HP - 1) {
+        ub = pk(hi_of(q.du[e][0]), dn.x);
+        vb = pk(hi_of(q.dv[e][0]), dn.y);
+    } else {
+        ub = q.du[e][P + 1];
+        vb = q.dv[e][P + 1];
+    }
+    const p64 psb = q.pv[e][P];
+    const p64 B1 = fma2(psl, ul, fma2(psr, ur, fma2(pst, ut, fma2(psb, ub, q.b1[e][P]))));
+    const p64 B2 = fma2(psl, vl, fma2(psr, vr, fma2(pst, vt, fma2(psb, vb, q.b2[e][P]))));
+    const p64 nu = fma2(q.na11[e][P], B1, fma2(q.na12[e][P], B2, q.du[e][P]));
+    const p64 nv = fma2(q.na12[e][P], B1, fma2(q.na22[e][P], B2, q.dv[e][P]));
+    q.du[e][P] = fma2(nomega2, nu, q.du[e][P]);
+    q.dv[e][P] = fma2(nomega2, nv, q.dv[e][P]);
+}
+
+// relax pairs [P, PEND) of colour C; with SF_SOR_SKIP a pair whose deeper row has depth <= k is skipped
+// (half sweep k only has to be right for pixels at depth >= k+1 from the tile edge; warp-uniform)
+template <int C, int P, int PEND>
+__device__ __forceinline__ void sor_relax_range(SorRegs &q, const float2 up, const float2 dn, const p64 nomega2, int k,
+                                                const int (&pdepth)[SOR_HP]) {
+    if constexpr (P < PEND) {
+        if (!SF_SOR_SKIP || k < pdepth[P]) sor_relax_pair<C, P>(q, up, dn, nomega2);
+        sor_relax_range<C, P + 1, PEND>(q, up, dn, nomega2, k, pdepth);
     }
 }
 
-__global__ void __launch_bounds__(SOR_NW * 32, 1) k_sor_tiled(const __grid_constant__ CUtensorMap tmap, SorTiledArgs a) {
+// shared-memory flag helpers for the warp-to-warp hand-shake
+__device__ __forceinline__ void st_release_shared(int *p, int v) {
+    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_shared(const int *p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(SOR_NW * 32, 1)
+k_sor_tiled(const __grid_constant__ CUtensorMap tmap_coef, const __grid_constant__ CUtensorMap tmap_iter,
+            const __grid_constant__ CUtensorMap tmap_row, SorTiledArgs a) {
     extern __shared__ unsigned char smem_raw[];
     // TMA destinations need 128-byte alignment; round the dynamic base up to 1 KB
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float *stage = reinterpret_cast<float *>(base);
-    float2 *exch = reinterpret_cast<float2 *>(base + SOR_STAGE_BYTES);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(base + SOR_STAGE_BYTES + SOR_EXCH_BYTES);
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // this warp's private staging block: [9 planes][SOR_R rows][64] + psi_v of the row above the strip [64]
+    float *stage = reinterpret_cast<float *>(base + warp * SOR_BLOCK_BYTES);
+    float2 *exch = reinterpret_cast<float2 *>(base + SOR_NW * SOR_BLOCK_BYTES);
+    int *pub = reinterpret_cast<int *>(base + SOR_NW * SOR_BLOCK_BYTES + SOR_EXCH_BYTES); // publications per warp
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(pub + 32) + warp;                        // TMA completion, per warp
+
     // halo: 2T pixels per side.  TMA needs the box origin 16-byte aligned along x, so the horizontal
     // halo is rounded up to a multiple of 4 floats (tile origins stay multiples of 4).
     const int hy = 2 * a.T, hx = (2 * a.T + 3) & ~3;
     const int IW = SOR_TW - 2 * hx, IH = SOR_TH - 2 * hy;
     const int ntiles = a.tiles_x * a.tiles_y;
-    const int nload = a.zero_init ? 7 : 9;
+    const int nhalf = 2 * a.T;
 
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
         mbar_init(mbar, 1);
+        pub[warp] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
+    // one warp = one strip of SOR_R rows: its coefficient planes (one 3-D box over the 7 consecutive arena planes),
+    // its iterate (one box over the du,dv plane pair) and the psi_v row above it arrive in the warp's own block
     auto issue = [&](int tile) {
         const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-        const int x0 = tx * IW - hx, y0 = ty * IH - hy;
-        mbar_expect_tx(mbar, (uint32_t)(nload * SOR_PLANE_FLOATS * 4));
-#pragma unroll 1
-        for (int pl = 0; pl < nload; pl++) {
-            const int z = (pl < 7) ? pl : (pl == 7 ? a.in_du_plane : a.in_dv_plane);
-            tma_load_3d(stage + pl * SOR_PLANE_FLOATS, &tmap, mbar, x0, y0, z);
-        }
+        const int x0 = tx * IW - hx, y0 = ty * IH - hy + warp * SOR_R;
+        mbar_expect_tx(mbar, (uint32_t)(((a.zero_init ? 7 : 9) * SOR_R + 1) * SOR_TW * 4));
+        tma_load_3d(stage, &tmap_coef, mbar, x0, y0, 0);
+        if (!a.zero_init) tma_load_3d(stage + 7 * SOR_R * SOR_TW, &tmap_iter, mbar, x0, y0, a.in_du_plane);
+        tma_load_3d(stage + 9 * SOR_R * SOR_TW, &tmap_row, mbar, x0, y0 - 1, SP_PV);
     };
 
     int tile = blockIdx.x;
     uint32_t phase = 0;
-    if (threadIdx.x == 0 && tile < ntiles) issue(tile);
+    int npub = 0; // publications of this warp so far (= of every warp it is in step with)
+    if (lane == 0 && tile < ntiles) issue(tile);
 
-    // exchange area: exch[((buf*2 + side)*SOR_NW + warp)*32 + lane], side 0 = top row, 1 = bottom row
-    auto ex = [&](int buf, int side, int w) -> float2 * { return exch + ((buf * 2 + side) * SOR_NW + w) * 32 + lane; };
+    // Boundary rows travel between neighbouring warps through a 2-slot ring per warp and side:
+    // exch[((slot*2 + side)*SOR_NW + warp)*32 + lane], side 0 = top row, 1 = bottom row.  There is NO CTA-wide
+    // barrier in the tile loop: a warp only waits for the publication counters of its two neighbours, so the
+    // warps of a CTA drift apart by up to one half sweep per warp and the load / relax / store phases of
+    // different warps (and the TMA pulls of the next tile) overlap.
+    auto ex = [&](int slot, int side, int w) -> float2 * { return exch + ((slot * 2 + side) * SOR_NW + w) * 32 + lane; };
+#ifdef SF_SOR_CLOCKS
+    long long wait_clk = 0;
+#endif
+    auto publish = [&](float2 top, float2 bottom) {
+        *ex(npub & 1, 0, warp) = top;
+        *ex(npub & 1, 1, warp) = bottom;
+        npub++;
+#if SF_SOR_SYNC == 1
+        __syncwarp();
+        if (lane == 0) st_release_shared(pub + warp, npub);
+#endif
+    };
+    // wait until both neighbours have made publication number `need` (1-based)
+    auto wait_neighbours = [&](int need) {
+        SOR_CLK(w0);
+#if SF_SOR_SYNC == 0
+        (void)need;
+        __syncthreads();
+#else
+        uint32_t spins = 0;
+        if (warp > 0)
+            while (ld_acquire_shared(pub + warp - 1) < need)
+                if (++spins > (1u << 24)) __trap();
+        if (warp < SOR_NW - 1)
+            while (ld_acquire_shared(pub + warp + 1) < need)
+                if (++spins > (1u << 24)) __trap();
+        __syncwarp();
+#endif
+#ifdef SF_SOR_CLOCKS
+        wait_clk += clock64() - w0;
+#endif
+    };
+    const p64 nomega2 = pk(-a.omega, -a.omega);
+    const float2 zero2 = make_float2(0.0f, 0.0f);
+    // Half sweep k only has to be right for pixels at depth >= k+1 from the tile edge, so (with SF_SOR_SKIP) a
+    // row pair whose deeper row has depth <= k is skipped in half sweep k (warp-uniform).
+    int pdepth[SOR_HP];
+#pragma unroll
+    for (int p = 0; p < SOR_HP; p++) {
+        const int r0 = warp * SOR_R + p, r1 = r0 + SOR_HP;
+        const int d0 = r0 < SOR_TH - 1 - r0 ? r0 : SOR_TH - 1 - r0, d1 = r1 < SOR_TH - 1 - r1 ? r1 : SOR_TH - 1 - r1;
+        pdepth[p] = d0 > d1 ? d0 : d1;
+    }
 
     while (tile < ntiles) {
         const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
         const int x0 = tx * IW - hx, y0 = ty * IH - hy;
 
+        SOR_CLK(c0);
         mbar_wait(mbar, phase);
         phase ^= 1u;
+        SOR_CLK(c1);
 
         // ---- shared -> registers
         SorRegs q;
+        {
+            // LDS.64 delivers the two COLUMNS of one row; a pair is (row p, row p+4) of ONE column, so every two
+            // loads are transposed into two pairs.  Each pair is then passed through one FFMA2 (x*1 + 0, or x*(-1) + 0
+            // for the negated blocks) so that it is DEFINED by a 64-bit instruction: ptxas then keeps it in an
+            // aligned register pair instead of re-assembling it from two scalars with MOVs in front of every use.
+            const p64 one2 = pk(a.one, a.one), mone2 = pk(-a.one, -a.one), z2 = pk(0.0f, 0.0f);
+            const float2 *row0 = reinterpret_cast<const float2 *>(stage) + lane;
+            auto ld2 = [&](int plane, int p, p64 &c0, p64 &c1, p64 scale) {
+                const float2 lo = row0[((plane * SOR_R + p) * SOR_TW) / 2];
+                const float2 hi = row0[((plane * SOR_R + p + SOR_HP) * SOR_TW) / 2];
+                c0 = fma2(pk(lo.x, hi.x), scale, z2);
+                c1 = fma2(pk(lo.y, hi.y), scale, z2);
+            };
 #pragma unroll
-        for (int r = 0; r < SOR_R; r++) {
-            const int tr = warp * SOR_R + r;
-            const float2 *row = reinterpret_cast<const float2 *>(stage + tr * SOR_TW) + lane;
-            float2 v;
-            v = row[(SP_A11 * SOR_PLANE_FLOATS) / 2]; q.a11[r][0] = v.x; q.a11[r][1] = v.y;
-            v = row[(SP_A12 * SOR_PLANE_FLOATS) / 2]; q.a12[r][0] = v.x; q.a12[r][1] = v.y;
-            v = row[(SP_A22 * SOR_PLANE_FLOATS) / 2]; q.a22[r][0] = v.x; q.a22[r][1] = v.y;
-            v = row[(SP_B1 * SOR_PLANE_FLOATS) / 2];  q.b1[r][0] = v.x;  q.b1[r][1] = v.y;
-            v = row[(SP_B2 * SOR_PLANE_FLOATS) / 2];  q.b2[r][0] = v.x;  q.b2[r][1] = v.y;
-            v = row[(SP_PH * SOR_PLANE_FLOATS) / 2];  q.phm[r] = v.x;    q.phr[r] = v.y;
-            const float left = __shfl_up_sync(0xffffffffu, v.y, 1);
-            q.phl[r] = (lane == 0) ? 0.0f : left; // column -1 of the tile is never needed for a valid pixel
-            v = row[(SP_PV * SOR_PLANE_FLOATS) / 2];  q.pv[r][0] = v.x;  q.pv[r][1] = v.y;
-            if (a.zero_init) {
-                q.du[r][0] = q.du[r][1] = q.dv[r][0] = q.dv[r][1] = 0.0f;
-            } else {
-                v = row[(7 * SOR_PLANE_FLOATS) / 2]; q.du[r][0] = v.x; q.du[r][1] = v.y;
-                v = row[(8 * SOR_PLANE_FLOATS) / 2]; q.dv[r][0] = v.x; q.dv[r][1] = v.y;
+            for (int p = 0; p < SOR_HP; p++) {
+                ld2(SP_A11, p, q.na11[0][p], q.na11[1][p], mone2);
+                ld2(SP_A12, p, q.na12[0][p], q.na12[1][p], mone2);
+                ld2(SP_A22, p, q.na22[0][p], q.na22[1][p], mone2);
+                ld2(SP_B1, p, q.b1[0][p], q.b1[1][p], one2);
+                ld2(SP_B2, p, q.b2[0][p], q.b2[1][p], one2);
+                ld2(SP_PV, p, q.pv[0][p], q.pv[1][p], one2);
+                ld2(SP_PH, p, q.phm[p], q.phr[p], one2);
+                const p64 left = shfl_up2(q.phr[p]);
+                q.phl[p] = (lane == 0) ? z2 : left; // column -1 of the tile is never needed for a valid pixel
+                if (a.zero_init) {
+                    q.du[0][p] = q.du[1][p] = q.dv[0][p] = q.dv[1][p] = z2;
+                } else {
+                    ld2(7, p, q.du[0][p], q.du[1][p], one2);
+                    ld2(8, p, q.dv[0][p], q.dv[1][p], one2);
+                }
             }
+            // psi_v of the row above the strip (zero-filled by the TMA unit above the image)
+            const float2 above = row0[(9 * SOR_R * SOR_TW) / 2];
+            q.pvt[0] = fma2(pk(above.x, lo_of(q.pv[0][SOR_HP - 1])), one2, z2);
+            q.pvt[1] = fma2(pk(above.y, lo_of(q.pv[1][SOR_HP - 1])), one2, z2);
         }
-        if (warp > 0) {
-            const float2 v = (reinterpret_cast<const float2 *>(stage + SP_PV * SOR_PLANE_FLOATS + (warp * SOR_R - 1) * SOR_TW))[lane];
-            q.pvt[0] = v.x; q.pvt[1] = v.y;
-        } else {
-            q.pvt[0] = q.pvt[1] = 0.0f; // row -1 of the tile: halo or outside the image
-        }
-        // initial publication "as if colour 1 had just been relaxed": top row column 1, bottom row column 0
-        *ex(1, 0, warp) = make_float2(q.du[0][1], q.dv[0][1]);
-        *ex(1, 1, warp) = make_float2(q.du[SOR_R - 1][0], q.dv[SOR_R - 1][0]);
-        __syncthreads(); // staging buffer fully consumed + exchange visible
-
+        __syncwarp(); // every lane has left the staging block
         const int next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < ntiles) issue(next); // overlaps with the relaxation below
+        if (lane == 0 && next < ntiles) issue(next); // the pull of the next strip overlaps everything below
 
-        // ---- 2T half sweeps in registers
-        const float2 zero2 = make_float2(0.0f, 0.0f);
-        // Half sweep k (0-based) only has to be right for pixels at depth >= k+1 from the tile edge (depth
-        // d becomes garbage-tolerant once k >= d).  A warp whose innermost row has depth <= k therefore
-        // idles in half sweep k (it still joins the barrier):
-        const int wdepth = (warp < SOR_NW / 2) ? (warp * SOR_R + SOR_R - 1) : ((SOR_NW - 1 - warp) * SOR_R + SOR_R - 1);
+        // initial publication "as if colour 1 had just been relaxed": top row column 1, bottom row column 0
+        const int pub0 = npub;
+        publish(make_float2(lo_of(q.du[1][0]), lo_of(q.dv[1][0])), make_float2(hi_of(q.du[0][SOR_HP - 1]), hi_of(q.dv[0][SOR_HP - 1])));
+
+        // ---- 2T half sweeps in registers.  Per half sweep: the interior pairs (own rows only), then -- once the
+        // neighbours' boundary rows of the previous half sweep are visible -- the two boundary pairs, then publish.
+        SOR_CLK(c2);
 #pragma unroll 1
-        for (int t = 0; t < a.T; t++) {
-            if (2 * t < wdepth) {
-                const float2 up = (warp > 0) ? *ex(1, 1, warp - 1) : zero2;
-                const float2 dn = (warp < SOR_NW - 1) ? *ex(1, 0, warp + 1) : zero2;
-                sor_half_sweep<0>(q, up, dn, a.omega);
-                *ex(0, 0, warp) = make_float2(q.du[0][0], q.dv[0][0]);
-                *ex(0, 1, warp) = make_float2(q.du[SOR_R - 1][1], q.dv[SOR_R - 1][1]);
+        for (int k = 0; k < nhalf; k += 2) {
+            sor_relax_range<0, 1, SOR_HP - 1>(q, zero2, zero2, nomega2, k, pdepth);
+            wait_neighbours(pub0 + k + 1);
+            {
+                const int slot = (pub0 + k) & 1;
+                const float2 up = (warp > 0) ? *ex(slot, 1, warp - 1) : zero2;
+                const float2 dn = (warp < SOR_NW - 1) ? *ex(slot, 0, warp + 1) : zero2;
+                sor_relax_range<0, 0, 1>(q, up, dn, nomega2, k, pdepth);
+                sor_relax_range<0, SOR_HP - 1, SOR_HP>(q, up, dn, nomega2, k, pdepth);
+                publish(make_float2(lo_of(q.du[0][0]), lo_of(q.dv[0][0])), make_float2(hi_of(q.du[1][SOR_HP - 1]), hi_of(q.dv[1][SOR_HP - 1])));
             }
-            __syncthreads();
-            if (2 * t + 1 < wdepth) {
-                const float2 up = (warp > 0) ? *ex(0, 1, warp - 1) : zero2;
-                const float2 dn = (warp < SOR_NW - 1) ? *ex(0, 0, warp + 1) : zero2;
-                sor_half_sweep<1>(q, up, dn, a.omega);
-                *ex(1, 0, warp) = make_float2(q.du[0][1], q.dv[0][1]);
-                *ex(1, 1, warp) = make_float2(q.du[SOR_R - 1][0], q.dv[SOR_R - 1][0]);
+            sor_relax_range<1, 1, SOR_HP - 1>(q, zero2, zero2, nomega2, k + 1, pdepth);
+            wait_neighbours(pub0 + k + 2);
+            {
+                const int slot = (pub0 + k + 1) & 1;
+                const float2 up = (warp > 0) ? *ex(slot, 1, warp - 1) : zero2;
+                const float2 dn = (warp < SOR_NW - 1) ? *ex(slot, 0, warp + 1) : zero2;
+                sor_relax_range<1, 0, 1>(q, up, dn, nomega2, k + 1, pdepth);
+                sor_relax_range<1, SOR_HP - 1, SOR_HP>(q, up, dn, nomega2, k + 1, pdepth);
+                if (k + 2 < nhalf)
+                    publish(make_float2(lo_of(q.du[1][0]), lo_of(q.dv[1][0])), make_float2(hi_of(q.du[0][SOR_HP - 1]), hi_of(q.dv[0][SOR_HP - 1])));
             }
-            __syncthreads();
         }
 
         // ---- interior of the tile -> global (float2 per lane and row: 256 B per warp row)
+        SOR_CLK(c3);
         const int cx = 2 * lane, gx = x0 + cx;
         if (cx >= hx && cx < SOR_TW - hx && gx < a.g.W) {
 #pragma unroll
-            for (int r = 0; r < SOR_R; r++) {
-                const int tr = warp * SOR_R + r, gy = y0 + tr;
-                if (tr >= hy && tr < SOR_TH - hy && gy < a.g.H) {
-                    const size_t o = (size_t)gy * a.g.S + gx;
-                    *reinterpret_cast<float2 *>(a.out_du + o) = make_float2(q.du[r][0], q.du[r][1]);
-                    *reinterpret_cast<float2 *>(a.out_dv + o) = make_float2(q.dv[r][0], q.dv[r][1]);
+            for (int p = 0; p < SOR_HP; p++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int tr = warp * SOR_R + p + h * SOR_HP, gy = y0 + tr;
+                    if (tr >= hy && tr < SOR_TH - hy && gy < a.g.H) {
+                        const size_t o = (size_t)gy * a.g.S + gx;
+                        *reinterpret_cast<float2 *>(a.out_du + o) = h ? make_float2(hi_of(q.du[0][p]), hi_of(q.du[1][p]))
+                                                                      : make_float2(lo_of(q.du[0][p]), lo_of(q.du[1][p]));
+                        *reinterpret_cast<float2 *>(a.out_dv + o) = h ? make_float2(hi_of(q.dv[0][p]), hi_of(q.dv[1][p]))
+                                                                      : make_float2(lo_of(q.dv[0][p]), lo_of(q.dv[1][p]));
+                    }
                 }
             }
         }
         tile = next;
+#ifdef SF_SOR_CLOCKS
+        if (threadIdx.x == SF_SOR_CLOCK_THREAD) {
+            const long long c4 = clock64();
+            atomicAdd(&g_sor_clk[0], (unsigned long long)(c1 - c0));
+            atomicAdd(&g_sor_clk[1], (unsigned long long)(c2 - c1));
+            atomicAdd(&g_sor_clk[2], (unsigned long long)(c3 - c2));
+            atomicAdd(&g_sor_clk[3], (unsigned long long)wait_clk);
+            atomicAdd(&g_sor_clk[4], (unsigned long long)(c4 - c3));
+            atomicAdd(&g_sor_clk[7], 1ull);
+            wait_clk = 0;
+        }
+#endif
     }
 }
 
@@ -304,18 +487,23 @@ bool sor_plan_init(SorPlan &plan, Geom g, float *arena, int num_sms) {
         set_error("cuTensorMapEncodeTiled not available from the CUDA driver");
         return false;
     }
+    // three views of the same (x, y, plane) arena that differ in the box: a warp's coefficient strip (7 planes),
+    // its iterate strip (du,dv plane pair) and a single row (psi_v above the strip)
     const cuuint64_t dims[3] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)SP_COUNT};
     const cuuint64_t strides[2] = {(cuuint64_t)g.S * 4, (cuuint64_t)g.plane() * 4};
-    const cuuint32_t box[3] = {SOR_TW, SOR_TH, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(&plan.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, arena, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        char buf[128];
-        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (CUresult %d) for %dx%d stride %d", (int)r, g.W, g.H, g.S);
-        set_error(buf);
-        return false;
+    const cuuint32_t boxes[3][3] = {{SOR_TW, SOR_R, 7}, {SOR_TW, SOR_R, 2}, {SOR_TW, 1, 1}};
+    CUtensorMap *maps[3] = {&plan.tmap, &plan.tmap_iter, &plan.tmap_row};
+    for (int m = 0; m < 3; m++) {
+        const CUresult r = enc(maps[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, arena, dims, strides, boxes[m], estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            char buf[128];
+            snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (CUresult %d) for %dx%d stride %d", (int)r, g.W, g.H, g.S);
+            set_error(buf);
+            return false;
+        }
     }
     plan.tmap_valid = true;
     return true;
@@ -353,7 +541,8 @@ int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int 
         attr_set = true;
     }
     if (fuse < 1) fuse = 1;
-    if (fuse > 7) fuse = 7; // halo 2*fuse per side must leave an interior: 64 - 4*fuse >= 36
+    const int max_fuse = (SOR_TH - 4) / 4 < 7 ? (SOR_TH - 4) / 4 : 7; // the halo (2*fuse per side) must leave an interior
+    if (fuse > max_fuse) fuse = max_fuse;
     int done = 0;
     while (done < iterations) {
         const int T = (iterations - done < fuse) ? (iterations - done) : fuse;
@@ -364,6 +553,7 @@ int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int 
         a.tiles_x = (g.W + IW - 1) / IW;
         a.tiles_y = (g.H + IH - 1) / IH;
         a.omega = omega;
+        a.one = 1.0f;
         a.zero_init = (zero_init && done == 0) ? 1 : 0;
         a.in_du_plane = *cur ? SP_DUB : SP_DUA;
         a.in_dv_plane = *cur ? SP_DVB : SP_DVA;
@@ -371,7 +561,7 @@ int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int 
         a.out_dv = A + (size_t)(*cur ? SP_DVA : SP_DVB) * P;
         const int ntiles = a.tiles_x * a.tiles_y;
         const int grid = ntiles < plan.num_sms ? ntiles : plan.num_sms;
-        k_sor_tiled<<<grid, SOR_NW * 32, SOR_SMEM_BYTES, st>>>(plan.tmap, a);
+        k_sor_tiled<<<grid, SOR_NW * 32, SOR_SMEM_BYTES, st>>>(plan.tmap, plan.tmap_iter, plan.tmap_row, a);
         *cur ^= 1;
         done += T;
         launches++;
