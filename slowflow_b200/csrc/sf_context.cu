@@ -153,9 +153,12 @@ int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d
     launch_dpsis_weight(st, g, d_im1, c->dpsis, 5.0f, avg0, std1, 255.0f); // variational.c:34
     c->prof_acc.kernel_launches++;
 
+    const bool fused_prep = c->data_variant == 0; // 1: separate warp kernel + tile-based data-term kernel (A/B reference)
     for (int outer = 0; outer < params->niter_outer; outer++) {
-        launch_warp(st, g, d_im2, d_wx, d_wy, 1, c->wim, c->mask); // variational.c:40
-        c->prof_acc.kernel_launches++;
+        if (!fused_prep) {
+            launch_warp(st, g, d_im2, d_wx, d_wy, 1, c->wim, c->mask); // variational.c:40
+            c->prof_acc.kernel_launches++;
+        }
         int cur = 0;
         for (int inner = 0; inner < params->niter_inner; inner++) {
             const bool first = (inner == 0), last = (inner == params->niter_inner - 1);
@@ -173,7 +176,11 @@ int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d
             cm.ph = A + SP_PH * P; cm.pv = A + SP_PV * P; cm.lap_u = d_wx; cm.lap_v = d_wy;
             cm.a11 = A + SP_A11 * P; cm.a12 = A + SP_A12 * P; cm.a22 = A + SP_A22 * P; cm.b1 = A + SP_B1 * P;
             cm.b2 = A + SP_B2 * P;
-            launch_data_term(st, g, term, cm);
+            if (fused_prep)
+                launch_prep_two_frame(st, g, c->num_sms, d_im1, d_im2, d_wx, d_wy, du, dv, cm.ph, cm.pv, half_delta_over3,
+                                      half_gamma_over3, cm.a11, cm.a12, cm.a22, cm.b1, cm.b2);
+            else
+                launch_data_term(st, g, term, cm);
             c->prof_end(PROF_DATA, ev);
             c->prof_acc.data_launches++;
             c->prof_acc.data_pixels += (long long)g.W * g.H;
@@ -237,6 +244,7 @@ int sfgpu_create(int device, void *stream, sfgpu_ctx **out) {
     }
     sfgpu_ctx *c = new sfgpu_ctx();
     c->device = device;
+    if (const char *e = getenv("SLOWFLOW_GPU_DATA_VARIANT")) c->data_variant = atoi(e); // A/B switch for benchmarking
     c->num_sms = prop.multiProcessorCount;
     if (stream) {
         c->stream = (cudaStream_t)stream;

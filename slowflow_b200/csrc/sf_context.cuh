@@ -11,6 +11,7 @@ struct sfgpu_ctx {
     int num_sms = 148;
 
     int sor_variant = 0; // 0 tiled, 1 per-half-sweep launches
+    int data_variant = 0; // 0 fused marching warp+data-term kernel, 1 separate warp + tile kernel (env SLOWFLOW_GPU_DATA_VARIANT)
     int sor_fuse = 0;    // 0 = auto
 
     // ---- level workspace (one allocation, re-made when the geometry grows)

@@ -79,6 +79,12 @@ struct DataCommon {
     float *a11, *a12, *a22, *b1, *b2;
 };
 void launch_data_term(cudaStream_t st, Geom g, const DataTermDesc &t, const DataCommon &cm);
+// K1+K2 fused, marching form (sf_prep.cu): warp + derivatives + two-frame data term + Laplacian + block inverse.
+// Writes the same five planes as launch_warp + launch_data_term(fuse_system) without the warped image in HBM.
+void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im1, const float *im2, const float *wx,
+                           const float *wy, const float *du, const float *dv, const float *ph, const float *pv,
+                           float half_delta_over3, float half_gamma_over3, float *a11, float *a12, float *a22, float *b1,
+                           float *b2);
 // sub_laplacian as a gather (operator twin)
 void launch_sub_laplacian(cudaStream_t st, Geom g, float *dst, const float *src, const float *ph, const float *pv);
 // in-place inverse of the 2x2 blocks (operator twin of the first SOR sweep's prologue)

@@ -1,0 +1,388 @@
+// sf_prep.cu -- K1+K2 fused, marching form: bilinear warp + image derivatives + two-frame data term
+// + div(psi grad w) + 2x2 block inverse in ONE pass over the frame pair (sm_100a).
+//
+// Replaces, per outer iteration of the two-frame path (variational.c:40-57):
+//     image_warp                  variational_aux.c:18-52     (the warped image and its mask never exist in HBM)
+//     get_derivatives             variational_aux.c:55-78     (nor do the 24 derivative planes)
+//     compute_data_and_match      variational_aux.c:215-302
+//     sub_laplacian x2            variational_aux.c:153-180
+//     block inverse of sor_coupled's first sweep              solver.c:101-106
+// HBM traffic: read wx,wy (8 B/px) + im1 (12) + im2 through L1/L2 gathers (12) + psi_h,psi_v (8); write the five
+// system planes (20).  SURVEY 8(d) counts 52 B/px for this step.
+//
+// Work decomposition (no shared memory, no CTA barrier):
+//   * one WARP owns a strip of 64 columns (lane l = columns 2l, 2l+1) and marches down a segment of rows;
+//   * every per-row quantity is a packed (column 2l, column 2l+1) pair in one 64-bit register, so the vertical
+//     stencils, the robust weights and the 2x2 system run on FFMA2 (sf_pack.cuh);
+//   * vertical taps come from rolling 4-row register windows (m, z, Ix, Iy, Iyz per channel), horizontal taps from
+//     the neighbouring lanes by warp shuffle.  The 5-tap-of-5-tap stencil needs +-4 columns = 2 lanes, so lanes
+//     2..29 (56 columns) produce output and consecutive strips overlap by 8 columns;
+//   * row r is loaded (and im2 warped) at step r; the output row of step r is o = r - 4.
+// Border semantics follow image.c:400-526: rows / columns outside the image are clamped at load time, which
+// reproduces the replicate border of the first derivative stage; the second stage (d/dx of Ix, d/dy of Iy)
+// replicates the first-stage VALUE, which is patched explicitly in edge strips / segments.
+#include <type_traits>
+
+#include "sf_internal.cuh"
+#include "sf_pack.cuh"
+#include "sf_stencil.cuh"
+
+namespace sf {
+
+constexpr int PR_OUT_LO = 2, PR_OUT_HI = 29;            // output lanes
+constexpr int PR_OUT_W = 2 * (PR_OUT_HI - PR_OUT_LO + 1); // 56 output columns per strip
+constexpr int PR_WARPS = 4;                             // warps per CTA (independent)
+
+struct Ring {
+    p64 m[3][4], z[3][4], ix[3][4], iy[3][4], iyz[3][4];
+};
+
+// per-lane geometry of the strip
+struct Lane {
+    int x0;       // first column of the pair (may be outside the image in edge strips)
+    int xc0, xc1; // clamped columns
+    int lane_l, lane_r, comp_r; // lanes holding column 0 / column W-1 (edge strips)
+};
+
+// (column 2l, column 2l+1) of one row.  Interior strips: one 8-byte load; edge strips: two clamped 4-byte loads.
+template <bool EDGE>
+__device__ __forceinline__ p64 load_pair(const float *__restrict__ plane, int rowoff, const Lane &L) {
+    if (!EDGE) return __ldg(reinterpret_cast<const p64 *>(plane + rowoff + L.x0));
+    return pk(__ldg(plane + rowoff + L.xc0), __ldg(plane + rowoff + L.xc1));
+}
+
+// horizontal 5-tap [1,-8,0,8,-1]/12 on a pair: columns (c0-2,c1-2) are the left lane's pair, (c0+2,c1+2) the right lane's
+__device__ __forceinline__ p64 hconv_pair(p64 v) {
+    const p64 l = shfl_up2(v), r = shfl_down2(v);
+    p64 t = mul2(splat2(SF_C0), l);
+    t = fma2(splat2(SF_C1), pk(hi_of(l), lo_of(v)), t);
+    t = fma2(splat2(SF_C3), pk(hi_of(v), lo_of(r)), t);
+    return fma2(splat2(SF_C4), r, t);
+}
+// vertical 5-tap on pairs (the centre tap has weight -0)
+__device__ __forceinline__ p64 vconv_pair(p64 m2, p64 m1, p64 p1, p64 p2) {
+    return fma2(splat2(SF_C4), p2, fma2(splat2(SF_C3), p1, fma2(splat2(SF_C1), m1, mul2(splat2(SF_C0), m2))));
+}
+// second-stage replicate border in x: columns outside the image take the VALUE at column 0 / W-1
+__device__ __forceinline__ p64 xedge_fix(p64 v, const Lane &L, int W) {
+    const float vl = __shfl_sync(0xffffffffu, lo_of(v), L.lane_l);
+    const float r0 = __shfl_sync(0xffffffffu, lo_of(v), L.lane_r), r1 = __shfl_sync(0xffffffffu, hi_of(v), L.lane_r);
+    const float vr = L.comp_r ? r1 : r0;
+    float a = lo_of(v), b = hi_of(v);
+    if (L.x0 < 0) a = vl;
+    if (L.x0 + 1 < 0) b = vl;
+    if (L.x0 > W - 1) a = vr;
+    if (L.x0 + 1 > W - 1) b = vr;
+    return pk(a, b);
+}
+// 1/x: MUFU.RCP (1 ulp) refined by one Newton step on the packed pipe (~0.5 ulp; the reference divides, divps)
+__device__ __forceinline__ p64 rcp2(p64 x) {
+    float a, b;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(lo_of(x)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(hi_of(x)));
+    const p64 r = pk(a, b);
+    const p64 e = fma2(mul2(x, splat2(-1.0f)), r, splat2(1.0f)); // 1 - x*r
+    return fma2(r, e, r);
+}
+
+struct PrepArgs {
+    Geom g;
+    const float *im1, *im2; // 3 planes each
+    const float *wx, *wy;   // flow: warps im2 and is the argument of the Laplacian
+    const float *du, *dv;   // current increment (nullable: 0)
+    const float *ph, *pv;   // smoothness diffusivities
+    float *a11, *a12, *a22, *b1, *b2;
+    float hd, hg;           // 0.5*delta/3, 0.5*gamma/3
+    int strips, seg_rows, nwork;
+};
+
+// the four bilinear taps of one warped pixel (variational_aux.c:18-52)
+struct Taps {
+    int o11, o12, o21, o22;
+    float w11, w12, w21, w22;
+};
+__device__ __forceinline__ Taps warp_taps(const Geom &g, float xx, float yy) {
+    const float Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
+    const float xf = floorf(xx), yf = floorf(yy);
+    const float dx = xx - xf, dy = yy - yf;
+    // clamp in float first so that huge flows cannot overflow the int conversion
+    const int x = (int)fminf(fmaxf(xf, -2.0f), Wm1 + 2.0f), y = (int)fminf(fmaxf(yf, -2.0f), Hm1 + 2.0f);
+    const int x1 = clampi(x, 0, g.W - 1), x2 = clampi(x + 1, 0, g.W - 1);
+    const int y1 = clampi(y, 0, g.H - 1) * g.S, y2 = clampi(y + 1, 0, g.H - 1) * g.S;
+    Taps t;
+    t.o11 = y1 + x1; t.o12 = y1 + x2; t.o21 = y2 + x1; t.o22 = y2 + x2;
+    // reference order: s11*(1-dx)*(1-dy) + s12*dx*(1-dy) + s21*(1-dx)*dy + s22*dx*dy
+    t.w11 = (1.0f - dx) * (1.0f - dy); t.w12 = dx * (1.0f - dy); t.w21 = (1.0f - dx) * dy; t.w22 = dx * dy;
+    return t;
+}
+__device__ __forceinline__ float warp_fetch(const float *__restrict__ src, const Taps &t) {
+    return __ldg(src + t.o11) * t.w11 + __ldg(src + t.o12) * t.w12 + __ldg(src + t.o21) * t.w21 + __ldg(src + t.o22) * t.w22;
+}
+
+// One warp marches down its (strip, segment).  EDGE: the strip touches the left or right image border.
+template <bool COLOR, bool EDGE>
+__device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, const int seg, const int lane) {
+    const Geom g = a.g;
+    const int W = g.W, H = g.H, H1 = H - 1, S = g.S;
+    const int P = (int)g.plane();
+
+    Lane L;
+    const int X0 = strip * PR_OUT_W - 2 * PR_OUT_LO;
+    L.x0 = X0 + 2 * lane;
+    L.xc0 = clampi(L.x0, 0, W - 1);
+    L.xc1 = clampi(L.x0 + 1, 0, W - 1);
+    L.lane_l = clampi((0 - X0) >> 1, 0, 31);
+    L.lane_r = clampi((W - 1 - X0) >> 1, 0, 31);
+    L.comp_r = (W - 1 - X0) & 1;
+
+    const int Y0 = seg * a.seg_rows;
+    const int Yend = min(Y0 + a.seg_rows, H);
+    const int Rbase = Y0 - 4;
+
+    const bool out_lane = (lane >= PR_OUT_LO) && (lane <= PR_OUT_HI) && (L.x0 < S);
+    const bool v0 = L.x0 < W, v1 = L.x0 + 1 < W; // valid (non-padding) columns of the pair
+    const float fxc0 = (float)L.xc0, fxc1 = (float)L.xc1;
+
+    const p64 zero2 = splat2(0.0f), half2 = splat2(0.5f), mone2 = splat2(-1.0f);
+    const p64 dnorm2 = splat2(0.1f * 0.1f);
+    const float eps_color = 0.001f * 0.001f, eps_grad = 0.001f * 0.001f;
+    const float Wm1 = (float)(W - 1), Hm1 = (float)H1;
+
+    Ring R;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int s = 0; s < 4; s++) R.m[c][s] = R.z[c][s] = R.ix[c][s] = R.iy[c][s] = R.iyz[c][s] = zero2;
+
+    // software pipeline: im1 and the flow of the NEXT row to be warped are loaded one step ahead
+    p64 An[3], fx, fy;
+    {
+        const int ro = clampi(Rbase, 0, H1) * S;
+#pragma unroll
+        for (int c = 0; c < 3; c++) An[c] = load_pair<EDGE>(a.im1 + c * P, ro, L);
+        fx = load_pair<EDGE>(a.wx, ro, L);
+        fy = load_pair<EDGE>(a.wy, ro, L);
+    }
+    p64 lu_m = zero2, lu_0 = zero2, lv_m = zero2, lv_0 = zero2; // Laplacian window: flow of rows o-1, o
+    p64 vt = zero2;                                            // psi_v of row o-1
+
+    // one marching step; U = (r - Rbase) & 3 is the ring slot of row r.  Everything is computed unconditionally
+    // (rows are clamped); only the stores are predicated, so every shuffle sits in straight-line code.
+    auto step = [&](auto Utag, const int r) {
+        constexpr int U = decltype(Utag)::value;
+        constexpr int U1 = (U + 1) & 3, U2 = (U + 2) & 3, U3 = (U + 3) & 3;
+        const int rr = clampi(r, 0, H1);
+        const int o = r - 4, oc = clampi(o, 0, H1);
+        const bool out_row = (o >= Y0) && (o < Yend); // warp-uniform
+
+        // ---- issue the gathers of row r (flow prefetched one step ago) and the loads of the next row
+        const Taps t0 = warp_taps(g, fxc0 + lo_of(fx), (float)rr + lo_of(fy));
+        const Taps t1 = warp_taps(g, fxc1 + hi_of(fx), (float)rr + hi_of(fy));
+        p64 A[3], B[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            A[c] = An[c];
+            B[c] = pk(warp_fetch(a.im2 + c * P, t0), warp_fetch(a.im2 + c * P, t1));
+        }
+        {
+            const int rn = clampi(r + 1, 0, H1) * S;
+#pragma unroll
+            for (int c = 0; c < 3; c++) An[c] = load_pair<EDGE>(a.im1 + c * P, rn, L);
+            fx = load_pair<EDGE>(a.wx, rn, L);
+            fy = load_pair<EDGE>(a.wy, rn, L);
+        }
+        const int oo = oc * S, on = clampi(o + 1, 0, H1) * S;
+        const p64 lu_p = load_pair<EDGE>(a.wx, on, L), lv_p = load_pair<EDGE>(a.wy, on, L); // flow of row o+1
+        const p64 hr = load_pair<EDGE>(a.ph, oo, L), vb = load_pair<EDGE>(a.pv, oo, L);
+        p64 u = zero2, v = zero2;
+        if (a.du) {
+            u = load_pair<EDGE>(a.du, oo, L);
+            v = load_pair<EDGE>(a.dv, oo, L);
+        }
+
+        // ---- work that does not need row r: Ix of row r-2, the x-derivatives and Ixy of the output row
+        p64 ix_new[3], ixx[3], ixz[3], ixy[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            ix_new[c] = hconv_pair(R.m[c][U2]);
+            if (EDGE) ix_new[c] = xedge_fix(ix_new[c], L, W);
+            ixx[c] = hconv_pair(R.ix[c][U]); // (columns outside the image were patched in Ix itself)
+            ixz[c] = hconv_pair(R.z[c][U]);
+            ixy[c] = vconv_pair(R.ix[c][U2], R.ix[c][U3], R.ix[c][U1], ix_new[c]);
+        }
+        // psi_h of the left edge from the neighbouring lane (0 at column 0), psi_v of the row above (0 at row 0),
+        // flow neighbours in row o, mask of the warp at row o
+        const float hl_lane = __shfl_up_sync(0xffffffffu, hi_of(hr), 1);
+        const p64 hl = pk(L.x0 > 0 ? hl_lane : 0.0f, lo_of(hr));
+        const p64 vtt = (o > 0) ? vt : zero2;
+        const float ul = __shfl_up_sync(0xffffffffu, hi_of(lu_0), 1), ur = __shfl_down_sync(0xffffffffu, lo_of(lu_0), 1);
+        const float vl = __shfl_up_sync(0xffffffffu, hi_of(lv_0), 1), vr = __shfl_down_sync(0xffffffffu, lo_of(lv_0), 1);
+        float mk0, mk1;
+        {
+            const float xx0 = fxc0 + lo_of(lu_0), yy0 = (float)o + lo_of(lv_0);
+            const float xx1 = fxc1 + hi_of(lu_0), yy1 = (float)o + hi_of(lv_0);
+            mk0 = (xx0 >= 0.0f && xx0 <= Wm1 && yy0 >= 0.0f && yy0 <= Hm1) ? 1.0f : 0.0f;
+            mk1 = (xx1 >= 0.0f && xx1 <= Wm1 && yy1 >= 0.0f && yy1 <= Hm1) ? 1.0f : 0.0f;
+        }
+
+        // ---- row r: m = (B + A)/2, z = B - A; first-stage y-derivatives of row r-2; Iyy of the output row; data term
+        p64 n = zero2, s11 = zero2, s12 = zero2, s22 = zero2, sb1 = zero2, sb2 = zero2;
+        p64 cn = zero2, c11 = zero2, c12 = zero2, c22 = zero2, cb1 = zero2, cb2 = zero2;
+        p64 iy_keep[3], iyz_keep[3], m_keep[3], z_keep[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const p64 m_new = mul2(add2(B[c], A[c]), half2);
+            const p64 z_new = fma2(A[c], mone2, B[c]);
+            p64 iy_new = vconv_pair(R.m[c][U], R.m[c][U1], R.m[c][U3], m_new);
+            const p64 iyz_new = vconv_pair(R.z[c][U], R.z[c][U1], R.z[c][U3], z_new);
+            // second-stage replicate border in y: Iy of rows beyond the last row is Iy(H-1)
+            if (r - 2 > H1) iy_new = R.iy[c][U1];
+            p64 iy_m2 = R.iy[c][U2], iy_m1 = R.iy[c][U3];
+            if (o == 0) iy_m2 = iy_m1 = R.iy[c][U];     // rows -2, -1 take Iy(0)
+            else if (o == 1) iy_m2 = R.iy[c][U3];       // row -1 takes Iy(0)
+            const p64 iyy = vconv_pair(iy_m2, iy_m1, R.iy[c][U1], iy_new);
+            const p64 iyz = R.iyz[c][U];
+            // gradient constancy (variational_aux.c:268-296)
+            const p64 ivx = rcp2(fma2(ixx[c], ixx[c], fma2(ixy[c], ixy[c], dnorm2)));
+            const p64 ivy = rcp2(fma2(iyy, iyy, fma2(ixy[c], ixy[c], dnorm2)));
+            const p64 rx = fma2(ixy[c], v, fma2(ixx[c], u, ixz[c]));
+            const p64 ry = fma2(iyy, v, fma2(ixy[c], u, iyz));
+            n = fma2(mul2(rx, rx), ivx, n);
+            n = fma2(mul2(ry, ry), ivy, n);
+            const p64 px = mul2(ixx[c], ivx), sx = mul2(ixy[c], ivx), qy = mul2(ixy[c], ivy), ty = mul2(iyy, ivy);
+            s11 = fma2(qy, ixy[c], fma2(px, ixx[c], s11));
+            s12 = fma2(qy, iyy, fma2(px, ixy[c], s12));
+            s22 = fma2(sx, ixy[c], fma2(ty, iyy, s22));
+            sb1 = fma2(qy, iyz, fma2(px, ixz[c], sb1));
+            sb2 = fma2(sx, ixz[c], fma2(ty, iyz, sb2));
+            if (COLOR) { // colour constancy (variational_aux.c:241-266)
+                const p64 ix = R.ix[c][U], iy = R.iy[c][U], iz = R.z[c][U];
+                const p64 inv = rcp2(fma2(iy, iy, fma2(ix, ix, dnorm2)));
+                const p64 rc = fma2(iy, v, fma2(ix, u, iz));
+                cn = fma2(mul2(rc, rc), inv, cn);
+                const p64 gx = mul2(ix, inv), gy = mul2(iy, inv);
+                c11 = fma2(gx, ix, c11);
+                c12 = fma2(gx, iy, c12);
+                c22 = fma2(gy, iy, c22);
+                cb1 = fma2(gx, iz, cb1);
+                cb2 = fma2(gy, iz, cb2);
+            }
+            iy_keep[c] = iy_new; iyz_keep[c] = iyz_new; m_keep[c] = m_new; z_keep[c] = z_new;
+        }
+        // ---- robust weights, system, Laplacian, block inverse
+        const p64 tg = pk(mk0 * a.hg * rsqrtf(lo_of(n) + eps_grad), mk1 * a.hg * rsqrtf(hi_of(n) + eps_grad));
+        p64 a11 = mul2(tg, s11), a12 = mul2(tg, s12), a22 = mul2(tg, s22);
+        const p64 ntg = mul2(tg, mone2);
+        p64 b1 = mul2(ntg, sb1), b2 = mul2(ntg, sb2);
+        if (COLOR) {
+            const p64 tc = pk(mk0 * a.hd * rsqrtf(lo_of(cn) + eps_color), mk1 * a.hd * rsqrtf(hi_of(cn) + eps_color));
+            const p64 ntc = mul2(tc, mone2);
+            a11 = fma2(tc, c11, a11);
+            a12 = fma2(tc, c12, a12);
+            a22 = fma2(tc, c22, a22);
+            b1 = fma2(ntc, cb1, b1);
+            b2 = fma2(ntc, cb2, b2);
+        }
+        {
+            // b += div(psi grad w): left edge, right edge, upper edge, lower edge (variational_aux.c:158-179)
+            const p64 nhl = mul2(hl, mone2), nvt = mul2(vtt, mone2);
+            const p64 wl_u = pk(ul, lo_of(lu_0)), wr_u = pk(hi_of(lu_0), ur);
+            const p64 wl_v = pk(vl, lo_of(lv_0)), wr_v = pk(hi_of(lv_0), vr);
+            b1 = fma2(nhl, fma2(wl_u, mone2, lu_0), b1);
+            b1 = fma2(hr, fma2(lu_0, mone2, wr_u), b1);
+            b1 = fma2(nvt, fma2(lu_m, mone2, lu_0), b1);
+            b1 = fma2(vb, fma2(lu_0, mone2, lu_p), b1);
+            b2 = fma2(nhl, fma2(wl_v, mone2, lv_0), b2);
+            b2 = fma2(hr, fma2(lv_0, mone2, wr_v), b2);
+            b2 = fma2(nvt, fma2(lv_m, mone2, lv_0), b2);
+            b2 = fma2(vb, fma2(lv_0, mone2, lv_p), b2);
+        }
+        // inverse of [[a11 + sum psi, a12], [a12, a22 + sum psi]] (solver.c:101-106)
+        const p64 sp = add2(add2(add2(hl, hr), vtt), vb);
+        const p64 D11 = add2(a22, sp), D22 = add2(a11, sp);
+        const p64 det = fma2(mul2(a12, a12), mone2, mul2(D11, D22));
+        const p64 rdet = rcp2(det);
+        const p64 i11 = mul2(D11, rdet), i22 = mul2(D22, rdet), i12 = mul2(mul2(a12, mone2), rdet);
+        if (out_row && out_lane) {
+            const int off = o * S + L.x0;
+            // padding columns: defined zeros (the reference leaves garbage there)
+            *reinterpret_cast<float2 *>(a.a11 + off) = make_float2(v0 ? lo_of(i11) : 0.0f, v1 ? hi_of(i11) : 0.0f);
+            *reinterpret_cast<float2 *>(a.a12 + off) = make_float2(v0 ? lo_of(i12) : 0.0f, v1 ? hi_of(i12) : 0.0f);
+            *reinterpret_cast<float2 *>(a.a22 + off) = make_float2(v0 ? lo_of(i22) : 0.0f, v1 ? hi_of(i22) : 0.0f);
+            *reinterpret_cast<float2 *>(a.b1 + off) = make_float2(v0 ? lo_of(b1) : 0.0f, v1 ? hi_of(b1) : 0.0f);
+            *reinterpret_cast<float2 *>(a.b2 + off) = make_float2(v0 ? lo_of(b2) : 0.0f, v1 ? hi_of(b2) : 0.0f);
+        }
+
+        // ---- rotate the windows
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            R.m[c][U] = m_keep[c];
+            R.z[c][U] = z_keep[c];
+            R.ix[c][U2] = ix_new[c];
+            R.iy[c][U2] = iy_keep[c];
+            R.iyz[c][U2] = iyz_keep[c];
+        }
+        vt = vb;
+        lu_m = lu_0; lu_0 = lu_p;
+        lv_m = lv_0; lv_0 = lv_p;
+    };
+
+    const int Rend = Yend + 4; // last loaded row is Yend + 3
+#pragma unroll 1
+    for (int r = Rbase; r < Rend; r += 4) {
+        step(std::integral_constant<int, 0>{}, r);
+        step(std::integral_constant<int, 1>{}, r + 1);
+        step(std::integral_constant<int, 2>{}, r + 2);
+        step(std::integral_constant<int, 3>{}, r + 3);
+    }
+}
+
+template <bool COLOR>
+__global__ void __launch_bounds__(PR_WARPS * 32) k_prep_two_frame(PrepArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int work = blockIdx.x * PR_WARPS + (threadIdx.x >> 5);
+    if (work >= a.nwork) return; // whole warp
+    const int strip = work % a.strips, seg = work / a.strips;
+    const int X0 = strip * PR_OUT_W - 2 * PR_OUT_LO;
+    if ((X0 < 0) || (X0 + 63 > a.g.W - 1)) prep_march<COLOR, true>(a, strip, seg, lane);
+    else prep_march<COLOR, false>(a, strip, seg, lane);
+}
+
+// rows per segment: the largest number of (strip, segment) work items that is still ONE wave of resident warps
+// (a second, mostly empty wave would double the kernel time), but at least 16 rows (8 warm-up rows per segment)
+static int prep_seg_rows(Geom g, int num_sms, int resident_warps_per_sm) {
+    const int strips = (g.S + PR_OUT_W - 1) / PR_OUT_W;
+    int segs = (num_sms * resident_warps_per_sm) / strips;
+    if (segs < 1) segs = 1;
+    int rows = (g.H + segs - 1) / segs;
+    if (rows < 16) rows = 16;
+    return (rows + 3) & ~3;
+}
+
+void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im1, const float *im2, const float *wx,
+                           const float *wy, const float *du, const float *dv, const float *ph, const float *pv,
+                           float half_delta_over3, float half_gamma_over3, float *a11, float *a12, float *a22, float *b1,
+                           float *b2) {
+    PrepArgs a;
+    a.g = g;
+    a.im1 = im1; a.im2 = im2; a.wx = wx; a.wy = wy; a.du = du; a.dv = dv; a.ph = ph; a.pv = pv;
+    a.a11 = a11; a.a12 = a12; a.a22 = a22; a.b1 = b1; a.b2 = b2;
+    a.hd = half_delta_over3; a.hg = half_gamma_over3;
+    a.strips = (g.S + PR_OUT_W - 1) / PR_OUT_W;
+    static int resident[2] = {0, 0}; // resident warps per SM of the two instantiations
+    const int color = half_delta_over3 != 0.0f ? 1 : 0;
+    if (!resident[color]) {
+        int blocks_per_sm = 0;
+        if (color) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_prep_two_frame<true>, PR_WARPS * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_prep_two_frame<false>, PR_WARPS * 32, 0);
+        resident[color] = (blocks_per_sm > 0 ? blocks_per_sm : 1) * PR_WARPS;
+    }
+    a.seg_rows = prep_seg_rows(g, num_sms, resident[color]);
+    const int segs = (g.H + a.seg_rows - 1) / a.seg_rows;
+    a.nwork = a.strips * segs;
+    const int blocks = (a.nwork + PR_WARPS - 1) / PR_WARPS;
+    if (half_delta_over3 != 0.0f) k_prep_two_frame<true><<<blocks, PR_WARPS * 32, 0, st>>>(a);
+    else k_prep_two_frame<false><<<blocks, PR_WARPS * 32, 0, st>>>(a);
+}
+
+} // namespace sf

@@ -19,6 +19,7 @@
 //   * du,dv ping-pong between two arena buffers (a tile's halo is another tile's interior).
 // Variant 1 (validation, tiny images): one launch per half sweep straight from global memory.
 #include "sf_internal.cuh"
+#include "sf_pack.cuh"
 
 #ifndef SF_SOR_NW
 #define SF_SOR_NW 8
@@ -133,39 +134,6 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 // packed-fp32 FFMA2 (fma.rn.f32x2, sm_100): both rows of a pair have the same colour in a given column.
 // (64-bit inline-asm operands make ptxas keep the pairs in aligned register pairs; with float2 values it
 // re-assembled every operand with MOVs.)
-typedef unsigned long long p64;
-__device__ __forceinline__ p64 pk(float lo, float hi) {
-    p64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ p64 pkv(float lo, float hi) {
-    p64 r;
-    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float lo_of(p64 v) {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return a;
-}
-__device__ __forceinline__ float hi_of(p64 v) {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return b;
-}
-__device__ __forceinline__ p64 fma2(p64 a, p64 b, p64 c) {
-    p64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ p64 shfl_up2(p64 v) {
-    return pk(__shfl_up_sync(0xffffffffu, lo_of(v), 1), __shfl_up_sync(0xffffffffu, hi_of(v), 1));
-}
-__device__ __forceinline__ p64 shfl_down2(p64 v) {
-    return pk(__shfl_down_sync(0xffffffffu, lo_of(v), 1), __shfl_down_sync(0xffffffffu, hi_of(v), 1));
-}
-
 struct SorRegs {
     p64 na11[2][SOR_HP], na12[2][SOR_HP], na22[2][SOR_HP]; // NEGATED inverse blocks, [column][pair]
     p64 b1[2][SOR_HP], b2[2][SOR_HP];
