@@ -1,5 +1,7 @@
 // sf_context.cu -- context management, the two-frame driver and the C ABI of include/slowflow_gpu.h
 // (two-frame, sequence, operator twins, profiling).  The multi-frame driver lives in sf_mt.cu.
+#include <utility>
+
 #include "sf_context.cuh"
 
 #include <stdlib.h>
@@ -154,6 +156,45 @@ int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d
     c->prof_acc.kernel_launches++;
 
     const bool fused_prep = c->data_variant == 0; // 1: separate warp kernel + tile-based data-term kernel (A/B reference)
+    if (fused_prep && params->niter_inner == 1 && params->niter_solver > 0) {
+        // Default shape of the loop (one inner iteration): per outer iteration the flow update of the previous
+        // iteration (variational.c:60-69 collapsed to w += du) is folded into the smoothness pass, so an outer
+        // iteration is {update+smoothness, warp+derivatives+data term+Laplacian+block inverse, SOR launches}.
+        // The flow ping-pongs between the caller's planes and (uu, vv); the last update lands in the caller's.
+        float *fx = d_wx, *fy = d_wy, *ax = c->uu, *ay = c->vv;
+        const float *pdu = nullptr, *pdv = nullptr;
+        for (int outer = 0; outer < params->niter_outer; outer++) {
+            if (outer == 0) {
+                launch_smoothness(st, g, fx, fy, c->dpsis, half_alpha, two_frame_reg, 1, A + SP_PH * P, A + SP_PV * P);
+            } else {
+                launch_update_smoothness(st, g, fx, fy, pdu, pdv, c->dpsis, half_alpha, two_frame_reg, 1, ax, ay,
+                                         A + SP_PH * P, A + SP_PV * P);
+                std::swap(fx, ax);
+                std::swap(fy, ay);
+            }
+            cudaEvent_t ev;
+            c->prof_begin(PROF_DATA, ev);
+            launch_prep_two_frame(st, g, c->num_sms, d_im1, d_im2, fx, fy, nullptr, nullptr, A + SP_PH * P, A + SP_PV * P,
+                                  half_delta_over3, half_gamma_over3, A + SP_A11 * P, A + SP_A12 * P, A + SP_A22 * P,
+                                  A + SP_B1 * P, A + SP_B2 * P);
+            c->prof_end(PROF_DATA, ev);
+            c->prof_acc.data_launches++;
+            c->prof_acc.data_pixels += (long long)g.W * g.H;
+            c->prof_acc.kernel_launches += 2;
+            int cur = 0;
+            rc = run_sor(c, params->niter_solver, params->sor_omega, &cur, true); // variational.c:57
+            if (rc != SFGPU_OK) return rc;
+            pdu = A + (size_t)(cur ? SP_DUB : SP_DUA) * P;
+            pdv = A + (size_t)(cur ? SP_DVB : SP_DVA) * P;
+        }
+        if (pdu) {
+            launch_add(st, g, d_wx, fx, pdu);
+            launch_add(st, g, d_wy, fy, pdv);
+            c->prof_acc.kernel_launches += 2;
+        }
+        SF_CUDA(cudaGetLastError());
+        return SFGPU_OK;
+    }
     for (int outer = 0; outer < params->niter_outer; outer++) {
         if (!fused_prep) {
             launch_warp(st, g, d_im2, d_wx, d_wy, 1, c->wim, c->mask); // variational.c:40

@@ -51,6 +51,10 @@ void launch_warp(cudaStream_t st, Geom g, const float *src3, const float *wx, co
 // K3: smoothness diffusivities.  reg.type < 0: two-frame form (variational_aux.c:84), else MT modes 0/1.
 void launch_smoothness(cudaStream_t st, Geom g, const float *uu, const float *vv, const float *w, float alpha_factor,
                        Penalty reg, int mode, float *ph, float *pv);
+// K3 fused with the flow update: smoothness of (wx + du, wy + dv), which is also stored to (wx_out, wy_out)
+void launch_update_smoothness(cudaStream_t st, Geom g, const float *wx, const float *wy, const float *du, const float *dv,
+                              const float *w, float alpha_factor, Penalty reg, int mode, float *wx_out, float *wy_out,
+                              float *ph, float *pv);
 // K2: derivatives + robust data term of ONE term, fused (sf_data.cu).  A term pairs two colour images:
 //   m = 0.5*(B + A) (spatial derivatives are taken on it), z = zsign>0 ? B - A : A - B (temporal difference).
 enum DataKind { DK_TWO_FRAME = 0, DK_MT_SUCC = 1, DK_MT_REF = 2 };

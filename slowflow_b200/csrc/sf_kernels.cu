@@ -103,69 +103,143 @@ void launch_warp(cudaStream_t st, Geom g, const float *src3, const float *wx, co
 // ------------------------------------------------------------------------------------------ K3
 // psi_h(i,j): edge (i,j)-(i+1,j); psi_v(i,j): edge (i,j)-(i,j+1).  3-tap central differences
 // [-0.5, 0, 0.5] with image.c:400-423 vertical border folding and clamped horizontal reads.
-__device__ __forceinline__ float hdiff3(float m1, float s0, float p1) { return -0.5f * m1 + (-0.0f) * s0 + 0.5f * p1; }
-__device__ __forceinline__ float vdiff3(float m1, float s0, float p1, int j, int H) {
-    if (j == 0) return (-0.5f + -0.0f) * s0 + 0.5f * p1;
-    if (j == H - 1) return -0.5f * m1 + (-0.0f + 0.5f) * s0;
-    return -0.5f * m1 + (-0.0f) * s0 + 0.5f * p1;
+//
+// One thread owns 4 consecutive pixels of one row: the 3x6 neighbourhood of the flow comes from float4 loads of rows
+// j-1, j, j+1 plus the neighbouring lanes' edge columns (warp shuffle; the two outer lanes of a warp load theirs).
+// UPDATE: the flow is uu = wx + du, vv = wy + dv (variational.c:60-61 / :68-69 for niter_inner == 1) -- the sum is
+// formed on the fly, stored to (wx_out, wy_out) (a different buffer: neighbouring rows are read by other CTAs) and the
+// separate flow-update pass disappears.
+struct Row6 {
+    float c[6]; // columns i4-1 .. i4+4, clamped to the image
+};
+template <bool UPDATE>
+__device__ __forceinline__ float4 load_flow4(const float *__restrict__ w, const float *__restrict__ d, size_t o) {
+    float4 a = *reinterpret_cast<const float4 *>(w + o);
+    if (UPDATE) {
+        const float4 b = *reinterpret_cast<const float4 *>(d + o);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    return a;
+}
+template <bool UPDATE>
+__device__ __forceinline__ float load_flow1(const float *__restrict__ w, const float *__restrict__ d, size_t o) {
+    return UPDATE ? w[o] + d[o] : w[o];
+}
+// row `r` of the (updated) flow around columns i4..i4+3; raw = the unclamped float4 (what the update stores)
+template <bool UPDATE>
+__device__ __forceinline__ Row6 load_row6(const Geom &g, const float *__restrict__ w, const float *__restrict__ d, int r,
+                                          int i4, int lane, float4 *raw) {
+    const size_t ro = (size_t)r * g.S;
+    const float4 a = load_flow4<UPDATE>(w, d, ro + i4);
+    if (raw) *raw = a;
+    const int W1 = g.W - 1;
+    Row6 q;
+    q.c[1] = a.x; q.c[2] = a.y; q.c[3] = a.z; q.c[4] = a.w;
+    // columns beyond W-1 (stride padding) replicate column W-1, which lies in this float4 (S - W <= 3)
+    if (i4 + 3 > W1) {
+        const float last = (W1 - i4 == 0) ? a.x : (W1 - i4 == 1) ? a.y : a.z;
+        if (i4 + 1 > W1) q.c[2] = last;
+        if (i4 + 2 > W1) q.c[3] = last;
+        q.c[4] = last;
+    }
+    const float from_l = __shfl_up_sync(0xffffffffu, q.c[4], 1), from_r = __shfl_down_sync(0xffffffffu, q.c[1], 1);
+    if (i4 == 0) q.c[0] = q.c[1];
+    else q.c[0] = (lane > 0) ? from_l : load_flow1<UPDATE>(w, d, ro + i4 - 1);
+    if (i4 + 4 > W1) q.c[5] = q.c[4];
+    else q.c[5] = (lane < 31) ? from_r : load_flow1<UPDATE>(w, d, ro + i4 + 4);
+    return q;
 }
 
-__global__ void __launch_bounds__(256) k_smoothness(Geom g, const float *__restrict__ uu, const float *__restrict__ vv,
-                                                    const float *__restrict__ w, float alpha_factor, Penalty reg,
-                                                    int mode, float *__restrict__ ph, float *__restrict__ pv) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Central differences: with the rows / columns clamped at load time, -0.5*m + (-0)*c + 0.5*p (and its border-folded
+// forms, image.c:400-423) equals 0.5*(p - m) exactly (scaling by 0.5 is exact), and the average of two of them is
+// 0.25*((p - m) + (p' - m')).
+// TWO_FRAME: (w + w')*half_alpha / sqrt(s^2 + 1e-6) (variational_aux.c:124,139) as a product with MUFU.RSQ (2 ulp;
+// the reference rounds a double quotient once) -- otherwise the pluggable penalty of variational_aux_mt.cpp:65,90.
+template <bool TWO_FRAME>
+__device__ __forceinline__ float edge_weight(const Penalty &reg, float ww, float alpha_factor, float ssq) {
+    if (TWO_FRAME) return ww * alpha_factor * rsqrtf(ssq + 0.001f * 0.001f);
+    return smooth_weight(reg, ww, alpha_factor, ssq);
+}
+
+template <bool UPDATE, bool TWO_FRAME>
+__global__ void __launch_bounds__(256) k_flow_smooth(Geom g, const float *__restrict__ wx, const float *__restrict__ wy,
+                                                     const float *__restrict__ du, const float *__restrict__ dv,
+                                                     const float *__restrict__ w, float alpha_factor, Penalty reg, int mode,
+                                                     float *__restrict__ wx_out, float *__restrict__ wy_out,
+                                                     float *__restrict__ ph, float *__restrict__ pv) {
+    const int lane = threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= g.S || j >= g.H) return;
-    const size_t o = (size_t)j * g.S + i;
-    float h = 0.0f, v = 0.0f;
-    if (i < g.W) {
-        const int W1 = g.W - 1, H1 = g.H - 1;
-        auto U = [&](int x, int y) { return uu[(size_t)clampi(y, 0, H1) * g.S + clampi(x, 0, W1)]; };
-        auto V = [&](int x, int y) { return vv[(size_t)clampi(y, 0, H1) * g.S + clampi(x, 0, W1)]; };
-        const float u00 = U(i, j), v00 = V(i, j);
-        if (i < g.W - 1) {
-            const float ux1 = U(i + 1, j) - u00, vx1 = V(i + 1, j) - v00;
-            float tu = 0.0f, tv = 0.0f;
-            if (mode != 0) {
-                const float uy2a = vdiff3(U(i, j - 1), u00, U(i, j + 1), j, g.H);
-                const float uy2b = vdiff3(U(i + 1, j - 1), U(i + 1, j), U(i + 1, j + 1), j, g.H);
-                const float vy2a = vdiff3(V(i, j - 1), v00, V(i, j + 1), j, g.H);
-                const float vy2b = vdiff3(V(i + 1, j - 1), V(i + 1, j), V(i + 1, j + 1), j, g.H);
-                tu = 0.5f * (uy2a + uy2b);
-                tv = 0.5f * (vy2a + vy2b);
-            }
+    if (j >= g.H) return; // warp-uniform (a warp is one row segment)
+    int i4 = (blockIdx.x * 32 + lane) * 4;
+    const bool live = i4 < g.S;
+    if (!live) i4 = g.S - 4; // keep the lane in the shuffles with a valid address
+    const int H1 = g.H - 1, W1 = g.W - 1;
+    const int jm = j > 0 ? j - 1 : 0, jp = j < H1 ? j + 1 : H1;
+    float4 ru, rv;
+    const Row6 Um = load_row6<UPDATE>(g, wx, du, jm, i4, lane, nullptr), U0 = load_row6<UPDATE>(g, wx, du, j, i4, lane, &ru),
+               Up = load_row6<UPDATE>(g, wx, du, jp, i4, lane, nullptr);
+    const Row6 Vm = load_row6<UPDATE>(g, wy, dv, jm, i4, lane, nullptr), V0 = load_row6<UPDATE>(g, wy, dv, j, i4, lane, &rv),
+               Vp = load_row6<UPDATE>(g, wy, dv, jp, i4, lane, nullptr);
+    const size_t o = (size_t)j * g.S + i4;
+    // smoothness weights: row j columns i4..i4+4, row j+1 columns i4..i4+3
+    float w0[5], w1[4];
+    {
+        const float4 a = *reinterpret_cast<const float4 *>(w + o);
+        w0[0] = a.x; w0[1] = a.y; w0[2] = a.z; w0[3] = a.w;
+        const float from_r = __shfl_down_sync(0xffffffffu, a.x, 1);
+        w0[4] = (lane < 31) ? from_r : ((i4 + 4 <= W1) ? w[o + 4] : 0.0f);
+        const float4 b = *reinterpret_cast<const float4 *>(w + (size_t)jp * g.S + i4);
+        w1[0] = b.x; w1[1] = b.y; w1[2] = b.z; w1[3] = b.w;
+    }
+    if (!live) return;
+    const float cross = (mode != 0) ? 0.25f : 0.0f; // mode 0 (variational_aux_mt.cpp:30-60): forward differences only
+    float h[4], v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = i4 + k;
+        const float u00 = U0.c[k + 1], v00 = V0.c[k + 1];
+        {
+            const float ux1 = U0.c[k + 2] - u00, vx1 = V0.c[k + 2] - v00;
+            const float tu = cross * ((Up.c[k + 1] - Um.c[k + 1]) + (Up.c[k + 2] - Um.c[k + 2]));
+            const float tv = cross * ((Vp.c[k + 1] - Vm.c[k + 1]) + (Vp.c[k + 2] - Vm.c[k + 2]));
             const float uxsq = ux1 * ux1 + tu * tu;
             const float vxsq = vx1 * vx1 + tv * tv;
-            const float ssq = uxsq + vxsq;
-            const float ww = w[o] + w[o + 1];
-            h = smooth_weight(reg, ww, alpha_factor, ssq);
+            h[k] = (i < W1) ? edge_weight<TWO_FRAME>(reg, w0[k] + w0[k + 1], alpha_factor, uxsq + vxsq) : 0.0f;
         }
-        if (j < g.H - 1) {
-            const float uy1 = U(i, j + 1) - u00, vy1 = V(i, j + 1) - v00;
-            float tu = 0.0f, tv = 0.0f;
-            if (mode != 0) {
-                const float ux2a = hdiff3(U(i - 1, j), u00, U(i + 1, j));
-                const float ux2b = hdiff3(U(i - 1, j + 1), U(i, j + 1), U(i + 1, j + 1));
-                const float vx2a = hdiff3(V(i - 1, j), v00, V(i + 1, j));
-                const float vx2b = hdiff3(V(i - 1, j + 1), V(i, j + 1), V(i + 1, j + 1));
-                tu = 0.5f * (ux2a + ux2b);
-                tv = 0.5f * (vx2a + vx2b);
-            }
+        {
+            const float uy1 = Up.c[k + 1] - u00, vy1 = Vp.c[k + 1] - v00;
+            const float tu = cross * ((U0.c[k + 2] - U0.c[k]) + (Up.c[k + 2] - Up.c[k]));
+            const float tv = cross * ((V0.c[k + 2] - V0.c[k]) + (Vp.c[k + 2] - Vp.c[k]));
             const float uysq = uy1 * uy1 + tu * tu;
             const float vysq = vy1 * vy1 + tv * tv;
-            const float ssq = uysq + vysq;
-            const float ww = w[o] + w[o + g.S];
-            v = smooth_weight(reg, ww, alpha_factor, ssq);
+            v[k] = (i < g.W && j < H1) ? edge_weight<TWO_FRAME>(reg, w0[k] + w1[k], alpha_factor, uysq + vysq) : 0.0f;
         }
     }
-    ph[o] = h;
-    pv[o] = v;
+    *reinterpret_cast<float4 *>(ph + o) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4 *>(pv + o) = make_float4(v[0], v[1], v[2], v[3]);
+    if (UPDATE) {
+        *reinterpret_cast<float4 *>(wx_out + o) = ru;
+        *reinterpret_cast<float4 *>(wy_out + o) = rv;
+    }
 }
 
 void launch_smoothness(cudaStream_t st, Geom g, const float *uu, const float *vv, const float *w, float alpha_factor,
                        Penalty reg, int mode, float *ph, float *pv) {
-    dim3 b(32, 8), grid((g.S + 31) / 32, (g.H + 7) / 8);
-    k_smoothness<<<grid, b, 0, st>>>(g, uu, vv, w, alpha_factor, reg, mode, ph, pv);
+    dim3 b(32, 8), grid((g.S / 4 + 31) / 32, (g.H + 7) / 8);
+    if (reg.type < 0)
+        k_flow_smooth<false, true><<<grid, b, 0, st>>>(g, uu, vv, nullptr, nullptr, w, alpha_factor, reg, mode, nullptr, nullptr, ph, pv);
+    else
+        k_flow_smooth<false, false><<<grid, b, 0, st>>>(g, uu, vv, nullptr, nullptr, w, alpha_factor, reg, mode, nullptr, nullptr, ph, pv);
+}
+
+void launch_update_smoothness(cudaStream_t st, Geom g, const float *wx, const float *wy, const float *du, const float *dv,
+                              const float *w, float alpha_factor, Penalty reg, int mode, float *wx_out, float *wy_out,
+                              float *ph, float *pv) {
+    dim3 b(32, 8), grid((g.S / 4 + 31) / 32, (g.H + 7) / 8);
+    if (reg.type < 0)
+        k_flow_smooth<true, true><<<grid, b, 0, st>>>(g, wx, wy, du, dv, w, alpha_factor, reg, mode, wx_out, wy_out, ph, pv);
+    else
+        k_flow_smooth<true, false><<<grid, b, 0, st>>>(g, wx, wy, du, dv, w, alpha_factor, reg, mode, wx_out, wy_out, ph, pv);
 }
 
 // ------------------------------------------------------------------------------------------ small operators
