@@ -154,8 +154,17 @@ typedef struct sfgpu_mt_stats_s {
     int outer_iterations;  /* total outer iterations executed over all levels / alternations */
     int sor_calls;         /* sor_coupled invocations */
     int graphcut_calls;    /* optimizeOcc invocations */
+    /* host wall-clock split of the call (milliseconds) */
+    double setup_ms;       /* workspace, uploads, pyramid (until the coarsest level starts) */
+    double graphcut_ms;    /* optimizeOcc: data costs + labelling, all calls */
+    double total_ms;
 } sfgpu_mt_stats_t;
 int sfgpu_get_mt_stats(sfgpu_ctx *ctx, sfgpu_mt_stats_t *out);
+
+/* Labelling step of optimizeOcc (variational_aux_mt.cpp:851-881: gco expansion on a grid graph with data costs
+ * d0/d1 per site and Potts weight alpha) as the exact binary min-cut the GPU path uses.  Host-only operator twin for
+ * tests: costs are dense w*h arrays, labels[p] in {0, 1}; int_terms selects gco's stock integer EnergyTermType. */
+int sfgpu_grid_mincut(int w, int h, const float *d0, const float *d1, float alpha, int int_terms, int *labels);
 
 /* ---- per-kernel timing (CUDA events on the context's stream) for bench.py's roofline ---- */
 typedef struct sfgpu_profile_s {

@@ -619,6 +619,24 @@ Img *resize_flow(const Img *src, int w, int h, float mul) { /* resize + image_mu
 
 extern "C" {
 
+/* labelling step of optimizeOcc alone (variational_aux_mt.cpp:851-881) on dense w*h cost arrays: the checker of the
+ * product's sfgpu_grid_mincut */
+int sfo_mincut(int w, int h, const float *d0, const float *d1, float alpha, int int_terms, int *labels) {
+    auto q = [&](double e) -> int64_t { return (int64_t)llround((int_terms ? (double)(int)e : e) * 16777216.0); };
+    sfo::GridCut gc(w, h);
+    const int64_t pair = q((double)alpha);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const int p = y * w + x;
+            gc.set_terminal(p, q((double)d1[p]), q((double)d0[p]));
+            if (x + 1 < w) gc.set_edge_right(p, pair);
+            if (y + 1 < h) gc.set_edge_down(p, pair);
+        }
+    gc.maxflow();
+    for (int p = 0; p < w * h; p++) labels[p] = gc.label(p);
+    return 0;
+}
+
 /* normalize (variational_mt.cpp:17-85) */
 int sfo_normalize(sfo_color_image_t *const *seq, int F, sfo_mt_params_t *p) {
     double avg[3] = {0, 0, 0}, sd[3] = {0, 0, 0};

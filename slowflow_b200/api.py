@@ -29,7 +29,8 @@ class Profile(C.Structure):
 
 class MTStats(C.Structure):
     _fields_ = [("levels", C.c_int), ("outer_iterations", C.c_int), ("sor_calls", C.c_int),
-                ("graphcut_calls", C.c_int)]
+                ("graphcut_calls", C.c_int), ("setup_ms", C.c_double), ("graphcut_ms", C.c_double),
+                ("total_ms", C.c_double)]
 
 
 # every symbol include/slowflow_gpu.h declares (checked by tests/test_abi.py)
@@ -40,7 +41,7 @@ ABI_SYMBOLS = [
     "sfgpu_host_unregister", "sfgpu_variational_mt", "sfgpu_normalize", "sfgpu_get_mt_stats", "sfgpu_profile_enable",
     "sfgpu_profile_reset", "sfgpu_profile_get", "sfgpu_image_warp", "sfgpu_compute_dpsis_weight",
     "sfgpu_compute_smoothness", "sfgpu_compute_data_and_match", "sfgpu_sub_laplacian", "sfgpu_sor_coupled",
-    "sfgpu_version",
+    "sfgpu_version", "sfgpu_grid_mincut",
 ]
 
 
@@ -91,6 +92,7 @@ def load_library(path=None):
                                                  C.c_float]
     lib.sfgpu_sub_laplacian.argtypes = [C.c_void_p, IP, IP, IP, IP]
     lib.sfgpu_sor_coupled.argtypes = [C.c_void_p, IP, IP, IP, IP, IP, IP, IP, IP, IP, C.c_int, C.c_float]
+    lib.sfgpu_grid_mincut.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_int, C.POINTER(C.c_int)]
     if path is None:
         _LIB = lib
     return lib

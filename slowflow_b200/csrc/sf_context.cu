@@ -307,6 +307,7 @@ void sfgpu_destroy(sfgpu_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (auto &p : c->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->ev_free) cudaEventDestroy(e);
+    if (c->mtw) sf::mt_work_free(c->mtw);
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
     if (c->h2d) cudaStreamDestroy(c->h2d);

@@ -4,6 +4,11 @@
 
 #include "sf_internal.cuh"
 
+namespace sf {
+struct MtWork; // multi-frame workspace (sf_mt.cu), kept between calls
+void mt_work_free(MtWork *w);
+} // namespace sf
+
 struct sfgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -39,6 +44,7 @@ struct sfgpu_ctx {
     sfgpu_profile_t prof_acc{};
 
     sfgpu_mt_stats_t mt_stats{};
+    sf::MtWork *mtw = nullptr;
 
     // helpers
     int ensure_workspace(sf::Geom geom);

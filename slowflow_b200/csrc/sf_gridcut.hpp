@@ -1,232 +1,233 @@
-// sf_gridcut.hpp -- exact s-t min-cut on a 4-connected W x H grid (Boykov-Kolmogorov search trees, integer
-// capacities), host side of the occlusion labelling step (Variational_AUX_MT::optimizeOcc,
-// variational_aux_mt.cpp:851-881).
+// sf_gridcut.hpp -- exact s-t min-cut on a 4-connected W x H grid with ONE neighbour capacity (binary Potts), host side
+// of the occlusion labelling step (Variational_AUX_MT::optimizeOcc, variational_aux_mt.cpp:851-881).
 //
-// The reference calls the un-vendored gco-v3.0 alpha-expansion here (README.md:33-34).  With two labels and a
-// Potts pairwise cost the energy is submodular, so one min-cut gives the optimum that expansion converges to
-// from the all-zero labelling.  The per-pixel data costs are evaluated on the GPU (sf_mt.cu);
-// only this graph search runs on the host -- SURVEY 8(f) ranks a device min-cut as the next step.
-// Labels are canonical: label 1 <=> the pixel can still reach the sink in the residual graph of a maximum
-// flow; costs are quantised to integers (x 2^24) so no floating-point residue can blur that set.
+// The reference calls the un-vendored gco-v3.0 alpha-expansion here (README.md:33-34).  With two labels and a Potts
+// pairwise cost the energy is submodular, so one min-cut gives the optimum that expansion converges to from the
+// all-zero labelling.  The per-pixel terminal capacities are evaluated AND quantised on the GPU
+// (k_occ_terminals, sf_mt.cu); only this graph search runs on the host.
+//
+// Shape of the instances (measured on the synthetic windows): the occlusion penalty makes almost every pixel prefer
+// label 0 (terminal capacity towards the source), a few percent sit on the sink.  The search is therefore rooted at the
+// sink only: a forest T of pixels with a non-saturated path to the sink grows over residual arcs; touching a pixel that
+// still has source capacity closes an augmenting path source -> pixel -> ... -> root -> sink.  Orphans are re-attached
+// as in Boykov-Kolmogorov (sink tree only, with their time-stamp / distance heuristics).  Work is proportional to the
+// explored forest, not to W*H; per call the O(W*H) part is four memsets.
+//   * arcs are implicit: f_right[p], f_down[p] = net flow p -> right / lower neighbour in [-cap, cap];
+//     residual(p -> q) = cap - f(p -> q).  No capacity arrays to initialise.
+//   * labels are canonical: label 1 <=> the pixel can still reach the sink in the residual graph of a maximum flow
+//     <=> it is in T at termination.  Capacities are integers (costs x 2^24), so that set is exact.
+// The object is kept by the context and reused (buffers grow, never shrink).
 #pragma once
 #include <stdint.h>
+#include <string.h>
 #include <vector>
 
 namespace sf {
 
-class GridCut {
+class SinkForestCut {
 public:
     typedef int64_t cap_t;
-    GridCut(int w, int h) : W(w), H(h), N(w * h), tr(N, 0), rc((size_t)N * 4, 0), parent(N, P_NONE), sink(N, 0),
-                            ts(N, 0), dist(N, 0), next(N, -1), qfirst{-1, -1}, qlast{-1, -1}, time_(0), flow_(0) {}
+    enum : uint8_t { P_LEFT = 0, P_RIGHT = 1, P_UP = 2, P_DOWN = 3, P_TERMINAL = 4, P_ORPHAN = 5, P_NONE = 6 };
 
-    // terminal capacities: source->p (paid when p ends on the sink side = label 1), p->sink (label 0)
-    void set_terminal(int p, cap_t cap_source, cap_t cap_sink) {
-        const cap_t m = cap_source < cap_sink ? cap_source : cap_sink;
-        flow_ += m;
-        tr[p] = cap_source - cap_sink;
+    // tr[p] = cap(source -> p) - cap(p -> sink) (> 0: source side preferred); pair = the neighbour capacity.
+    // On return in_forest()[p] != P_NONE  <=>  label 1.  tr is modified in place (residual terminal capacities).
+    cap_t solve(int w, int h, cap_t *tr_io, cap_t pair_cap) {
+        W = w; H = h; N = w * h; tr = tr_io; cap = pair_cap;
+        fr.assign((size_t)N, 0);
+        fd.assign((size_t)N, 0);
+        parent.assign((size_t)N, (uint8_t)P_NONE);
+        ts.assign((size_t)N, 0);
+        dist.resize((size_t)N);
+        queued.assign((size_t)N, 0);
+        active.clear();
+        head = 0;
+        orphans.clear();
+        ohead = 0;
+        time_ = 0;
+        flow_ = 0;
+        for (int p = 0; p < N; p++)
+            if (tr[p] < 0) {
+                parent[p] = P_TERMINAL;
+                dist[p] = 1;
+                push_active(p);
+            }
+        for (;;) {
+            const int i = pop_active();
+            if (i < 0) break;
+            grow(i);
+        }
+        return flow_;
     }
-    // symmetric neighbour capacity between p and its right (dir 1) / lower (dir 3) neighbour
-    void set_edge_right(int p, cap_t c) { rc[(size_t)p * 4 + 1] = c; rc[(size_t)(p + 1) * 4 + 0] = c; }
-    void set_edge_down(int p, cap_t c) { rc[(size_t)p * 4 + 3] = c; rc[(size_t)(p + W) * 4 + 2] = c; }
-
-    cap_t maxflow();
-    // 1 <=> sink side (can reach the sink in the residual graph)
-    int label(int p) const { return (parent[p] != P_NONE && sink[p]) ? 1 : 0; }
+    const uint8_t *in_forest() const { return parent.data(); }
+    int label(int p) const { return parent[p] != P_NONE ? 1 : 0; }
 
 private:
-    enum { P_TERMINAL = 4, P_ORPHAN = 5, P_NONE = 6 };
-    int W, H, N;
-    std::vector<cap_t> tr; // > 0: residual source->p ; < 0: residual p->sink
-    std::vector<cap_t> rc; // residual capacity of arc p -> neighbour(dir), dir 0 left, 1 right, 2 up, 3 down
-    std::vector<uint8_t> parent, sink;
-    std::vector<int> ts, dist, next;
-    int qfirst[2], qlast[2];
+    int W = 0, H = 0, N = 0;
+    cap_t *tr = nullptr;
+    cap_t cap = 0, flow_ = 0;
+    std::vector<cap_t> fr, fd;   // net flow towards the right / lower neighbour
+    std::vector<uint8_t> parent; // direction of the parent arc (towards the sink), or a P_* marker
+    std::vector<int> ts, dist;   // BK distance-to-terminal cache
+    std::vector<uint8_t> queued;
+    std::vector<int> active;
+    size_t head = 0;
     std::vector<int> orphans;
-    size_t orphan_head = 0;
-    int time_;
-    cap_t flow_;
+    size_t ohead = 0;
+    int time_ = 0;
 
     inline int nb(int p, int d) const {
         switch (d) {
-        case 0: return (p % W > 0) ? p - 1 : -1;
-        case 1: return (p % W < W - 1) ? p + 1 : -1;
-        case 2: return (p >= W) ? p - W : -1;
+        case P_LEFT: return (p % W > 0) ? p - 1 : -1;
+        case P_RIGHT: return (p % W < W - 1) ? p + 1 : -1;
+        case P_UP: return (p >= W) ? p - W : -1;
         default: return (p < N - W) ? p + W : -1;
         }
     }
-    inline cap_t &cap(int p, int d) { return rc[(size_t)p * 4 + d]; }
-    void set_active(int i) {
-        if (next[i] != -1) return;
-        next[i] = i; // end marker
-        if (qlast[1] >= 0) next[qlast[1]] = i; else qfirst[1] = i;
-        qlast[1] = i;
+    // residual capacity of the arc p -> nb(p, d) (the neighbour must exist)
+    inline cap_t res(int p, int d) const {
+        switch (d) {
+        case P_LEFT: return cap + fr[p - 1];
+        case P_RIGHT: return cap - fr[p];
+        case P_UP: return cap + fd[p - W];
+        default: return cap - fd[p];
+        }
     }
-    int next_active() {
-        for (;;) {
-            int i = qfirst[0];
-            if (i < 0) {
-                qfirst[0] = i = qfirst[1]; qlast[0] = qlast[1];
-                qfirst[1] = qlast[1] = -1;
-                if (i < 0) return -1;
+    inline void send(int p, int d, cap_t x) { // x units along p -> nb(p, d)
+        switch (d) {
+        case P_LEFT: fr[p - 1] -= x; break;
+        case P_RIGHT: fr[p] += x; break;
+        case P_UP: fd[p - W] -= x; break;
+        default: fd[p] += x; break;
+        }
+    }
+    void push_active(int i) {
+        if (queued[i]) return;
+        queued[i] = 1;
+        active.push_back(i);
+    }
+    int pop_active() {
+        while (head < active.size()) {
+            const int i = active[head++];
+            queued[i] = 0;
+            if (head > (1u << 16) && head * 2 > active.size()) {
+                active.erase(active.begin(), active.begin() + head);
+                head = 0;
             }
-            if (next[i] == i) qfirst[0] = qlast[0] = -1; else qfirst[0] = next[i];
-            next[i] = -1;
-            if (parent[i] != P_NONE) return i; // only nodes still in a tree are active
+            if (parent[i] != P_NONE) return i; // only forest members are active
         }
+        active.clear();
+        head = 0;
+        return -1;
     }
-    void push_orphan_front(int i) { parent[i] = P_ORPHAN; orphans.insert(orphans.begin() + orphan_head, i); }
-    void push_orphan_back(int i) { parent[i] = P_ORPHAN; orphans.push_back(i); }
-    void augment(int i, int d);
-    void process_orphan(int i, int is_sink);
-};
+    void make_orphan_front(int i) {
+        parent[i] = P_ORPHAN;
+        orphans.insert(orphans.begin() + ohead, i);
+    }
+    void make_orphan_back(int i) {
+        parent[i] = P_ORPHAN;
+        orphans.push_back(i);
+    }
 
-inline void GridCut::augment(int i_src, int d_mid) {
-    // middle arc: i_src (source tree) -> j_snk (sink tree) along direction d_mid
-    const int j_snk = nb(i_src, d_mid);
-    cap_t bottleneck = cap(i_src, d_mid);
-    for (int i = i_src;;) { // source tree: flow runs parent -> child, i.e. along sister of parent arc
-        const int pd = parent[i];
-        if (pd == P_TERMINAL) { if (tr[i] < bottleneck) bottleneck = tr[i]; break; }
-        const int p = nb(i, pd);
-        const cap_t r = cap(p, pd ^ 1);
-        if (r < bottleneck) bottleneck = r;
-        i = p;
+    // one augmentation: source -> j -> (arc d) -> i -> ... -> root -> sink
+    void augment(int j, int d) {
+        const int i0 = nb(j, d);
+        cap_t b = tr[j];
+        const cap_t mid = res(j, d);
+        if (mid < b) b = mid;
+        for (int i = i0;;) {
+            const int pd = parent[i];
+            if (pd == P_TERMINAL) {
+                if (-tr[i] < b) b = -tr[i];
+                break;
+            }
+            const cap_t r = res(i, pd);
+            if (r < b) b = r;
+            i = nb(i, pd);
+        }
+        tr[j] -= b;
+        send(j, d, b);
+        for (int i = i0;;) {
+            const int pd = parent[i];
+            if (pd == P_TERMINAL) {
+                tr[i] += b;
+                if (tr[i] == 0) make_orphan_front(i);
+                break;
+            }
+            const int up = nb(i, pd);
+            send(i, pd, b);
+            if (res(i, pd) == 0) make_orphan_front(i);
+            i = up;
+        }
+        flow_ += b;
     }
-    for (int i = j_snk;;) { // sink tree: flow runs child -> parent along the parent arc
-        const int pd = parent[i];
-        if (pd == P_TERMINAL) { if (-tr[i] < bottleneck) bottleneck = -tr[i]; break; }
-        const cap_t r = cap(i, pd);
-        if (r < bottleneck) bottleneck = r;
-        i = nb(i, pd);
-    }
-    cap(i_src, d_mid) -= bottleneck;
-    cap(j_snk, d_mid ^ 1) += bottleneck;
-    for (int i = i_src;;) {
-        const int pd = parent[i];
-        if (pd == P_TERMINAL) { tr[i] -= bottleneck; if (tr[i] == 0) push_orphan_front(i); break; }
-        const int p = nb(i, pd);
-        cap(i, pd) += bottleneck;
-        cap(p, pd ^ 1) -= bottleneck;
-        if (cap(p, pd ^ 1) == 0) push_orphan_front(i);
-        i = p;
-    }
-    for (int i = j_snk;;) {
-        const int pd = parent[i];
-        if (pd == P_TERMINAL) { tr[i] += bottleneck; if (tr[i] == 0) push_orphan_front(i); break; }
-        const int p = nb(i, pd);
-        cap(p, pd ^ 1) += bottleneck;
-        cap(i, pd) -= bottleneck;
-        if (cap(i, pd) == 0) push_orphan_front(i);
-        i = p;
-    }
-    flow_ += bottleneck;
-}
 
-inline void GridCut::process_orphan(int i, int is_sink) {
-    const int INF_D = 1 << 30;
-    int best_d = -1, best_dist = INF_D;
-    for (int d = 0; d < 4; d++) {
-        const int j = nb(i, d);
-        if (j < 0) continue;
-        // residual in the direction of flow: source tree j -> i, sink tree i -> j
-        const cap_t r = is_sink ? cap(i, d) : cap(j, d ^ 1);
-        if (r <= 0 || parent[j] == P_NONE || sink[j] != is_sink) continue;
-        // does j's path lead to the terminal?
-        int dd = 0, k = j;
-        for (;;) {
-            if (ts[k] == time_) { dd += dist[k]; break; }
-            const int pd = parent[k];
-            dd++;
-            if (pd == P_TERMINAL) { ts[k] = time_; dist[k] = 1; break; }
-            if (pd == P_ORPHAN || pd == P_NONE) { dd = INF_D; break; }
-            k = nb(k, pd);
+    void adopt(int i) {
+        const int INF_D = 1 << 30;
+        int best_d = -1, best_dist = INF_D;
+        for (int d = 0; d < 4; d++) {
+            const int j = nb(i, d);
+            if (j < 0 || parent[j] == P_NONE || res(i, d) <= 0) continue;
+            int dd = 0, k = j; // does j still hang on the sink?
+            for (;;) {
+                if (ts[k] == time_) { dd += dist[k]; break; }
+                const int pd = parent[k];
+                dd++;
+                if (pd == P_TERMINAL) { ts[k] = time_; dist[k] = 1; break; }
+                if (pd == P_ORPHAN || pd == P_NONE) { dd = INF_D; break; }
+                k = nb(k, pd);
+            }
+            if (dd < INF_D) {
+                if (dd < best_dist) { best_dist = dd; best_d = d; }
+                for (k = j; ts[k] != time_; k = nb(k, parent[k])) { ts[k] = time_; dist[k] = dd--; }
+            }
         }
-        if (dd < INF_D) {
-            if (dd < best_dist) { best_dist = dd; best_d = d; }
-            for (k = j; ts[k] != time_; k = nb(k, parent[k])) { ts[k] = time_; dist[k] = dd--; }
+        if (best_d >= 0) {
+            parent[i] = (uint8_t)best_d;
+            ts[i] = time_;
+            dist[i] = best_dist + 1;
+            return;
+        }
+        parent[i] = P_NONE; // leaves the forest: neighbours may grab it again, its children lose their path
+        for (int d = 0; d < 4; d++) {
+            const int j = nb(i, d);
+            if (j < 0 || parent[j] == P_NONE) continue;
+            if (res(i, d) > 0) push_active(j);
+            const int pd = parent[j];
+            if (pd < 4 && nb(j, pd) == i) make_orphan_back(j);
         }
     }
-    if (best_d >= 0) {
-        parent[i] = (uint8_t)best_d;
-        ts[i] = time_;
-        dist[i] = best_dist + 1;
-        return;
-    }
-    parent[i] = P_NONE;
-    for (int d = 0; d < 4; d++) {
-        const int j = nb(i, d);
-        if (j < 0 || parent[j] == P_NONE || sink[j] != is_sink) continue;
-        const cap_t r = is_sink ? cap(i, d) : cap(j, d ^ 1);
-        if (r > 0) set_active(j);
-        const int pd = parent[j];
-        if (pd < 4 && nb(j, pd) == i) push_orphan_back(j);
-    }
-}
 
-inline GridCut::cap_t GridCut::maxflow() {
-    for (int i = 0; i < N; i++) {
-        if (tr[i] > 0) { sink[i] = 0; parent[i] = P_TERMINAL; dist[i] = 1; ts[i] = 0; set_active(i); }
-        else if (tr[i] < 0) { sink[i] = 1; parent[i] = P_TERMINAL; dist[i] = 1; ts[i] = 0; set_active(i); }
-        else parent[i] = P_NONE;
-    }
-    int current = -1;
-    for (;;) {
-        int i = current;
-        if (i >= 0) {
-            next[i] = -1;
-            if (parent[i] == P_NONE) i = -1;
-        }
-        if (i < 0) {
-            i = next_active();
-            if (i < 0) break;
-        }
-        int found_src = -1, found_dir = -1;
-        if (!sink[i]) {
-            for (int d = 0; d < 4 && found_src < 0; d++) {
+    void grow(int i) {
+        for (;;) { // stays on i while it keeps closing augmenting paths
+            int found = -1, found_d = -1;
+            for (int d = 0; d < 4 && found < 0; d++) {
                 const int j = nb(i, d);
-                if (j < 0 || cap(i, d) <= 0) continue;
+                if (j < 0) continue;
+                const int back = d ^ 1; // arc j -> i
+                if (res(j, back) <= 0) continue;
                 if (parent[j] == P_NONE) {
-                    sink[j] = 0; parent[j] = (uint8_t)(d ^ 1); ts[j] = ts[i]; dist[j] = dist[i] + 1; set_active(j);
-                } else if (sink[j]) {
-                    found_src = i; found_dir = d;
-                } else if (ts[j] <= ts[i] && dist[j] > dist[i]) {
-                    parent[j] = (uint8_t)(d ^ 1); ts[j] = ts[i]; dist[j] = dist[i] + 1;
+                    if (tr[j] > 0) { found = j; found_d = back; }
+                    else { parent[j] = (uint8_t)back; ts[j] = ts[i]; dist[j] = dist[i] + 1; push_active(j); }
+                } else if (parent[j] != P_ORPHAN && ts[j] <= ts[i] && dist[j] > dist[i]) {
+                    parent[j] = (uint8_t)back; ts[j] = ts[i]; dist[j] = dist[i] + 1; // shorter route to the sink
                 }
             }
-        } else {
-            for (int d = 0; d < 4 && found_src < 0; d++) {
-                const int j = nb(i, d);
-                if (j < 0 || cap(j, d ^ 1) <= 0) continue;
-                if (parent[j] == P_NONE) {
-                    sink[j] = 1; parent[j] = (uint8_t)(d ^ 1); ts[j] = ts[i]; dist[j] = dist[i] + 1; set_active(j);
-                } else if (!sink[j]) {
-                    found_src = j; found_dir = d ^ 1;
-                } else if (ts[j] <= ts[i] && dist[j] > dist[i]) {
-                    parent[j] = (uint8_t)(d ^ 1); ts[j] = ts[i]; dist[j] = dist[i] + 1;
+            time_++;
+            if (found < 0) return;
+            augment(found, found_d);
+            while (ohead < orphans.size()) {
+                const int o = orphans[ohead++];
+                if (ohead > 4096 && ohead * 2 > orphans.size()) {
+                    orphans.erase(orphans.begin(), orphans.begin() + ohead);
+                    ohead = 0;
                 }
-            }
-        }
-        time_++;
-        if (found_src >= 0) {
-            next[i] = i; // keep i active
-            current = i;
-            augment(found_src, found_dir);
-            while (orphan_head < orphans.size()) {
-                const int o = orphans[orphan_head++];
-                if (orphan_head > 4096 && orphan_head * 2 > orphans.size()) {
-                    orphans.erase(orphans.begin(), orphans.begin() + orphan_head);
-                    orphan_head = 0;
-                }
-                process_orphan(o, sink[o]);
+                adopt(o);
             }
             orphans.clear();
-            orphan_head = 0;
-        } else {
-            current = -1;
+            ohead = 0;
+            if (parent[i] == P_NONE) return; // i itself lost its path
         }
     }
-    return flow_;
-}
+};
 
 } // namespace sf

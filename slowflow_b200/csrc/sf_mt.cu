@@ -14,9 +14,11 @@
 #include "sf_context.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "sf_gridcut.hpp"
@@ -78,7 +80,14 @@ struct OccArgs {
     float delta_over3, gamma_over3, penalty;
     Penalty pc, pg;
 };
-__global__ void __launch_bounds__(256) k_occ_costs(Geom g, OccArgs a, float *__restrict__ d0, float *__restrict__ d1) {
+// The two data costs are quantised exactly like the labelling step does on the host (x 2^24, round half away from zero;
+// gco's stock int EnergyTermType truncates the cost first) and only their difference leaves the GPU:
+// tr[y*W + x] = q(d1) - q(d0) = cap(source -> p) - cap(p -> sink) of SinkForestCut (sf_gridcut.hpp).
+__device__ __forceinline__ long long occ_quantise(float e, int int_terms) {
+    return llround((int_terms ? (double)(int)e : (double)e) * 16777216.0);
+}
+__global__ void __launch_bounds__(256) k_occ_costs(Geom g, OccArgs a, float *__restrict__ d0, float *__restrict__ d1,
+                                                   long long *__restrict__ tr, int int_terms) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= g.W || j >= g.H) return;
@@ -116,8 +125,20 @@ __global__ void __launch_bounds__(256) k_occ_costs(Geom g, OccArgs a, float *__r
     }
     if (nrm[0] == 0.f) nrm[0] = 1.f;
     if (nrm[1] == 0.f) nrm[1] = 1.f;
-    d0[o] = 0.01f * e[0] / nrm[0] + a.penalty * 0.0f;
-    d1[o] = 0.01f * e[1] / nrm[1] + a.penalty * 1.0f;
+    const float c0 = 0.01f * e[0] / nrm[0] + a.penalty * 0.0f;
+    const float c1 = 0.01f * e[1] / nrm[1] + a.penalty * 1.0f;
+    if (d0) { d0[o] = c0; d1[o] = c1; }
+    if (tr) tr[(size_t)j * g.W + i] = occ_quantise(c1, int_terms) - occ_quantise(c0, int_terms);
+}
+
+// labels of the min-cut (forest membership bytes, dense W*H) -> occlusion plane: +1 in the forest, -1 outside, 0 in
+// the stride padding (variational_aux_mt.cpp:879)
+__global__ void __launch_bounds__(256) k_occ_labels(Geom g, const unsigned char *__restrict__ member, unsigned char none,
+                                                    float *__restrict__ occ) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.S || j >= g.H) return;
+    occ[(size_t)j * g.S + i] = (i < g.W) ? (member[(size_t)j * g.W + i] != none ? 1.0f : -1.0f) : 0.0f;
 }
 
 // separable Gaussian (replicate border), symmetric-sum evaluation like cv::GaussianBlur's float path
@@ -212,18 +233,56 @@ struct MtLevel {
     std::vector<float *> frames; // F colour images (3 planes each)
 };
 
+// Per-context multi-frame workspace; kept between calls (buffers only grow).
 struct MtWork {
     float *pool = nullptr;
     size_t pool_floats = 0;
     float *part_dev = nullptr;
     float *part_host = nullptr; // pinned
     size_t part_cap = 0;
-    ~MtWork() {
+    long long *tr_host = nullptr; // pinned: terminal capacities of the occlusion min-cut
+    unsigned char *lab_dev = nullptr;
+    size_t cut_nodes = 0;
+    SinkForestCut cut;
+    ~MtWork() { release(); }
+    void release() {
         if (pool) cudaFree(pool);
         if (part_dev) cudaFree(part_dev);
         if (part_host) cudaFreeHost(part_host);
+        if (tr_host) cudaFreeHost(tr_host);
+        if (lab_dev) cudaFree(lab_dev);
+        pool = part_dev = part_host = nullptr;
+        tr_host = nullptr;
+        lab_dev = nullptr;
+        pool_floats = part_cap = cut_nodes = 0;
+    }
+    int reserve(size_t floats, size_t partials, size_t nodes) {
+        if (floats > pool_floats) {
+            if (pool) cudaFree(pool);
+            pool = nullptr; pool_floats = 0;
+            SF_CUDA(cudaMalloc(&pool, floats * sizeof(float)));
+            pool_floats = floats;
+        }
+        if (partials > part_cap) {
+            if (part_dev) cudaFree(part_dev);
+            if (part_host) cudaFreeHost(part_host);
+            part_dev = part_host = nullptr; part_cap = 0;
+            SF_CUDA(cudaMalloc(&part_dev, partials * sizeof(float)));
+            SF_CUDA(cudaMallocHost(&part_host, partials * sizeof(float)));
+            part_cap = partials;
+        }
+        if (nodes > cut_nodes) {
+            if (tr_host) cudaFreeHost(tr_host);
+            if (lab_dev) cudaFree(lab_dev);
+            tr_host = nullptr; lab_dev = nullptr; cut_nodes = 0;
+            SF_CUDA(cudaMallocHost(&tr_host, nodes * sizeof(long long)));
+            SF_CUDA(cudaMalloc(&lab_dev, nodes));
+            cut_nodes = nodes;
+        }
+        return SFGPU_OK;
     }
 };
+void mt_work_free(MtWork *w) { delete w; }
 
 static BlurTaps make_taps(double sigma) {
     // cv::getGaussianKernel: n = cvRound(8 sigma + 1) | 1 for CV_32F, exp(-x^2 / 2 sigma^2) normalised
@@ -280,8 +339,17 @@ static void warp_all(LevelCtx &L) { // Variational_MT::get_derivatives, warping 
     }
 }
 
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static SinkForestCut::cap_t occ_quantise_host(double e, bool int_terms) {
+    return (SinkForestCut::cap_t)llround((int_terms ? (double)(int)e : e) * 16777216.0);
+}
+
 static int optimize_occ(LevelCtx &L) { // variational_aux_mt.cpp:758-887
     const Geom g = L.g;
+    const double t_begin = now_ms();
     OccArgs a;
     memset(&a, 0, sizeof(a));
     const int F = 2 * L.ref + 1;
@@ -293,32 +361,26 @@ static int optimize_occ(LevelCtx &L) { // variational_aux_mt.cpp:758-887
     a.penalty = L.p->occlusion_penalty;
     a.pc = L.pc;
     a.pg = L.pg;
-    k_occ_costs<<<grid2d(g.W, g.H), dim3(32, 8), 0, L.c->stream>>>(g, a, L.d0, L.d1);
+    // d0,d1 are two consecutive planes: reused as the dense W*H array of 64-bit terminal capacities
+    const bool int_terms = L.p->graphcut_int_terms != 0;
+    long long *tr_dev = reinterpret_cast<long long *>(L.d0);
+    MtWork &wk = *L.work;
+    const size_t N = (size_t)g.W * g.H;
+    k_occ_costs<<<grid2d(g.W, g.H), dim3(32, 8), 0, L.c->stream>>>(g, a, nullptr, nullptr, tr_dev, int_terms ? 1 : 0);
     L.c->prof_acc.kernel_launches++;
-    const size_t P = g.plane();
-    std::vector<float> h0(P), h1(P), hocc(P, 0.0f);
-    SF_CUDA(cudaMemcpyAsync(h0.data(), L.d0, P * sizeof(float), cudaMemcpyDeviceToHost, L.c->stream));
-    SF_CUDA(cudaMemcpyAsync(h1.data(), L.d1, P * sizeof(float), cudaMemcpyDeviceToHost, L.c->stream));
+    SF_CUDA(cudaMemcpyAsync(wk.tr_host, tr_dev, N * sizeof(long long), cudaMemcpyDeviceToHost, L.c->stream));
     SF_CUDA(cudaStreamSynchronize(L.c->stream));
     // binary Potts labelling = one min-cut (gco stand-in semantics; int EnergyTermType optional)
-    const bool int_terms = L.p->graphcut_int_terms != 0;
-    auto q = [&](double e) -> int64_t { return (int64_t)llround((int_terms ? (double)(int)e : e) * 16777216.0); };
-    GridCut gc(g.W, g.H);
-    const int64_t pair = q((double)L.p->occlusion_alpha);
-    for (int y = 0; y < g.H; y++)
-        for (int x = 0; x < g.W; x++) {
-            const int pnode = y * g.W + x;
-            const size_t o = (size_t)y * g.S + x;
-            gc.set_terminal(pnode, q((double)h1[o]), q((double)h0[o]));
-            if (x + 1 < g.W) gc.set_edge_right(pnode, pair);
-            if (y + 1 < g.H) gc.set_edge_down(pnode, pair);
-        }
-    gc.maxflow();
-    for (int y = 0; y < g.H; y++)
-        for (int x = 0; x < g.W; x++) hocc[(size_t)y * g.S + x] = (float)(2 * gc.label(y * g.W + x) - 1); // :879
-    SF_CUDA(cudaMemcpyAsync(L.occ, hocc.data(), P * sizeof(float), cudaMemcpyHostToDevice, L.c->stream));
-    SF_CUDA(cudaStreamSynchronize(L.c->stream));
+    const double t_flow = now_ms();
+    wk.cut.solve(g.W, g.H, reinterpret_cast<SinkForestCut::cap_t *>(wk.tr_host), occ_quantise_host((double)L.p->occlusion_alpha, int_terms));
+    if (getenv("SLOWFLOW_GPU_TRACE"))
+        fprintf(stderr, "optimize_occ %dx%d: costs+d2h %.2f ms, min-cut %.2f ms\n", g.W, g.H, t_flow - t_begin, now_ms() - t_flow);
+    SF_CUDA(cudaMemcpyAsync(wk.lab_dev, wk.cut.in_forest(), N, cudaMemcpyHostToDevice, L.c->stream));
+    k_occ_labels<<<grid2d(g.S, g.H), dim3(32, 8), 0, L.c->stream>>>(g, wk.lab_dev, (unsigned char)SinkForestCut::P_NONE, L.occ);
+    L.c->prof_acc.kernel_launches++;
+    SF_CUDA(cudaStreamSynchronize(L.c->stream)); // the forest bytes are read by the copy above
     L.c->mt_stats.graphcut_calls++;
+    L.c->mt_stats.graphcut_ms += now_ms() - t_begin;
     return SFGPU_OK;
 }
 
@@ -490,6 +552,20 @@ void sf_mt_params_default(sf_mt_params_t *p) { // slow_flow.cpp:64-128 (setDefau
     for (int k = 0; k < 3; k++) { p->img_norm_avg[k] = 0.0f; p->img_norm_std[k] = 1.0f; }
 }
 
+int sfgpu_grid_mincut(int w, int h, const float *d0, const float *d1, float alpha, int int_terms, int *labels) {
+    if (w <= 0 || h <= 0 || !d0 || !d1 || !labels) {
+        set_error("sfgpu_grid_mincut: bad argument");
+        return SFGPU_ERR_ARG;
+    }
+    const size_t n = (size_t)w * h;
+    std::vector<SinkForestCut::cap_t> tr(n);
+    for (size_t p = 0; p < n; p++) tr[p] = occ_quantise_host((double)d1[p], int_terms != 0) - occ_quantise_host((double)d0[p], int_terms != 0);
+    SinkForestCut cut;
+    cut.solve(w, h, tr.data(), occ_quantise_host((double)alpha, int_terms != 0));
+    for (size_t p = 0; p < n; p++) labels[p] = cut.label((int)p);
+    return SFGPU_OK;
+}
+
 int sfgpu_get_mt_stats(sfgpu_ctx *c, sfgpu_mt_stats_t *out) {
     if (!c || !out) return SFGPU_ERR_ARG;
     *out = c->mt_stats;
@@ -578,6 +654,7 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
     SF_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     memset(&c->mt_stats, 0, sizeof(c->mt_stats));
+    const double t_call = now_ms();
     if (avg_change_out) avg_change_out[0] = avg_change_out[1] = 0.f;
 
     // ---- pyramid geometry (variational_mt.cpp:583-652): floor((float)w * p_scale); a level is dropped when
@@ -605,12 +682,12 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
     for (int l = 0; l < L; l++) frame_floats += (size_t)F * 3 * geoms[l].plane();
     const size_t work_planes = (size_t)(F - 1) * 3 + (F - 1) + 2 /*wx wy*/ + 2 /*wx,wy of next level*/ + 2 /*uu vv*/ + 2 /*odu odv*/ + 1 /*dpsis*/ +
                                1 /*occ*/ + 2 /*d0 d1*/ + 3 /*blur tmp*/ + (channel_w ? 3 : 0);
-    MtWork work;
-    work.pool_floats = frame_floats + work_planes * P0;
-    SF_CUDA(cudaMalloc(&work.pool, work.pool_floats * sizeof(float)));
-    work.part_cap = (size_t)((g0.W + 31) / 32) * 64 * 4;
-    SF_CUDA(cudaMalloc(&work.part_dev, work.part_cap * sizeof(float)));
-    SF_CUDA(cudaMallocHost(&work.part_host, work.part_cap * sizeof(float)));
+    if (!c->mtw) c->mtw = new MtWork();
+    MtWork &work = *c->mtw;
+    {
+        const int rcw = work.reserve(frame_floats + work_planes * P0, (size_t)((g0.W + 31) / 32) * 64 * 4, (size_t)g0.W * g0.H);
+        if (rcw != SFGPU_OK) return rcw;
+    }
     float *ptr = work.pool;
     std::vector<MtLevel> levels(L);
     for (int l = 0; l < L; l++) {
@@ -665,6 +742,7 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
     }
     float avg_change[2] = {0.f, 0.f};
     int rc = c->ensure_workspace(g0); // size the level workspace once for the finest level
+    if (cudaStreamSynchronize(st) == cudaSuccess) c->mt_stats.setup_ms = now_ms() - t_call;
     for (int l = L - 1; l >= 0 && rc == SFGPU_OK; l--) {
         const Geom g = geoms[l];
         if (l < L - 1) { // up-sample the flow of level l+1 and scale the vectors (:687-722)
@@ -705,6 +783,7 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
         SF_CUDA(cudaMemcpyAsync(occlusions_out->data, occ, P0 * sizeof(float), cudaMemcpyDeviceToHost, st));
     SF_CUDA(cudaStreamSynchronize(st));
     if (avg_change_out) { avg_change_out[0] = avg_change[0]; avg_change_out[1] = avg_change[1]; }
+    c->mt_stats.total_ms = now_ms() - t_call;
     return SFGPU_OK;
 }
 

@@ -1,0 +1,87 @@
+"""Host min-cut of the occlusion labelling step (slowflow_b200/csrc/sf_gridcut.hpp, sink-rooted search forest)
+against brute force and against the oracle's full Boykov-Kolmogorov restatement (oracle/sfo_gridcut.hpp).
+
+Labels are canonical (minimal sink side of a maximum flow), so two exact algorithms must agree on EVERY pixel,
+not only on the energy.  No GPU is needed: sfgpu_grid_mincut is a host-only operator twin of the labelling inside
+Variational_AUX_MT::optimizeOcc (variational_aux_mt.cpp:851-881)."""
+import ctypes as C
+import itertools
+
+import numpy as np
+import pytest
+
+from slowflow_b200.api import load_library
+
+FP, IP = C.POINTER(C.c_float), C.POINTER(C.c_int)
+
+
+def product_cut(w, h, d0, d1, alpha, int_terms=0):
+    lib = load_library()
+    lab = np.full(w * h, -7, np.int32)
+    rc = lib.sfgpu_grid_mincut(w, h, d0.ctypes.data_as(FP), d1.ctypes.data_as(FP), C.c_float(alpha), int_terms,
+                               lab.ctypes.data_as(IP))
+    assert rc == 0
+    return lab
+
+
+def oracle_cut(oracle, w, h, d0, d1, alpha, int_terms=0):
+    L = oracle.lib
+    L.sfo_mincut.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_int, IP]
+    lab = np.full(w * h, -7, np.int32)
+    assert L.sfo_mincut(w, h, d0.ctypes.data_as(FP), d1.ctypes.data_as(FP), C.c_float(alpha), int_terms,
+                        lab.ctypes.data_as(IP)) == 0
+    return lab
+
+
+def test_mincut_brute_force():
+    r = np.random.RandomState(3)
+    w, h = 4, 3
+    q = lambda v: np.round(np.asarray(v, np.float64) * 2 ** 24) / 2 ** 24
+
+    def energy(lab, d0, d1, a):
+        e = sum(d1[p] if lab[p] else d0[p] for p in range(w * h))
+        for y in range(h):
+            for x in range(w):
+                p = y * w + x
+                e += a * (int(x + 1 < w and lab[p] != lab[p + 1]) + int(y + 1 < h and lab[p] != lab[p + w]))
+        return e
+
+    for _ in range(80):
+        d0, d1 = r.rand(w * h).astype(np.float32), r.rand(w * h).astype(np.float32)
+        a = np.float32(r.rand() * 0.5)
+        lab = product_cut(w, h, d0, d1, float(a))
+        assert set(np.unique(lab)) <= {0, 1}
+        best = min(energy(l, q(d0), q(d1), float(q(a))) for l in itertools.product([0, 1], repeat=w * h))
+        assert abs(energy(lab, q(d0), q(d1), float(q(a))) - best) < 1e-9
+    # integer EnergyTermType (stock gco): every cost < 1 truncates to 0 -> nothing leaves label 0
+    assert not product_cut(w, h, d0, d1, float(a), int_terms=1).any()
+
+
+@pytest.mark.parametrize("w,h,seed,kind", [
+    (37, 23, 1, "uniform"), (64, 48, 2, "uniform"), (131, 77, 3, "occlusion"), (200, 150, 4, "occlusion"),
+    (97, 61, 5, "ties"), (1, 40, 6, "uniform"), (40, 1, 7, "uniform"), (160, 120, 8, "blobs"),
+])
+def test_mincut_matches_oracle_labels(oracle, w, h, seed, kind):
+    """Every pixel's label equals the oracle's (canonical cut), on the cost statistics the path produces:
+    'occlusion' = tiny label-0 costs, label-1 costs = penalty 0.1 + tiny, a few strongly occluded blobs."""
+    r = np.random.RandomState(seed)
+    n = w * h
+    if kind == "uniform":
+        d0, d1, alpha = r.rand(n), r.rand(n), 0.3 * r.rand()
+    elif kind == "ties":  # many equal costs: exercises the canonical (minimal sink side) choice
+        d0, d1, alpha = r.randint(0, 3, n) * 0.25, r.randint(0, 3, n) * 0.25, 0.25
+    else:
+        d0 = 0.002 * r.rand(n)
+        d1 = 0.1 + 0.002 * r.rand(n)
+        yy, xx = np.mgrid[0:h, 0:w]
+        for _ in range(6 if kind == "occlusion" else 25):
+            cx, cy, rad = r.randint(0, w), r.randint(0, h), r.randint(2, max(3, min(w, h) // 5))
+            m = ((xx - cx) ** 2 + (yy - cy) ** 2 <= rad * rad).ravel()
+            d0[m] += r.rand() * (0.6 if kind == "occlusion" else 0.25)
+        alpha = 0.1
+    d0, d1 = d0.astype(np.float32), d1.astype(np.float32)
+    a = product_cut(w, h, d0, d1, float(alpha))
+    b = oracle_cut(oracle, w, h, d0, d1, float(alpha))
+    assert np.array_equal(a, b), "labels differ at %d of %d pixels" % (int((a != b).sum()), n)
+    if kind in ("occlusion", "blobs"):
+        assert 0 < a.sum() < n  # both labels occur
