@@ -251,6 +251,7 @@ __device__ __forceinline__ void term_mt_ref(const Derivs &d, float u, float v, f
 
 template <int KIND>
 __global__ void __launch_bounds__(256) k_data_term(Geom g, DataTermDesc t, DataCommon cm) {
+    pdl_enter();
     extern __shared__ float smem[];
     float *sm_m = smem;                       // [3][DT_MH][DT_MW]
     float *sm_z = sm_m + 3 * DT_MH * DT_MW;   // [3][DT_MH][DT_MW]
@@ -420,9 +421,9 @@ void launch_data_term(cudaStream_t st, Geom g, const DataTermDesc &t, const Data
         attr_set = true;
     }
     switch (t.kind) {
-    case DK_MT_SUCC: k_data_term<DK_MT_SUCC><<<grid, b, smem, st>>>(g, t, cm); break;
-    case DK_MT_REF: k_data_term<DK_MT_REF><<<grid, b, smem, st>>>(g, t, cm); break;
-    default: k_data_term<DK_TWO_FRAME><<<grid, b, smem, st>>>(g, t, cm); break;
+    case DK_MT_SUCC: launch_pdl(k_data_term<DK_MT_SUCC>, grid, b, smem, st, g, t, cm); break;
+    case DK_MT_REF: launch_pdl(k_data_term<DK_MT_REF>, grid, b, smem, st, g, t, cm); break;
+    default: launch_pdl(k_data_term<DK_TWO_FRAME>, grid, b, smem, st, g, t, cm); break;
     }
 }
 

@@ -30,6 +30,32 @@ bool cuda_ok(cudaError_t e, const char *what);
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): every kernel of the refinement chain starts with pdl_enter() -- it lets the
+// NEXT launch of the stream become resident while this grid drains, then waits until the PREVIOUS grid has completed
+// and flushed its memory -- and is launched through launch_pdl().  A field is ~50 dependent launches of 10-140 us; the
+// launch latency between them (about 2 us each) is what this hides.  Nothing above pdl_enter() may touch global memory.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // robust penalties (penalty_functions/*.h), selected at run time inside the kernels by a small POD
 struct Penalty {
     int type;        // SF_ROBUST_*

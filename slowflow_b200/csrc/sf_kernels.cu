@@ -20,6 +20,7 @@ namespace sf {
 __global__ void __launch_bounds__(256) k_dpsis_weight(Geom g, const float *__restrict__ im, float *__restrict__ out,
                                                       float coef, float a1, float a2, float a3, float s1, float s2,
                                                       float s3, float divisor) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= g.S || j >= g.H) return;
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(256) k_dpsis_weight(Geom g, const float *__res
 void launch_dpsis_weight(cudaStream_t st, Geom g, const float *im3, float *out, float coef, const float avg[3],
                          const float stdv[3], float divisor) {
     dim3 b(32, 8), grid((g.S + 31) / 32, (g.H + 7) / 8);
-    k_dpsis_weight<<<grid, b, 0, st>>>(g, im3, out, coef, avg[0], avg[1], avg[2], stdv[0], stdv[1], stdv[2], divisor);
+    launch_pdl(k_dpsis_weight, grid, b, 0, st, g, im3, out, coef, avg[0], avg[1], avg[2], stdv[0], stdv[1], stdv[2], divisor);
 }
 
 // ------------------------------------------------------------------------------------------ K1
@@ -52,6 +53,7 @@ void launch_dpsis_weight(cudaStream_t st, Geom g, const float *im3, float *out, 
 __global__ void __launch_bounds__(256) k_warp(Geom g, const float *__restrict__ src, const float *__restrict__ wx,
                                               const float *__restrict__ wy, float factor, float *__restrict__ dst,
                                               float *__restrict__ mask) {
+    pdl_enter();
     const int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i4 >= g.S || j >= g.H) return;
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(256) k_warp(Geom g, const float *__restrict__ 
 void launch_warp(cudaStream_t st, Geom g, const float *src3, const float *wx, const float *wy, int factor,
                  float *dst3, float *mask) {
     dim3 b(32, 8), grid((g.S / 4 + 31) / 32, (g.H + 7) / 8);
-    k_warp<<<grid, b, 0, st>>>(g, src3, wx, wy, (float)factor, dst3, mask);
+    launch_pdl(k_warp, grid, b, 0, st, g, src3, wx, wy, (float)factor, dst3, mask);
 }
 
 // ------------------------------------------------------------------------------------------ K3
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(256) k_flow_smooth(Geom g, const float *__rest
                                                      const float *__restrict__ w, float alpha_factor, Penalty reg, int mode,
                                                      float *__restrict__ wx_out, float *__restrict__ wy_out,
                                                      float *__restrict__ ph, float *__restrict__ pv) {
+    pdl_enter();
     const int lane = threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (j >= g.H) return; // warp-uniform (a warp is one row segment)
@@ -227,9 +230,9 @@ void launch_smoothness(cudaStream_t st, Geom g, const float *uu, const float *vv
                        Penalty reg, int mode, float *ph, float *pv) {
     dim3 b(32, 8), grid((g.S / 4 + 31) / 32, (g.H + 7) / 8);
     if (reg.type < 0)
-        k_flow_smooth<false, true><<<grid, b, 0, st>>>(g, uu, vv, nullptr, nullptr, w, alpha_factor, reg, mode, nullptr, nullptr, ph, pv);
+        launch_pdl(k_flow_smooth<false, true>, grid, b, 0, st, g, uu, vv, nullptr, nullptr, w, alpha_factor, reg, mode, nullptr, nullptr, ph, pv);
     else
-        k_flow_smooth<false, false><<<grid, b, 0, st>>>(g, uu, vv, nullptr, nullptr, w, alpha_factor, reg, mode, nullptr, nullptr, ph, pv);
+        launch_pdl(k_flow_smooth<false, false>, grid, b, 0, st, g, uu, vv, nullptr, nullptr, w, alpha_factor, reg, mode, nullptr, nullptr, ph, pv);
 }
 
 void launch_update_smoothness(cudaStream_t st, Geom g, const float *wx, const float *wy, const float *du, const float *dv,
@@ -237,9 +240,9 @@ void launch_update_smoothness(cudaStream_t st, Geom g, const float *wx, const fl
                               float *ph, float *pv) {
     dim3 b(32, 8), grid((g.S / 4 + 31) / 32, (g.H + 7) / 8);
     if (reg.type < 0)
-        k_flow_smooth<true, true><<<grid, b, 0, st>>>(g, wx, wy, du, dv, w, alpha_factor, reg, mode, wx_out, wy_out, ph, pv);
+        launch_pdl(k_flow_smooth<true, true>, grid, b, 0, st, g, wx, wy, du, dv, w, alpha_factor, reg, mode, wx_out, wy_out, ph, pv);
     else
-        k_flow_smooth<true, false><<<grid, b, 0, st>>>(g, wx, wy, du, dv, w, alpha_factor, reg, mode, wx_out, wy_out, ph, pv);
+        launch_pdl(k_flow_smooth<true, false>, grid, b, 0, st, g, wx, wy, du, dv, w, alpha_factor, reg, mode, wx_out, wy_out, ph, pv);
 }
 
 // ------------------------------------------------------------------------------------------ small operators
@@ -285,6 +288,7 @@ void launch_invert_blocks(cudaStream_t st, Geom g, float *a11, float *a12, float
 
 __global__ void __launch_bounds__(256) k_add4(size_t n4, float4 *__restrict__ dst, const float4 *__restrict__ a,
                                               const float4 *__restrict__ b) {
+    pdl_enter();
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (size_t)gridDim.x * blockDim.x) {
         const float4 x = a[k], y = b[k];
         dst[k] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
@@ -293,8 +297,8 @@ __global__ void __launch_bounds__(256) k_add4(size_t n4, float4 *__restrict__ ds
 void launch_add(cudaStream_t st, Geom g, float *dst, const float *a, const float *b) {
     const size_t n4 = g.plane() / 4;
     const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
-    k_add4<<<blocks, 256, 0, st>>>(n4, reinterpret_cast<float4 *>(dst), reinterpret_cast<const float4 *>(a),
-                                   reinterpret_cast<const float4 *>(b));
+    launch_pdl(k_add4, dim3(blocks), dim3(256), 0, st, n4, reinterpret_cast<float4 *>(dst), reinterpret_cast<const float4 *>(a),
+               reinterpret_cast<const float4 *>(b));
 }
 
 __global__ void __launch_bounds__(256) k_fill(size_t n, float *__restrict__ dst, float v) {

@@ -339,6 +339,7 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
 
 template <bool COLOR>
 __global__ void __launch_bounds__(PR_WARPS * 32) k_prep_two_frame(PrepArgs a) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int work = blockIdx.x * PR_WARPS + (threadIdx.x >> 5);
     if (work >= a.nwork) return; // whole warp
@@ -381,8 +382,8 @@ void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im
     const int segs = (g.H + a.seg_rows - 1) / a.seg_rows;
     a.nwork = a.strips * segs;
     const int blocks = (a.nwork + PR_WARPS - 1) / PR_WARPS;
-    if (half_delta_over3 != 0.0f) k_prep_two_frame<true><<<blocks, PR_WARPS * 32, 0, st>>>(a);
-    else k_prep_two_frame<false><<<blocks, PR_WARPS * 32, 0, st>>>(a);
+    if (half_delta_over3 != 0.0f) launch_pdl(k_prep_two_frame<true>, dim3(blocks), dim3(PR_WARPS * 32), 0, st, a);
+    else launch_pdl(k_prep_two_frame<false>, dim3(blocks), dim3(PR_WARPS * 32), 0, st, a);
 }
 
 } // namespace sf

@@ -57,6 +57,9 @@ __global__ void __launch_bounds__(256) k_sor_half_global(Geom g, const float *__
 #ifndef SF_SOR_SKIP
 #define SF_SOR_SKIP 0
 #endif
+#ifndef SF_SOR_PDL
+#define SF_SOR_PDL 1 // chain consecutive launches with programmatic dependent launch
+#endif
 #ifndef SF_SOR_SYNC
 #define SF_SOR_SYNC 0 // 0: one CTA barrier per half sweep; 1: neighbour-to-neighbour publication counters
 #endif
@@ -253,6 +256,11 @@ k_sor_tiled(const __grid_constant__ CUtensorMap tmap_coef, const __grid_constant
         tma_load_3d(stage + 9 * SOR_R * SOR_TW, &tmap_row, mbar, x0, y0 - 1, SP_PV);
     };
 
+#if SF_SOR_PDL
+    // the next launch of the chain may become resident while this grid drains (sf_internal.cuh: pdl_enter); the
+    // barrier set-up above touches no global memory
+    pdl_enter();
+#endif
     int tile = blockIdx.x;
     uint32_t phase = 0;
     int npub = 0; // publications of this warp so far (= of every warp it is in step with)
@@ -529,7 +537,15 @@ int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int 
         a.out_dv = A + (size_t)(*cur ? SP_DVA : SP_DVB) * P;
         const int ntiles = a.tiles_x * a.tiles_y;
         const int grid = ntiles < plan.num_sms ? ntiles : plan.num_sms;
+#if SF_SOR_PDL
+        if (launch_pdl(k_sor_tiled, dim3(grid), dim3(SOR_NW * 32), (size_t)SOR_SMEM_BYTES, st, plan.tmap, plan.tmap_iter, plan.tmap_row, a) !=
+            cudaSuccess) {
+            set_error("cudaLaunchKernelEx(k_sor_tiled) failed");
+            return -1;
+        }
+#else
         k_sor_tiled<<<grid, SOR_NW * 32, SOR_SMEM_BYTES, st>>>(plan.tmap, plan.tmap_iter, plan.tmap_row, a);
+#endif
         *cur ^= 1;
         done += T;
         launches++;
