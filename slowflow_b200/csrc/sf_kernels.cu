@@ -25,9 +25,12 @@ __global__ void __launch_bounds__(256) k_dpsis_weight(Geom g, const float *__res
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= g.S || j >= g.H) return;
     const size_t P = g.plane();
+    // luminance / divisor as a product with the correctly rounded reciprocal (<= 1 ulp from the reference's quotient,
+    // variational_aux.c:190-196): nine IEEE divisions per pixel were most of this kernel's instructions
+    const float inv_div = __frcp_rn(divisor);
     auto lum = [&](int x, int y) -> float {
         const size_t o = (size_t)y * g.S + x;
-        return (0.299f * (im[o] * s1 + a1) + 0.587f * (im[o + P] * s2 + a2) + 0.114f * (im[o + 2 * P] * s3 + a3)) / divisor;
+        return (0.299f * (im[o] * s1 + a1) + 0.587f * (im[o + P] * s2 + a2) + 0.114f * (im[o + 2 * P] * s3 + a3)) * inv_div;
     };
     float v = 0.0f;
     if (i < g.W) {
