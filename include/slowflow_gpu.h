@@ -161,6 +161,28 @@ typedef struct sfgpu_mt_stats_s {
 } sfgpu_mt_stats_t;
 int sfgpu_get_mt_stats(sfgpu_ctx *ctx, sfgpu_mt_stats_t *out);
 
+/* Output side of a window: the files dense_tracking consumes (dense_tracking.cpp:1119-1162).  Host only.
+ *  - .flo: writeFlowFile / readFlowFile of epic_flow_extended/io.c:50-96 (tag 202021.25, width, height, interleaved u,v)
+ *  - occlusion .pbm: slow_flow.cpp:893-905 (labels -1/0/+1 -> 0/128/255 -> binary PBM as cv::imwrite stores it) */
+int sfgpu_write_flo(const char *filename, const image_t *flowx, const image_t *flowy);
+int sfgpu_read_flo_size(const char *filename, int *width, int *height);
+int sfgpu_read_flo(const char *filename, image_t *flowx, image_t *flowy);
+int sfgpu_write_occlusion_pbm(const char *filename, const image_t *occlusions);
+/* device selection for "one host thread per device" drivers that do not link the CUDA runtime themselves;
+ * sfgpu_create(-1, ...) creates the context on the calling thread's current device */
+int sfgpu_set_device(int device);
+int sfgpu_get_device(void);
+
+/* Input side of a window (what slow_flow.cpp does to each frame before the solver):
+ *  - sfgpu_prescale: GaussianBlur(sigma = 1/sqrt(2*scale), replicate border) + resize(fx = fy = scale, INTER_LINEAR) of a
+ *    float colour image (slow_flow.cpp:538-542).  dst must have the geometry sfgpu_prescale_size reports
+ *    (cvRound(width*scale) x cvRound(height*scale), stride = ceil4).
+ *  - sfgpu_raw_weighting: rawWeighting (utils/utils.cpp:1336-1374, slow_flow.cpp:596-600): channel weights of a Bayer
+ *    mosaic with its red site at (red_x, red_y); weight is clamped to [0, 3].  Only valid columns are written. */
+int sfgpu_prescale_size(int width, int height, float scale, int *out_width, int *out_height);
+int sfgpu_prescale(sfgpu_ctx *ctx, color_image_t *dst, const color_image_t *src, float scale);
+int sfgpu_raw_weighting(sfgpu_ctx *ctx, color_image_t *weights, int red_x, int red_y, float weight);
+
 /* Labelling step of optimizeOcc (variational_aux_mt.cpp:851-881: gco expansion on a grid graph with data costs
  * d0/d1 per site and Potts weight alpha) as the exact binary min-cut the GPU path uses.  Host-only operator twin for
  * tests: costs are dense w*h arrays, labels[p] in {0, 1}; int_terms selects gco's stock integer EnergyTermType. */

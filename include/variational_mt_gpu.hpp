@@ -97,9 +97,8 @@ public:
         sf_mt_params_t m;
         sf_mt_params_from_list(params, &m);
         if (one_direction) m.one_direction = 1;
-        if (!ctx_) {
-            int dev = 0;
-            if (sfgpu_create(dev, NULL, &ctx_) != SFGPU_OK) fail();
+        if (!ctx_) { // on the calling thread's current device: one host thread per device (slow_flow.cpp:706)
+            if (sfgpu_create(-1, NULL, &ctx_) != SFGPU_OK) fail();
         }
         if (occ_.data) free(occ_.data);
         occ_.width = wx->width; occ_.height = wx->height; occ_.stride = wx->stride;
@@ -127,7 +126,7 @@ template <class Params> inline void normalize(color_image_t **seq, unsigned F, P
     sfgpu_ctx *ctx = NULL;
     sf_mt_params_t m;
     sf_mt_params_from_list(params, &m);
-    if (sfgpu_create(0, NULL, &ctx) != SFGPU_OK || sfgpu_normalize(ctx, seq, (int)F, &m) != SFGPU_OK) {
+    if (sfgpu_create(-1, NULL, &ctx) != SFGPU_OK || sfgpu_normalize(ctx, seq, (int)F, &m) != SFGPU_OK) {
         fprintf(stderr, "error in normalize(): %s\n", sfgpu_last_error());
         exit(1);
     }

@@ -475,3 +475,37 @@ void sfo_variational(sfo_image_t *wx, sfo_image_t *wy, const sfo_color_image_t *
     sfo_color_image_delete(Ixx); sfo_color_image_delete(Ixy); sfo_color_image_delete(Iyy);
     sfo_color_image_delete(Ixz); sfo_color_image_delete(Iyz);
 }
+
+
+/* ---------------------------------------------------------------- on-disk outputs (checkers of sfgpu_write_flo / _pbm) */
+/* writeFlowFile, epic_flow_extended/io.c:78-96: element-wise fwrite exactly as written there */
+int sfo_write_flo(const char *filename, const sfo_image_t *flowx, const sfo_image_t *flowy) {
+    FILE *stream = fopen(filename, "wb");
+    if (stream == 0) return 1;
+    const float help = 202021.25;
+    fwrite(&help, sizeof(float), 1, stream);
+    const int aXSize = flowx->width, aYSize = flowx->height;
+    fwrite(&aXSize, sizeof(int), 1, stream);
+    fwrite(&aYSize, sizeof(int), 1, stream);
+    int y, x;
+    for (y = 0; y < aYSize; y++)
+        for (x = 0; x < aXSize; x++) {
+            fwrite(&flowx->data[y * flowx->stride + x], sizeof(float), 1, stream);
+            fwrite(&flowy->data[y * flowy->stride + x], sizeof(float), 1, stream);
+        }
+    fclose(stream);
+    return 0;
+}
+
+/* slow_flow.cpp:893-905: occ_mat = 0.5*(occ + 1); convertTo(CV_8UC1, 255) (saturate_cast: round half to even);
+ * imwrite(".pbm", PXM_BINARY=1) -- returns the 8-bit image; the P4 packing of cv::imwrite is pinned against python cv2
+ * in tests/test_io.py */
+int sfo_occlusion_to_u8(const sfo_image_t *occ, unsigned char *dst /* width*height, dense */) {
+    int y, x;
+    for (y = 0; y < occ->height; y++)
+        for (x = 0; x < occ->width; x++) {
+            const double v = nearbyint(0.5 * ((double)occ->data[y * occ->stride + x] + 1.0) * 255.0);
+            dst[y * occ->width + x] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    return 0;
+}

@@ -619,6 +619,65 @@ Img *resize_flow(const Img *src, int w, int h, float mul) { /* resize + image_mu
 
 extern "C" {
 
+/* frame pre-scale of slow_flow.cpp:538-542: GaussianBlur(sigma = 1/sqrt(2*scale), BORDER_REPLICATE) + resize(Size(0,0), scale,
+ * scale, INTER_LINEAR) on a CV_32F image.  cv::resize by factor: dsize = cvRound(src*f) and the coordinate map uses 1/f
+ * (not the ratio of the rounded sizes) -- pinned to python cv2 in tests/test_oracle_pin_mt.py. */
+int sfo_prescale_size(int width, int height, float scale, int *ow, int *oh) {
+    *ow = (int)lrint((double)width * (double)scale);
+    *oh = (int)lrint((double)height * (double)scale);
+    return (*ow > 0 && *oh > 0) ? 0 : 1;
+}
+int sfo_prescale(sfo_color_image_t *dst, const sfo_color_image_t *src, float scale) {
+    const double sigma = 1.0 / sqrt((double)(2.0f * scale));
+    const double inv = 1.0 / (double)scale;
+    const size_t Ps = (size_t)src->stride * src->height, Pd = (size_t)dst->stride * dst->height;
+    std::vector<float> blur(Ps);
+    for (int c = 0; c < 3; c++) {
+        gaussian_blur(src->c1 + c * Ps, blur.data(), src->height, src->width, src->stride, sigma);
+        float *d = dst->c1 + c * Pd;
+        for (int y = 0; y < dst->height; y++) {
+            float fy = (float)((y + 0.5) * inv - 0.5);
+            int sy = (int)floorf(fy);
+            fy -= sy;
+            if (sy < 0) { sy = 0; fy = 0; }
+            if (sy >= src->height - 1) { sy = src->height - 1; fy = 0; }
+            const int y1 = std::min(sy + 1, src->height - 1);
+            for (int x = 0; x < dst->width; x++) {
+                float fx = (float)((x + 0.5) * inv - 0.5);
+                int sx = (int)floorf(fx);
+                fx -= sx;
+                if (sx < 0) { sx = 0; fx = 0; }
+                if (sx >= src->width - 1) { sx = src->width - 1; fx = 0; }
+                const int x1 = std::min(sx + 1, src->width - 1);
+                const float a1 = fx, a0 = 1.f - fx, b1 = fy, b0 = 1.f - fy;
+                const float r0 = blur[(size_t)sy * src->stride + sx] * a0 + blur[(size_t)sy * src->stride + x1] * a1;
+                const float r1 = blur[(size_t)y1 * src->stride + sx] * a0 + blur[(size_t)y1 * src->stride + x1] * a1;
+                d[(size_t)y * dst->stride + x] = r0 * b0 + r1 * b1;
+            }
+        }
+    }
+    return 0;
+}
+
+/* rawWeighting (utils/utils.cpp:1336-1374): channel weights of a Bayer mosaic, red site at (red_x, red_y) */
+int sfo_raw_weighting(sfo_color_image_t *weights, int red_x, int red_y, float weight) {
+    weight = (float)fmin(fmax(weight, 0.0), 3.0);
+    float *R = weights->c1, *G = weights->c2, *B = weights->c3;
+    for (int x = 0; x < weights->width; x++)
+        for (int y = 0; y < weights->height; y++) {
+            const size_t o = (size_t)y * weights->stride + x;
+            const float other = (float)(0.5 * (3 - weight));
+            if ((y + (1 - red_y)) % 2 == 0) { /* blue row */
+                if ((red_y == 1 && (x + (1 - red_x)) % 2 == 0) || (red_y == 0 && (x + red_x) % 2 == 0)) { R[o] = other; G[o] = weight; B[o] = other; }
+                else { R[o] = other; G[o] = other; B[o] = weight; }
+            } else { /* red row */
+                if ((red_y == 0 && (x + (1 - red_x)) % 2 == 0) || (red_y == 1 && (x + red_x) % 2 == 0)) { R[o] = other; G[o] = weight; B[o] = other; }
+                else { R[o] = weight; G[o] = other; B[o] = other; }
+            }
+        }
+    return 0;
+}
+
 /* labelling step of optimizeOcc alone (variational_aux_mt.cpp:851-881) on dense w*h cost arrays: the checker of the
  * product's sfgpu_grid_mincut */
 int sfo_mincut(int w, int h, const float *d0, const float *d1, float alpha, int int_terms, int *labels) {

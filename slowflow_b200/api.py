@@ -41,7 +41,8 @@ ABI_SYMBOLS = [
     "sfgpu_host_unregister", "sfgpu_variational_mt", "sfgpu_normalize", "sfgpu_get_mt_stats", "sfgpu_profile_enable",
     "sfgpu_profile_reset", "sfgpu_profile_get", "sfgpu_image_warp", "sfgpu_compute_dpsis_weight",
     "sfgpu_compute_smoothness", "sfgpu_compute_data_and_match", "sfgpu_sub_laplacian", "sfgpu_sor_coupled",
-    "sfgpu_version", "sfgpu_grid_mincut",
+    "sfgpu_version", "sfgpu_grid_mincut", "sfgpu_prescale_size", "sfgpu_prescale", "sfgpu_raw_weighting",
+    "sfgpu_write_flo", "sfgpu_read_flo_size", "sfgpu_read_flo", "sfgpu_write_occlusion_pbm", "sfgpu_set_device", "sfgpu_get_device",
 ]
 
 
@@ -92,6 +93,14 @@ def load_library(path=None):
                                                  C.c_float]
     lib.sfgpu_sub_laplacian.argtypes = [C.c_void_p, IP, IP, IP, IP]
     lib.sfgpu_sor_coupled.argtypes = [C.c_void_p, IP, IP, IP, IP, IP, IP, IP, IP, IP, C.c_int, C.c_float]
+    lib.sfgpu_prescale_size.argtypes = [C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.sfgpu_prescale.argtypes = [C.c_void_p, CP, CP, C.c_float]
+    lib.sfgpu_raw_weighting.argtypes = [C.c_void_p, CP, C.c_int, C.c_int, C.c_float]
+    lib.sfgpu_write_flo.argtypes = [C.c_char_p, IP, IP]
+    lib.sfgpu_read_flo_size.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.sfgpu_read_flo.argtypes = [C.c_char_p, IP, IP]
+    lib.sfgpu_write_occlusion_pbm.argtypes = [C.c_char_p, IP]
+    lib.sfgpu_set_device.argtypes = [C.c_int]
     lib.sfgpu_grid_mincut.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_int, C.POINTER(C.c_int)]
     if path is None:
         _LIB = lib
@@ -194,6 +203,20 @@ class Context:
                "sfgpu_variational_mt")
         return float(out[0]), float(out[1])
 
+    # --- input side of a window (slow_flow.cpp:538-542, 596-600)
+    def prescale(self, src, scale):
+        """GaussianBlur + resize by `scale` of a float colour image -> new ColorImage."""
+        w, h = C.c_int(), C.c_int()
+        _check(self.lib, self.lib.sfgpu_prescale_size(src.width, src.height, scale, C.byref(w), C.byref(h)),
+               "sfgpu_prescale_size")
+        dst = ColorImage(w.value, h.value)
+        _check(self.lib, self.lib.sfgpu_prescale(self.h, dst.ptr(), src.ptr(), scale), "sfgpu_prescale")
+        return dst
+
+    def raw_weighting(self, weights, red_x, red_y, weight):
+        _check(self.lib, self.lib.sfgpu_raw_weighting(self.h, weights.ptr(), int(red_x), int(red_y), weight),
+               "sfgpu_raw_weighting")
+
     def mt_stats(self):
         s = MTStats()
         _check(self.lib, self.lib.sfgpu_get_mt_stats(self.h, C.byref(s)), "sfgpu_get_mt_stats")
@@ -259,3 +282,25 @@ class Variational_MT:
             p.one_direction = 1
         self._occlusions = Image(wx.width, wx.height)
         return self.ctx.variational_mt(wx, wy, im, p, self._channel_w, self._occlusions)
+
+
+def write_flo(path, wx, wy):
+    """writeFlowFile (epic_flow_extended/io.c:78-96)."""
+    lib = load_library()
+    _check(lib, lib.sfgpu_write_flo(str(path).encode(), wx.ptr(), wy.ptr()), "sfgpu_write_flo")
+
+
+def read_flo(path):
+    """readFlowFile (epic_flow_extended/io.c:50-75) -> (wx, wy)."""
+    lib = load_library()
+    w, h = C.c_int(), C.c_int()
+    _check(lib, lib.sfgpu_read_flo_size(str(path).encode(), C.byref(w), C.byref(h)), "sfgpu_read_flo_size")
+    wx, wy = Image(w.value, h.value), Image(w.value, h.value)
+    _check(lib, lib.sfgpu_read_flo(str(path).encode(), wx.ptr(), wy.ptr()), "sfgpu_read_flo")
+    return wx, wy
+
+
+def write_occlusion_pbm(path, occ):
+    """Occlusion labels as slow_flow.cpp:893-905 stores them."""
+    lib = load_library()
+    _check(lib, lib.sfgpu_write_occlusion_pbm(str(path).encode(), occ.ptr()), "sfgpu_write_occlusion_pbm")

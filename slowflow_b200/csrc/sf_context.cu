@@ -272,6 +272,7 @@ int sfgpu_create(int device, void *stream, sfgpu_ctx **out) {
         set_error("sfgpu_create: no CUDA device available (this library has no CPU fallback)");
         return SFGPU_ERR_CUDA;
     }
+    if (device == -1 && cudaGetDevice(&device) != cudaSuccess) device = 0; // -1: the calling thread's current device
     if (device < 0 || device >= n) {
         set_error("sfgpu_create: device index out of range");
         return SFGPU_ERR_ARG;
@@ -282,6 +283,10 @@ int sfgpu_create(int device, void *stream, sfgpu_ctx **out) {
     if (prop.major < 10) {
         set_error("sfgpu_create: device is not sm_100 class (kernels are built for sm_100a only)");
         return SFGPU_ERR_UNSUPPORTED;
+    }
+    if (!sor_device_init() || !data_term_device_init()) {
+        set_error("sfgpu_create: cudaFuncSetAttribute failed (dynamic shared memory opt-in)");
+        return SFGPU_ERR_CUDA;
     }
     sfgpu_ctx *c = new sfgpu_ctx();
     c->device = device;

@@ -410,16 +410,16 @@ __global__ void __launch_bounds__(256) k_data_term(Geom g, DataTermDesc t, DataC
     }
 }
 
+bool data_term_device_init() { // per device, called by sfgpu_create
+    const int smem = (int)(DT_SMEM_FLOATS * sizeof(float));
+    return cudaFuncSetAttribute(k_data_term<DK_TWO_FRAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+           cudaFuncSetAttribute(k_data_term<DK_MT_SUCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+           cudaFuncSetAttribute(k_data_term<DK_MT_REF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+}
+
 void launch_data_term(cudaStream_t st, Geom g, const DataTermDesc &t, const DataCommon &cm) {
     dim3 b(32, 8), grid((g.S + DT_TW - 1) / DT_TW, (g.H + DT_TH - 1) / DT_TH);
     const size_t smem = DT_SMEM_FLOATS * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_data_term<DK_TWO_FRAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_data_term<DK_MT_SUCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_data_term<DK_MT_REF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
     switch (t.kind) {
     case DK_MT_SUCC: launch_pdl(k_data_term<DK_MT_SUCC>, grid, b, smem, st, g, t, cm); break;
     case DK_MT_REF: launch_pdl(k_data_term<DK_MT_REF>, grid, b, smem, st, g, t, cm); break;

@@ -137,6 +137,9 @@ struct SorPlan {
     bool tmap_valid = false;
     int num_sms = 0;
 };
+// per-device kernel attributes (dynamic shared memory opt-in); called once per context on its device
+bool sor_device_init();
+bool data_term_device_init();
 // Encode the TMA descriptor for an arena.  Returns false (and sets the error) on failure.
 bool sor_plan_init(SorPlan &plan, Geom g, float *arena, int num_sms);
 // Runs `iterations` sweeps; the iterate starts in (duA,dvA) when *cur==0 or (duB,dvB) when *cur==1 and

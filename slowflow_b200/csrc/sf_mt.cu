@@ -193,6 +193,27 @@ __global__ void __launch_bounds__(256) k_resize(Geom gs, const float *__restrict
     }
 }
 
+// rawWeighting (utils/utils.cpp:1336-1374): per-pixel channel weights of a Bayer mosaic whose red site is at
+// (red_x, red_y) mod 2 -- the measured channel gets `weight`, the two interpolated ones 0.5*(3 - weight)
+__global__ void __launch_bounds__(256) k_raw_weights(Geom g, float *__restrict__ w3, int red_x, int red_y, float weight) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= g.W || y >= g.H) return;
+    const size_t P = g.plane(), o = (size_t)y * g.S + x;
+    const float other = 0.5f * (3.0f - weight);
+    int measured; // 0 R, 1 G, 2 B
+    if ((y + (1 - red_y)) % 2 == 0) { // blue row
+        const bool green = (red_y == 1 && (x + (1 - red_x)) % 2 == 0) || (red_y == 0 && (x + red_x) % 2 == 0);
+        measured = green ? 1 : 2;
+    } else { // red row
+        const bool green = (red_y == 0 && (x + (1 - red_x)) % 2 == 0) || (red_y == 1 && (x + red_x) % 2 == 0);
+        measured = green ? 1 : 0;
+    }
+    w3[o] = measured == 0 ? weight : other;
+    w3[o + P] = measured == 1 ? weight : other;
+    w3[o + 2 * P] = measured == 2 ? weight : other;
+}
+
 // normalize(): per-channel sums in double (variational_mt.cpp:27-46), then (I - avg) / std (:61-69)
 __global__ void __launch_bounds__(256) k_norm_sums(Geom g, const float *__restrict__ im, double *__restrict__ sums /*6*/) {
     double s[6] = {0, 0, 0, 0, 0, 0};
@@ -618,6 +639,75 @@ int sfgpu_normalize(sfgpu_ctx *c, color_image_t *const *seq, int F, sf_mt_params
         params->img_norm_std[k] = (float)atof(buf);
     }
     c->prof_acc.kernel_launches += 2 * F;
+    return SFGPU_OK;
+}
+
+// ---- input side of a window: what slow_flow.cpp does to every frame before the solver sees it
+int sfgpu_prescale_size(int width, int height, float scale, int *out_width, int *out_height) {
+    if (width <= 0 || height <= 0 || !(scale > 0.0f) || !out_width || !out_height) {
+        set_error("sfgpu_prescale_size: bad argument");
+        return SFGPU_ERR_ARG;
+    }
+    // cv::resize(src, dst, Size(0,0), fx, fy): dsize = (cvRound(cols*fx), cvRound(rows*fy)), round half to even
+    *out_width = (int)lrint((double)width * (double)scale);
+    *out_height = (int)lrint((double)height * (double)scale);
+    if (*out_width < 1 || *out_height < 1) {
+        set_error("sfgpu_prescale_size: scaled image is empty");
+        return SFGPU_ERR_ARG;
+    }
+    return SFGPU_OK;
+}
+
+int sfgpu_prescale(sfgpu_ctx *c, color_image_t *dst, const color_image_t *src, float scale) {
+    if (!c || !dst || !src || !dst->c1 || !src->c1) {
+        set_error("sfgpu_prescale: null argument");
+        return SFGPU_ERR_ARG;
+    }
+    int dw = 0, dh = 0;
+    int rc = sfgpu_prescale_size(src->width, src->height, scale, &dw, &dh);
+    if (rc != SFGPU_OK) return rc;
+    if (dst->width != dw || dst->height != dh || dst->stride != ((dw + 3) / 4) * 4 || src->stride != ((src->width + 3) / 4) * 4) {
+        set_error("sfgpu_prescale: dst must have the geometry sfgpu_prescale_size reports");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const Geom gs{src->width, src->height, src->stride}, gd{dw, dh, dst->stride};
+    const size_t Ps = gs.plane(), Pd = gd.plane();
+    rc = c->ensure_io(9 * Ps + 3 * Pd);
+    if (rc != SFGPU_OK) return rc;
+    float *d_src = c->io, *d_tmp = c->io + 3 * Ps, *d_blur = c->io + 6 * Ps, *d_dst = c->io + 9 * Ps;
+    SF_CUDA(cudaMemcpyAsync(d_src, src->c1, 3 * Ps * sizeof(float), cudaMemcpyHostToDevice, st));
+    // GaussianBlur(img, img, Size(), 1/sqrt(2*scale), ..., BORDER_REPLICATE) then resize(..., scale, scale, INTER_LINEAR)
+    // (slow_flow.cpp:539-542); the mapping of a resize by factor uses 1/fx, not the ratio of the rounded sizes
+    const double sigma = 1.0 / sqrt((double)(2.0f * scale));
+    const BlurTaps taps = make_taps(sigma);
+    k_blur<<<grid2d(gs.W, gs.H), dim3(32, 8), 0, st>>>(gs, d_src, d_tmp, taps, 0, 3);
+    k_blur<<<grid2d(gs.W, gs.H), dim3(32, 8), 0, st>>>(gs, d_tmp, d_blur, taps, 1, 3);
+    k_resize<<<grid2d(gd.S, gd.H), dim3(32, 8), 0, st>>>(gs, d_blur, gd, d_dst, 1.0 / (double)scale, 1.0 / (double)scale, 1.0f, 3);
+    c->prof_acc.kernel_launches += 3;
+    SF_CUDA(cudaMemcpyAsync(dst->c1, d_dst, 3 * Pd * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaStreamSynchronize(st));
+    return SFGPU_OK;
+}
+
+int sfgpu_raw_weighting(sfgpu_ctx *c, color_image_t *weights, int red_x, int red_y, float weight) {
+    if (!c || !weights || !weights->c1 || weights->stride != ((weights->width + 3) / 4) * 4) {
+        set_error("sfgpu_raw_weighting: bad argument");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const Geom g{weights->width, weights->height, weights->stride};
+    const size_t P = g.plane();
+    int rc = c->ensure_io(3 * P);
+    if (rc != SFGPU_OK) return rc;
+    // the reference only writes the valid columns (utils/utils.cpp:1340-1372); the stride padding keeps the caller's values
+    SF_CUDA(cudaMemcpyAsync(c->io, weights->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st));
+    k_raw_weights<<<grid2d(g.W, g.H), dim3(32, 8), 0, st>>>(g, c->io, red_x, red_y, fminf(fmaxf(weight, 0.0f), 3.0f));
+    c->prof_acc.kernel_launches++;
+    SF_CUDA(cudaMemcpyAsync(weights->c1, c->io, 3 * P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaStreamSynchronize(st));
     return SFGPU_OK;
 }
 

@@ -21,6 +21,7 @@
 // Border semantics follow image.c:400-526: rows / columns outside the image are clamped at load time, which
 // reproduces the replicate border of the first derivative stage; the second stage (d/dx of Ix, d/dy of Iy)
 // replicates the first-stage VALUE, which is patched explicitly in edge strips / segments.
+#include <atomic>
 #include <type_traits>
 
 #include "sf_internal.cuh"
@@ -370,15 +371,19 @@ void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im
     a.a11 = a11; a.a12 = a12; a.a22 = a22; a.b1 = b1; a.b2 = b2;
     a.hd = half_delta_over3; a.hg = half_gamma_over3;
     a.strips = (g.S + PR_OUT_W - 1) / PR_OUT_W;
-    static int resident[2] = {0, 0}; // resident warps per SM of the two instantiations
+    // resident warps per SM of the two instantiations (the same on every device of the box: all are sm_100a;
+    // relaxed atomics because one host thread per device may get here at the same time)
+    static std::atomic<int> resident[2];
     const int color = half_delta_over3 != 0.0f ? 1 : 0;
-    if (!resident[color]) {
+    int res = resident[color].load(std::memory_order_relaxed);
+    if (!res) {
         int blocks_per_sm = 0;
         if (color) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_prep_two_frame<true>, PR_WARPS * 32, 0);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_prep_two_frame<false>, PR_WARPS * 32, 0);
-        resident[color] = (blocks_per_sm > 0 ? blocks_per_sm : 1) * PR_WARPS;
+        res = (blocks_per_sm > 0 ? blocks_per_sm : 1) * PR_WARPS;
+        resident[color].store(res, std::memory_order_relaxed);
     }
-    a.seg_rows = prep_seg_rows(g, num_sms, resident[color]);
+    a.seg_rows = prep_seg_rows(g, num_sms, res);
     const int segs = (g.H + a.seg_rows - 1) / a.seg_rows;
     a.nwork = a.strips * segs;
     const int blocks = (a.nwork + PR_WARPS - 1) / PR_WARPS;

@@ -439,18 +439,27 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static PFN_encodeTiled lookup_encode_fn() {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<PFN_encodeTiled>(p);
+    return nullptr;
+}
 static PFN_encodeTiled get_encode_fn() {
-    static PFN_encodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_encodeTiled>(p);
-    }
+    static const PFN_encodeTiled fn = lookup_encode_fn(); // initialised once, thread-safe (one host thread per device)
     return fn;
+}
+
+// Function attributes are per device: every context sets them on its own device when it is created (a process-wide
+// "done once" flag left the second GPU of a multi-threaded driver without its shared-memory opt-in).
+bool sor_device_init() {
+    if (cudaFuncSetAttribute(k_sor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, SOR_SMEM_BYTES) != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(k_sor_tiled) failed");
+        return false;
+    }
+    return true;
 }
 
 bool sor_plan_init(SorPlan &plan, Geom g, float *arena, int num_sms) {
@@ -507,14 +516,6 @@ int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int 
             launches += 2;
         }
         return launches;
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_sor_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, SOR_SMEM_BYTES) != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(k_sor_tiled) failed");
-            return -1;
-        }
-        attr_set = true;
     }
     if (fuse < 1) fuse = 1;
     const int max_fuse = (SOR_TH - 4) / 4 < 7 ? (SOR_TH - 4) / 4 : 7; // the halo (2*fuse per side) must leave an interior

@@ -132,3 +132,40 @@ def test_mt_gpu_vs_restatement(ctx, oracle):
     r = mh.run_cpu(oracle.lib, "sfo_", ims, wx, wy, p, SOR_REDBLACK)
     g = mh.run_gpu(ctx, ims, wx, wy, p)
     check(g, r, "vs restatement")
+
+
+# ------------------------------------------------------------------ input side of a window
+@pytest.mark.parametrize("w,h,scale", [(131, 97, 0.5), (200, 150, 0.75), (97, 61, 0.9), (64, 48, 0.3), (80, 60, 1.5)])
+def test_prescale_matches_oracle(ctx, oracle, w, h, scale):
+    """GaussianBlur + resize by factor (slow_flow.cpp:538-542) against the restatement pinned to cv2."""
+    import ctypes as C
+    from slowflow_b200 import ColorImage
+    from slowflow_b200.image import color_image_t
+    r = np.random.RandomState(w)
+    src = ColorImage.from_array((r.rand(3, h, w) * 255).astype(np.float32))
+    g = ctx.prescale(src, scale)
+    L = oracle.lib
+    CP = C.POINTER(color_image_t)
+    L.sfo_prescale.argtypes = [CP, CP, C.c_float]
+    ref = ColorImage(g.width, g.height)
+    assert L.sfo_prescale(ref.ptr(), src.ptr(), scale) == 0
+    assert (g.width, g.height) == (int(np.rint(w * np.float64(np.float32(scale)))), int(np.rint(h * np.float64(np.float32(scale)))))
+    assert np.abs(g.array - ref.array).max() <= 2e-4  # values up to 255: fp32 FMA contraction only
+
+
+@pytest.mark.parametrize("red_x,red_y,weight", [(0, 0, 1.0), (1, 0, 2.0), (0, 1, 0.5), (1, 1, 3.7), (1, 1, -1.0)])
+def test_raw_weighting_matches_oracle(ctx, oracle, red_x, red_y, weight):
+    """rawWeighting (utils/utils.cpp:1336-1374) is pure index logic: bit-exact, padding untouched."""
+    import ctypes as C
+    from slowflow_b200 import ColorImage
+    from slowflow_b200.image import color_image_t
+    w, h = 37, 22
+    a, b = ColorImage(w, h), ColorImage(w, h)
+    a.buf[:] = -5.0
+    b.buf[:] = -5.0
+    ctx.raw_weighting(a, red_x, red_y, weight)
+    L = oracle.lib
+    L.sfo_raw_weighting.argtypes = [C.POINTER(color_image_t), C.c_int, C.c_int, C.c_float]
+    assert L.sfo_raw_weighting(b.ptr(), red_x, red_y, weight) == 0
+    assert np.array_equal(a.buf, b.buf)
+    assert np.allclose(a.array.sum(axis=0), 3.0)  # the three weights of a pixel always add up to 3

@@ -100,3 +100,28 @@ def test_mincut_standin_is_optimal(reference):
     lab = np.ones(w * h, np.int32)
     L.sf_ref_mincut(w, h, d0.ctypes.data_as(FP), d1.ctypes.data_as(FP), a, 1, lab.ctypes.data_as(C.POINTER(C.c_int)))
     assert not lab.any()
+
+
+def test_prescale_restatement_matches_cv2(oracle):
+    """slow_flow.cpp:538-542 on a CV_32F image: GaussianBlur(Size(), s, s, BORDER_REPLICATE) + resize(Size(0,0), f, f,
+    INTER_LINEAR).  The resize-by-factor form rounds the size (cvRound) and maps coordinates with 1/f."""
+    cv2 = pytest.importorskip("cv2")
+    from slowflow_b200 import ColorImage
+    from slowflow_b200.image import color_image_t
+    L = oracle.lib
+    CP = C.POINTER(color_image_t)
+    L.sfo_prescale.argtypes = [CP, CP, C.c_float]
+    L.sfo_prescale_size.argtypes = [C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    r = np.random.RandomState(5)
+    for (w, h, f) in [(131, 97, 0.5), (200, 150, 0.75), (97, 61, 0.9), (64, 48, 0.3), (80, 60, 1.5)]:
+        img = (r.rand(h, w, 3) * 255).astype(np.float32)
+        sg = 1 / np.sqrt(np.float64(np.float32(2 * f)))
+        ref = cv2.GaussianBlur(img, (0, 0), sg, sigmaY=sg, borderType=cv2.BORDER_REPLICATE)
+        ref = cv2.resize(ref, None, fx=float(np.float32(f)), fy=float(np.float32(f)), interpolation=cv2.INTER_LINEAR)
+        ow, oh = C.c_int(), C.c_int()
+        assert L.sfo_prescale_size(w, h, f, C.byref(ow), C.byref(oh)) == 0
+        assert (oh.value, ow.value) == ref.shape[:2]
+        src = ColorImage.from_array(np.ascontiguousarray(img.transpose(2, 0, 1)))
+        dst = ColorImage(ow.value, oh.value)
+        assert L.sfo_prescale(dst.ptr(), src.ptr(), f) == 0
+        assert np.abs(dst.array - ref.transpose(2, 0, 1)).max() <= 1e-5 * 255

@@ -27,6 +27,7 @@ int main(int argc, char **argv) {
     float *d2; cudaMalloc(&d2, h.size() * 4); cudaMemcpy(d2, d, h.size() * 4, cudaMemcpyDeviceToDevice);
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     sf::SorPlan plan[2];
+    if (!sf::sor_device_init()) return 1;
     if (!sf::sor_plan_init(plan[0], g, d, sms) || !sf::sor_plan_init(plan[1], g, d2, sms)) return 1;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int fuse = 2; fuse <= 7; fuse++) {
