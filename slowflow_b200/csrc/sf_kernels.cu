@@ -17,28 +17,34 @@
 namespace sf {
 
 // ------------------------------------------------------------------------------------------ K0
+// CTA = 32 x 8 pixels; the luminance of the tile + 2 px halo is formed once in shared memory (1.7 evaluations per pixel
+// instead of 9: the kernel was instruction-bound on the nine de-normalise / weight / divide chains per pixel).
 __global__ void __launch_bounds__(256) k_dpsis_weight(Geom g, const float *__restrict__ im, float *__restrict__ out,
                                                       float coef, float a1, float a2, float a3, float s1, float s2,
                                                       float s3, float divisor) {
     pdl_enter();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= g.S || j >= g.H) return;
+    constexpr int TW = 32, TH = 8, LW = TW + 4, LH = TH + 4;
+    __shared__ float lum[LH][LW + 1];
+    const int i0 = blockIdx.x * TW, j0 = blockIdx.y * TH;
+    const int tid = threadIdx.y * TW + threadIdx.x;
     const size_t P = g.plane();
+    const int W1 = g.W - 1, H1 = g.H - 1;
     // luminance / divisor as a product with the correctly rounded reciprocal (<= 1 ulp from the reference's quotient,
-    // variational_aux.c:190-196): nine IEEE divisions per pixel were most of this kernel's instructions
+    // variational_aux.c:190-196)
     const float inv_div = __frcp_rn(divisor);
-    auto lum = [&](int x, int y) -> float {
-        const size_t o = (size_t)y * g.S + x;
-        return (0.299f * (im[o] * s1 + a1) + 0.587f * (im[o + P] * s2 + a2) + 0.114f * (im[o + 2 * P] * s3 + a3)) * inv_div;
-    };
+    for (int idx = tid; idx < LH * LW; idx += TW * TH) {
+        const int ly = idx / LW, lx = idx - ly * LW;
+        const size_t o = (size_t)clampi(j0 - 2 + ly, 0, H1) * g.S + clampi(i0 - 2 + lx, 0, W1);
+        lum[ly][lx] = (0.299f * (im[o] * s1 + a1) + 0.587f * (im[o + P] * s2 + a2) + 0.114f * (im[o + 2 * P] * s3 + a3)) * inv_div;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = i0 + tx, j = j0 + ty;
+    if (i >= g.S || j >= g.H) return;
     float v = 0.0f;
     if (i < g.W) {
-        const int W1 = g.W - 1, H1 = g.H - 1;
-        const float lx = hconv5(lum(clampi(i - 2, 0, W1), j), lum(clampi(i - 1, 0, W1), j), lum(i, j),
-                                lum(clampi(i + 1, 0, W1), j), lum(clampi(i + 2, 0, W1), j));
-        const float ly = vconv5(lum(i, clampi(j - 2, 0, H1)), lum(i, clampi(j - 1, 0, H1)), lum(i, j),
-                                lum(i, clampi(j + 1, 0, H1)), lum(i, clampi(j + 2, 0, H1)), j, g.H);
+        const float lx = hconv5(lum[ty + 2][tx], lum[ty + 2][tx + 1], lum[ty + 2][tx + 2], lum[ty + 2][tx + 3], lum[ty + 2][tx + 4]);
+        const float ly = vconv5(lum[ty][tx + 2], lum[ty + 1][tx + 2], lum[ty + 2][tx + 2], lum[ty + 3][tx + 2], lum[ty + 4][tx + 2], j, g.H);
         v = 0.5f * expf(-coef * sqrtf(lx * lx + ly * ly));
     }
     out[(size_t)j * g.S + i] = v;
@@ -130,14 +136,28 @@ template <bool UPDATE>
 __device__ __forceinline__ float load_flow1(const float *__restrict__ w, const float *__restrict__ d, size_t o) {
     return UPDATE ? w[o] + d[o] : w[o];
 }
-// row `r` of the (updated) flow around columns i4..i4+3; raw = the unclamped float4 (what the update stores)
+// Row `r` of the (updated) flow around columns i4..i4+3, in two phases so that EVERY global load of the thread is in
+// flight before the first shuffle waits for one of them (with load and shuffle interleaved per row, ptxas serialised
+// seven memory round trips per thread and the kernel ran at a quarter of the HBM rate):
+//   load_raw : the float4 (wx [+ du]) plus the edge neighbours that only the outer lanes of a warp need
+//   finish_row6 : replicate-border patching and the neighbour columns from the adjacent lanes
+struct RawRow {
+    float4 a;   // columns i4 .. i4+3 (unclamped: what the update stores)
+    float l, r; // columns i4-1 / i4+4 (meaningful in lane 0 / lane 31 only)
+};
 template <bool UPDATE>
-__device__ __forceinline__ Row6 load_row6(const Geom &g, const float *__restrict__ w, const float *__restrict__ d, int r,
-                                          int i4, int lane, float4 *raw) {
+__device__ __forceinline__ RawRow load_raw(const Geom &g, const float *__restrict__ w, const float *__restrict__ d, int r, int i4,
+                                           int lane) {
     const size_t ro = (size_t)r * g.S;
-    const float4 a = load_flow4<UPDATE>(w, d, ro + i4);
-    if (raw) *raw = a;
+    RawRow q;
+    q.a = load_flow4<UPDATE>(w, d, ro + i4);
+    q.l = (lane == 0 && i4 > 0) ? load_flow1<UPDATE>(w, d, ro + i4 - 1) : 0.0f;
+    q.r = (lane == 31 && i4 + 4 <= g.W - 1) ? load_flow1<UPDATE>(w, d, ro + i4 + 4) : 0.0f;
+    return q;
+}
+__device__ __forceinline__ Row6 finish_row6(const Geom &g, const RawRow &raw, int i4, int lane) {
     const int W1 = g.W - 1;
+    const float4 a = raw.a;
     Row6 q;
     q.c[1] = a.x; q.c[2] = a.y; q.c[3] = a.z; q.c[4] = a.w;
     // columns beyond W-1 (stride padding) replicate column W-1, which lies in this float4 (S - W <= 3)
@@ -149,9 +169,9 @@ __device__ __forceinline__ Row6 load_row6(const Geom &g, const float *__restrict
     }
     const float from_l = __shfl_up_sync(0xffffffffu, q.c[4], 1), from_r = __shfl_down_sync(0xffffffffu, q.c[1], 1);
     if (i4 == 0) q.c[0] = q.c[1];
-    else q.c[0] = (lane > 0) ? from_l : load_flow1<UPDATE>(w, d, ro + i4 - 1);
+    else q.c[0] = (lane > 0) ? from_l : raw.l;
     if (i4 + 4 > W1) q.c[5] = q.c[4];
-    else q.c[5] = (lane < 31) ? from_r : load_flow1<UPDATE>(w, d, ro + i4 + 4);
+    else q.c[5] = (lane < 31) ? from_r : raw.r;
     return q;
 }
 
@@ -181,21 +201,26 @@ __global__ void __launch_bounds__(256) k_flow_smooth(Geom g, const float *__rest
     if (!live) i4 = g.S - 4; // keep the lane in the shuffles with a valid address
     const int H1 = g.H - 1, W1 = g.W - 1;
     const int jm = j > 0 ? j - 1 : 0, jp = j < H1 ? j + 1 : H1;
-    float4 ru, rv;
-    const Row6 Um = load_row6<UPDATE>(g, wx, du, jm, i4, lane, nullptr), U0 = load_row6<UPDATE>(g, wx, du, j, i4, lane, &ru),
-               Up = load_row6<UPDATE>(g, wx, du, jp, i4, lane, nullptr);
-    const Row6 Vm = load_row6<UPDATE>(g, wy, dv, jm, i4, lane, nullptr), V0 = load_row6<UPDATE>(g, wy, dv, j, i4, lane, &rv),
-               Vp = load_row6<UPDATE>(g, wy, dv, jp, i4, lane, nullptr);
     const size_t o = (size_t)j * g.S + i4;
+    // ---- phase 1: every load of this thread
+    const RawRow rUm = load_raw<UPDATE>(g, wx, du, jm, i4, lane), rU0 = load_raw<UPDATE>(g, wx, du, j, i4, lane),
+                 rUp = load_raw<UPDATE>(g, wx, du, jp, i4, lane);
+    const RawRow rVm = load_raw<UPDATE>(g, wy, dv, jm, i4, lane), rV0 = load_raw<UPDATE>(g, wy, dv, j, i4, lane),
+                 rVp = load_raw<UPDATE>(g, wy, dv, jp, i4, lane);
+    const float4 wa = *reinterpret_cast<const float4 *>(w + o);
+    const float4 wb = *reinterpret_cast<const float4 *>(w + (size_t)jp * g.S + i4);
+    const float we = (lane == 31 && i4 + 4 <= W1) ? w[o + 4] : 0.0f;
+    // ---- phase 2: neighbour columns
+    const float4 ru = rU0.a, rv = rV0.a;
+    const Row6 Um = finish_row6(g, rUm, i4, lane), U0 = finish_row6(g, rU0, i4, lane), Up = finish_row6(g, rUp, i4, lane);
+    const Row6 Vm = finish_row6(g, rVm, i4, lane), V0 = finish_row6(g, rV0, i4, lane), Vp = finish_row6(g, rVp, i4, lane);
     // smoothness weights: row j columns i4..i4+4, row j+1 columns i4..i4+3
     float w0[5], w1[4];
     {
-        const float4 a = *reinterpret_cast<const float4 *>(w + o);
-        w0[0] = a.x; w0[1] = a.y; w0[2] = a.z; w0[3] = a.w;
-        const float from_r = __shfl_down_sync(0xffffffffu, a.x, 1);
-        w0[4] = (lane < 31) ? from_r : ((i4 + 4 <= W1) ? w[o + 4] : 0.0f);
-        const float4 b = *reinterpret_cast<const float4 *>(w + (size_t)jp * g.S + i4);
-        w1[0] = b.x; w1[1] = b.y; w1[2] = b.z; w1[3] = b.w;
+        w0[0] = wa.x; w0[1] = wa.y; w0[2] = wa.z; w0[3] = wa.w;
+        const float from_r = __shfl_down_sync(0xffffffffu, wa.x, 1);
+        w0[4] = (lane < 31) ? from_r : we;
+        w1[0] = wb.x; w1[1] = wb.y; w1[2] = wb.z; w1[3] = wb.w;
     }
     if (!live) return;
     const float cross = (mode != 0) ? 0.25f : 0.0f; // mode 0 (variational_aux_mt.cpp:30-60): forward differences only
