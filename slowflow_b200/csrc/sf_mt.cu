@@ -602,14 +602,20 @@ int sfgpu_normalize(sfgpu_ctx *c, color_image_t *const *seq, int F, sf_mt_params
     cudaStream_t st = c->stream;
     const Geom g{seq[0]->width, seq[0]->height, seq[0]->stride};
     const size_t P = g.plane();
+    // Short sequences (a window) stay resident between the two passes; long ones (a whole high-speed sequence, as the
+    // sharded driver normalises it) are streamed through ONE frame-sized buffer twice, so device memory stays bounded.
+    size_t resident_limit = (size_t)2 << 30;
+    if (const char *e = getenv("SLOWFLOW_GPU_NORMALIZE_RESIDENT_BYTES")) resident_limit = (size_t)strtoull(e, nullptr, 10); // tests
+    const bool resident = (size_t)F * 3 * P * sizeof(float) <= resident_limit;
+    const size_t fstride = resident ? 3 * P : 0;
     float *dev = nullptr;
     double *dsum = nullptr;
-    SF_CUDA(cudaMalloc(&dev, (size_t)F * 3 * P * sizeof(float)));
+    SF_CUDA(cudaMalloc(&dev, (resident ? (size_t)F : 1) * 3 * P * sizeof(float)));
     if (!cuda_ok(cudaMalloc(&dsum, (size_t)F * 6 * sizeof(double)), "cudaMalloc")) { cudaFree(dev); return SFGPU_ERR_CUDA; }
     cudaMemsetAsync(dsum, 0, (size_t)F * 6 * sizeof(double), st);
     for (int f = 0; f < F; f++) {
-        cudaMemcpyAsync(dev + (size_t)f * 3 * P, seq[f]->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st);
-        k_norm_sums<<<std::min(g.H, 592), 256, 0, st>>>(g, dev + (size_t)f * 3 * P, dsum + f * 6);
+        cudaMemcpyAsync(dev + (size_t)f * fstride, seq[f]->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st);
+        k_norm_sums<<<std::min(g.H, 592), 256, 0, st>>>(g, dev + (size_t)f * fstride, dsum + f * 6);
     }
     std::vector<double> hs((size_t)F * 6);
     cudaMemcpyAsync(hs.data(), dsum, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
@@ -623,8 +629,9 @@ int sfgpu_normalize(sfgpu_ctx *c, color_image_t *const *seq, int F, sf_mt_params
         sd[k] = sqrt((sd[k] / F) - avg[k] * avg[k]) / 255.0f; // :48-51
     }
     for (int f = 0; f < F; f++) {
-        k_norm_apply<<<grid2d(g.W, g.H), dim3(32, 8), 0, st>>>(g, dev + (size_t)f * 3 * P, avg[0], avg[1], avg[2], sd[0], sd[1], sd[2]);
-        cudaMemcpyAsync(seq[f]->c1, dev + (size_t)f * 3 * P, 3 * P * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (!resident) cudaMemcpyAsync(dev, seq[f]->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st);
+        k_norm_apply<<<grid2d(g.W, g.H), dim3(32, 8), 0, st>>>(g, dev + (size_t)f * fstride, avg[0], avg[1], avg[2], sd[0], sd[1], sd[2]);
+        cudaMemcpyAsync(seq[f]->c1, dev + (size_t)f * fstride, 3 * P * sizeof(float), cudaMemcpyDeviceToHost, st);
     }
     const bool ok = cuda_ok(cudaStreamSynchronize(st), "normalize apply");
     cudaFree(dev);

@@ -169,3 +169,16 @@ def test_raw_weighting_matches_oracle(ctx, oracle, red_x, red_y, weight):
     assert L.sfo_raw_weighting(b.ptr(), red_x, red_y, weight) == 0
     assert np.array_equal(a.buf, b.buf)
     assert np.allclose(a.array.sum(axis=0), 3.0)  # the three weights of a pixel always add up to 3
+
+
+def test_normalize_streaming_path_equals_resident(ctx, monkeypatch):
+    """Long sequences are normalised through one frame-sized device buffer (two passes); same result as resident."""
+    ims, _, _ = mh.window(120, 80, 3)
+    a, b = [f.copy() for f in ims], [f.copy() for f in ims]
+    pa, pb = mh.params(3), mh.params(3)
+    ctx.normalize(a, pa)
+    monkeypatch.setenv("SLOWFLOW_GPU_NORMALIZE_RESIDENT_BYTES", "0")
+    ctx.normalize(b, pb)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.array, y.array)
+    assert list(pa.img_norm_avg) == list(pb.img_norm_avg) and list(pa.img_norm_std) == list(pb.img_norm_std)
