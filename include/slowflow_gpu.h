@@ -230,6 +230,18 @@ int sfgpu_sor_coupled(sfgpu_ctx *ctx, image_t *du, image_t *dv, image_t *a11, im
                       const image_t *b1, const image_t *b2, const image_t *dpsis_horiz,
                       const image_t *dpsis_vert, int iterations, float omega);
 
+/* image.c:400-645, 658-688 and variational_aux.c:55-78 -- the separable filters and the derivative set the hot path
+ * computes on the fly, as stand-alone operators for tests.  order 1 = 3 taps, order 2 = 5 taps (coeffs[2*order+1]);
+ * color_image_convolve_hv: pass NULL coefficients for the direction that is skipped (like a NULL convolution_t*).
+ * get_derivatives uses the [1,-8,0,8,-1]/12 filter of variational.c:118-119. */
+int sfgpu_convolve_horiz(sfgpu_ctx *ctx, image_t *dst, const image_t *src, int order, const float *coeffs);
+int sfgpu_convolve_vert(sfgpu_ctx *ctx, image_t *dst, const image_t *src, int order, const float *coeffs);
+int sfgpu_color_image_convolve_hv(sfgpu_ctx *ctx, color_image_t *dst, const color_image_t *src, int horiz_order,
+                                  const float *horiz_coeffs, int vert_order, const float *vert_coeffs);
+int sfgpu_get_derivatives(sfgpu_ctx *ctx, const color_image_t *im1, const color_image_t *im2, color_image_t *dx,
+                          color_image_t *dy, color_image_t *dt, color_image_t *dxx, color_image_t *dxy, color_image_t *dyy,
+                          color_image_t *dxt, color_image_t *dyt);
+
 /* library / build identification, e.g. "slowflow_gpu 0.1 sm_100a" */
 const char *sfgpu_version(void);
 

@@ -43,6 +43,7 @@ ABI_SYMBOLS = [
     "sfgpu_compute_smoothness", "sfgpu_compute_data_and_match", "sfgpu_sub_laplacian", "sfgpu_sor_coupled",
     "sfgpu_version", "sfgpu_grid_mincut", "sfgpu_prescale_size", "sfgpu_prescale", "sfgpu_raw_weighting",
     "sfgpu_write_flo", "sfgpu_read_flo_size", "sfgpu_read_flo", "sfgpu_write_occlusion_pbm", "sfgpu_set_device", "sfgpu_get_device",
+    "sfgpu_convolve_horiz", "sfgpu_convolve_vert", "sfgpu_color_image_convolve_hv", "sfgpu_get_derivatives",
 ]
 
 
@@ -101,6 +102,10 @@ def load_library(path=None):
     lib.sfgpu_read_flo.argtypes = [C.c_char_p, IP, IP]
     lib.sfgpu_write_occlusion_pbm.argtypes = [C.c_char_p, IP]
     lib.sfgpu_set_device.argtypes = [C.c_int]
+    lib.sfgpu_convolve_horiz.argtypes = [C.c_void_p, IP, IP, C.c_int, FP]
+    lib.sfgpu_convolve_vert.argtypes = [C.c_void_p, IP, IP, C.c_int, FP]
+    lib.sfgpu_color_image_convolve_hv.argtypes = [C.c_void_p, CP, CP, C.c_int, FP, C.c_int, FP]
+    lib.sfgpu_get_derivatives.argtypes = [C.c_void_p] + [CP] * 10
     lib.sfgpu_grid_mincut.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_int, C.POINTER(C.c_int)]
     if path is None:
         _LIB = lib
@@ -242,6 +247,27 @@ class Context:
         _check(self.lib, self.lib.sfgpu_compute_data_and_match(self.h, a11.ptr(), a12.ptr(), a22.ptr(), b1.ptr(),
                                                                b2.ptr(), mask.ptr(), du.ptr(), dv.ptr(), im1.ptr(),
                                                                im2w.ptr(), hd, hg), "sfgpu_compute_data_and_match")
+
+    def convolve(self, dst, src, coeffs, vertical=False):
+        """convolve_horiz / convolve_vert (image.c:400-645) with 3 or 5 taps."""
+        arr = (C.c_float * len(coeffs))(*coeffs)
+        fn = self.lib.sfgpu_convolve_vert if vertical else self.lib.sfgpu_convolve_horiz
+        _check(self.lib, fn(self.h, dst.ptr(), src.ptr(), (len(coeffs) - 1) // 2, arr), "sfgpu_convolve")
+
+    def color_image_convolve_hv(self, dst, src, horiz=None, vert=None):
+        ha = (C.c_float * len(horiz))(*horiz) if horiz is not None else None
+        va = (C.c_float * len(vert))(*vert) if vert is not None else None
+        _check(self.lib, self.lib.sfgpu_color_image_convolve_hv(self.h, dst.ptr(), src.ptr(),
+                                                                (len(horiz) - 1) // 2 if horiz is not None else 0, ha,
+                                                                (len(vert) - 1) // 2 if vert is not None else 0, va),
+               "sfgpu_color_image_convolve_hv")
+
+    def get_derivatives(self, im1, im2):
+        """-> [dx, dy, dt, dxx, dxy, dyy, dxt, dyt] (variational_aux.c:55-78)."""
+        outs = [ColorImage(im1.width, im1.height) for _ in range(8)]
+        _check(self.lib, self.lib.sfgpu_get_derivatives(self.h, im1.ptr(), im2.ptr(), *[o.ptr() for o in outs]),
+               "sfgpu_get_derivatives")
+        return outs
 
     def sub_laplacian(self, dst, src, wh, wv):
         _check(self.lib, self.lib.sfgpu_sub_laplacian(self.h, dst.ptr(), src.ptr(), wh.ptr(), wv.ptr()),

@@ -571,6 +571,84 @@ int sfgpu_image_warp(sfgpu_ctx *c, color_image_t *dst, image_t *mask, const colo
     return SFGPU_OK;
 }
 
+static bool same_cgeom(const color_image_t *a, int w, int h, int s) { return a && a->c1 && a->width == w && a->height == h && a->stride == s; }
+
+static int convolve_planes(sfgpu_ctx *c, float *dst, const float *src, Geom g, int planes, int horder, const float *hc, int vorder,
+                           const float *vc, const char *what) {
+    if (!c || !dst || !src || (!hc && !vc) || (hc && (horder < 1 || horder > 2)) || (vc && (vorder < 1 || vorder > 2))) {
+        set_error(std::string(what) + ": bad argument (order 1 = 3 taps, 2 = 5 taps)");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    const size_t P = g.plane(), n = (size_t)planes * P;
+    int rc = c->ensure_io(3 * n);
+    if (rc != SFGPU_OK) return rc;
+    cudaStream_t st = c->stream;
+    float *d_src = c->io, *d_tmp = c->io + n, *d_dst = c->io + 2 * n;
+    SF_CUDA(cudaMemcpyAsync(d_src, src, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (hc && vc) { // image.c:665-680: horizontal into a temporary, then vertical
+        launch_convolve(st, g, d_src, d_tmp, false, horder, hc, planes);
+        launch_convolve(st, g, d_tmp, d_dst, true, vorder, vc, planes);
+        c->prof_acc.kernel_launches += 2;
+    } else {
+        launch_convolve(st, g, d_src, d_dst, vc != nullptr, hc ? horder : vorder, hc ? hc : vc, planes);
+        c->prof_acc.kernel_launches++;
+    }
+    SF_CUDA(cudaMemcpyAsync(dst, d_dst, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaStreamSynchronize(st));
+    return SFGPU_OK;
+}
+
+int sfgpu_convolve_horiz(sfgpu_ctx *c, image_t *dst, const image_t *src, int order, const float *coeffs) {
+    if (!src || !same_geom(dst, src->width, src->height, src->stride)) { set_error("sfgpu_convolve_horiz: geometry"); return SFGPU_ERR_ARG; }
+    return convolve_planes(c, dst->data, src->data, Geom{src->width, src->height, src->stride}, 1, order, coeffs, 0, nullptr, "sfgpu_convolve_horiz");
+}
+int sfgpu_convolve_vert(sfgpu_ctx *c, image_t *dst, const image_t *src, int order, const float *coeffs) {
+    if (!src || !same_geom(dst, src->width, src->height, src->stride)) { set_error("sfgpu_convolve_vert: geometry"); return SFGPU_ERR_ARG; }
+    return convolve_planes(c, dst->data, src->data, Geom{src->width, src->height, src->stride}, 1, 0, nullptr, order, coeffs, "sfgpu_convolve_vert");
+}
+int sfgpu_color_image_convolve_hv(sfgpu_ctx *c, color_image_t *dst, const color_image_t *src, int horiz_order, const float *horiz_coeffs,
+                                  int vert_order, const float *vert_coeffs) {
+    if (!src || !same_cgeom(dst, src->width, src->height, src->stride)) { set_error("sfgpu_color_image_convolve_hv: geometry"); return SFGPU_ERR_ARG; }
+    return convolve_planes(c, dst->c1, src->c1, Geom{src->width, src->height, src->stride}, 3, horiz_order, horiz_coeffs, vert_order, vert_coeffs,
+                           "sfgpu_color_image_convolve_hv");
+}
+
+// get_derivatives (variational_aux.c:55-78) with the 5-tap derivative filter of variational.c:118-119
+int sfgpu_get_derivatives(sfgpu_ctx *c, const color_image_t *im1, const color_image_t *im2, color_image_t *dx, color_image_t *dy,
+                          color_image_t *dt, color_image_t *dxx, color_image_t *dxy, color_image_t *dyy, color_image_t *dxt,
+                          color_image_t *dyt) {
+    if (!c || !im1 || !im1->c1) { set_error("sfgpu_get_derivatives: null argument"); return SFGPU_ERR_ARG; }
+    const int w = im1->width, h = im1->height, sd = im1->stride;
+    color_image_t *outs[8] = {dx, dy, dt, dxx, dxy, dyy, dxt, dyt};
+    if (!same_cgeom(im2, w, h, sd)) { set_error("sfgpu_get_derivatives: geometry"); return SFGPU_ERR_ARG; }
+    for (int k = 0; k < 8; k++)
+        if (!same_cgeom(outs[k], w, h, sd)) { set_error("sfgpu_get_derivatives: geometry"); return SFGPU_ERR_ARG; }
+    SF_CUDA(cudaSetDevice(c->device));
+    const Geom g{w, h, sd};
+    const size_t n = 3 * g.plane();
+    int rc = c->ensure_io(11 * n);
+    if (rc != SFGPU_OK) return rc;
+    cudaStream_t st = c->stream;
+    float *d1 = c->io, *d2 = d1 + n, *mean = d2 + n, *o[8];
+    for (int k = 0; k < 8; k++) o[k] = mean + (size_t)(k + 1) * n;
+    const float c5[5] = {1.0f / 12.0f, -8.0f / 12.0f, -0.0f, 8.0f / 12.0f, -(1.0f / 12.0f)};
+    SF_CUDA(cudaMemcpyAsync(d1, im1->c1, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    SF_CUDA(cudaMemcpyAsync(d2, im2->c1, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    launch_mean_diff(st, n, d1, d2, mean, o[2]);
+    launch_convolve(st, g, mean, o[0], false, 2, c5, 3); // dx
+    launch_convolve(st, g, mean, o[1], true, 2, c5, 3);  // dy
+    launch_convolve(st, g, o[0], o[3], false, 2, c5, 3); // dxx
+    launch_convolve(st, g, o[0], o[4], true, 2, c5, 3);  // dxy
+    launch_convolve(st, g, o[1], o[5], true, 2, c5, 3);  // dyy
+    launch_convolve(st, g, o[2], o[6], false, 2, c5, 3); // dxt
+    launch_convolve(st, g, o[2], o[7], true, 2, c5, 3);  // dyt
+    c->prof_acc.kernel_launches += 8;
+    for (int k = 0; k < 8; k++) SF_CUDA(cudaMemcpyAsync(outs[k]->c1, o[k], n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaStreamSynchronize(st));
+    return SFGPU_OK;
+}
+
 int sfgpu_compute_dpsis_weight(sfgpu_ctx *c, image_t *dst, const color_image_t *im, float coef, const float *avg3,
                                const float *std3, int hbit) {
     if (!c || !dst || !im) return SFGPU_ERR_ARG;

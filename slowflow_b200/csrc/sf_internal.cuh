@@ -115,6 +115,10 @@ void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im
                            const float *wy, const float *du, const float *dv, const float *ph, const float *pv,
                            float half_delta_over3, float half_gamma_over3, float *a11, float *a12, float *a22, float *b1,
                            float *b2);
+// convolve_horiz / convolve_vert over `planes` planes (operator twins; order 1 = 3 taps, 2 = 5 taps)
+void launch_convolve(cudaStream_t st, Geom g, const float *src, float *dst, bool vertical, int order, const float *coeffs,
+                     int planes);
+void launch_mean_diff(cudaStream_t st, size_t n, const float *im1, const float *im2, float *mean, float *dt);
 // sub_laplacian as a gather (operator twin)
 void launch_sub_laplacian(cudaStream_t st, Geom g, float *dst, const float *src, const float *ph, const float *pv);
 // in-place inverse of the 2x2 blocks (operator twin of the first SOR sweep's prologue)

@@ -273,6 +273,72 @@ void launch_update_smoothness(cudaStream_t st, Geom g, const float *wx, const fl
         launch_pdl(k_flow_smooth<true, false>, grid, b, 0, st, g, wx, wy, du, dv, w, alpha_factor, reg, mode, wx_out, wy_out, ph, pv);
 }
 
+// ------------------------------------------------------------------------------------------ separable filters
+// convolve_horiz / convolve_vert (image.c:400-645) with 3 or 5 taps over `planes` consecutive planes, all stride
+// columns like the reference: horizontal taps clamp the column to [0, W-1] (which is also what the reference's in-place
+// padding of src amounts to), vertical taps fold the coefficients of missing rows into the nearest row.  Operator
+// twins only -- the hot path never materialises a derivative plane.
+struct Taps5 {
+    float c[5];
+};
+template <bool VERT>
+__global__ void __launch_bounds__(256) k_convolve(Geom g, const float *__restrict__ src, float *__restrict__ dst, int order,
+                                                  Taps5 t, int planes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.S || j >= g.H) return;
+    const size_t P = g.plane();
+    const int W1 = g.W - 1, H = g.H;
+    const float *c = t.c;
+    for (int p = 0; p < planes; p++) {
+        const float *s = src + p * P;
+        const size_t o = (size_t)j * g.S + i;
+        float r;
+        if (!VERT) {
+            const float *row = s + (size_t)j * g.S;
+            if (order == 1) r = c[0] * row[clampi(i - 1, 0, W1)] + c[1] * row[clampi(i, 0, W1)] + c[2] * row[clampi(i + 1, 0, W1)];
+            else r = c[0] * row[clampi(i - 2, 0, W1)] + c[1] * row[clampi(i - 1, 0, W1)] + c[2] * row[clampi(i, 0, W1)] +
+                     c[3] * row[clampi(i + 1, 0, W1)] + c[4] * row[clampi(i + 2, 0, W1)];
+        } else {
+            auto at = [&](int dj) { return s[(size_t)clampi(j + dj, 0, H - 1) * g.S + i]; }; // only in-image rows are weighted
+            if (order == 1) {
+                if (j == 0) r = (c[0] + c[1]) * at(0) + c[2] * at(1);
+                else if (j == H - 1) r = c[0] * at(-1) + (c[1] + c[2]) * at(0);
+                else r = c[0] * at(-1) + c[1] * at(0) + c[2] * at(1);
+            } else {
+                if (j == 0) r = (c[0] + c[1] + c[2]) * at(0) + c[3] * at(1) + c[4] * at(2);
+                else if (j == 1) r = (c[0] + c[1]) * at(-1) + c[2] * at(0) + c[3] * at(1) + c[4] * at(2);
+                else if (j == H - 2) r = c[0] * at(-2) + c[1] * at(-1) + c[2] * at(0) + (c[3] + c[4]) * at(1);
+                else if (j == H - 1) r = c[0] * at(-2) + c[1] * at(-1) + (c[2] + c[3] + c[4]) * at(0);
+                else r = c[0] * at(-2) + c[1] * at(-1) + c[2] * at(0) + c[3] * at(1) + c[4] * at(2);
+            }
+        }
+        dst[p * P + o] = r;
+    }
+}
+void launch_convolve(cudaStream_t st, Geom g, const float *src, float *dst, bool vertical, int order, const float *coeffs,
+                     int planes) {
+    Taps5 t;
+    for (int k = 0; k < 5; k++) t.c[k] = (k < 2 * order + 1) ? coeffs[k] : 0.0f;
+    dim3 b(32, 8), grid((g.S + 31) / 32, (g.H + 7) / 8);
+    if (vertical) k_convolve<true><<<grid, b, 0, st>>>(g, src, dst, order, t, planes);
+    else k_convolve<false><<<grid, b, 0, st>>>(g, src, dst, order, t, planes);
+}
+
+// m = 0.5*(im2 + im1), dt = im2 - im1 over 3 planes (variational_aux.c:63-69)
+__global__ void __launch_bounds__(256) k_mean_diff(size_t n, const float *__restrict__ im1, const float *__restrict__ im2,
+                                                   float *__restrict__ mean, float *__restrict__ dt) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const float a = im1[k], b = im2[k];
+        mean[k] = 0.5f * (b + a);
+        dt[k] = b - a;
+    }
+}
+void launch_mean_diff(cudaStream_t st, size_t n, const float *im1, const float *im2, float *mean, float *dt) {
+    const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    k_mean_diff<<<blocks, 256, 0, st>>>(n, im1, im2, mean, dt);
+}
+
 // ------------------------------------------------------------------------------------------ small operators
 __global__ void __launch_bounds__(256) k_sub_laplacian(Geom g, float *__restrict__ dst, const float *__restrict__ src,
                                                        const float *__restrict__ ph, const float *__restrict__ pv) {

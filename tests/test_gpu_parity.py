@@ -224,3 +224,44 @@ def test_bad_arguments_are_reported(ctx):
     tiny = helpers.pair(4, 4)
     with pytest.raises(RuntimeError):
         ctx.variational(tiny[2], tiny[3], tiny[0], tiny[1], None)
+
+
+# ------------------------------------------------------------------ separable filters / derivative set (operator twins)
+@pytest.mark.parametrize("w,h", [(96, 64), (61, 45), (7, 5), (33, 6)])
+@pytest.mark.parametrize("taps", [3, 5])
+def test_convolve_horiz_vert(ctx, oracle, w, h, taps):
+    """convolve_horiz / convolve_vert (image.c:400-645): clamped columns, folded border rows, arbitrary coefficients."""
+    r = np.random.RandomState(w * 7 + h + taps)
+    src = helpers.rng_plane(w, h, w + h, -3, 3)
+    co = r.uniform(-1, 1, taps).astype(np.float32)
+    carr = (C.c_float * taps)(*co)
+    for vertical in (False, True):
+        g, o = helpers.new_like(src), helpers.new_like(src)
+        ctx.convolve(g, src, list(co), vertical=vertical)
+        fn = oracle.lib.sfo_convolve_vert if vertical else oracle.lib.sfo_convolve_horiz
+        fn(o.ptr(), src.ptr(), (taps - 1) // 2, carr)
+        assert relerr(g.array, o.array) <= 2e-6, (vertical, relerr(g.array, o.array))
+
+
+def test_color_image_convolve_hv_and_get_derivatives(ctx, oracle):
+    w, h = 93, 57
+    im1, im2, _, _ = helpers.pair(w, h)
+    c5 = [1 / 12.0, -8 / 12.0, 0.0, 8 / 12.0, -1 / 12.0]
+    c3 = [0.25, 0.5, 0.25]
+    # both directions = horizontal into a temporary, then vertical (image.c:665-680)
+    g = helpers.new_color_like(im1)
+    ctx.color_image_convolve_hv(g, im1, horiz=c5, vert=c3)
+    L = oracle.lib
+    from slowflow_b200 import Image
+    for k in range(3):
+        plane = Image.from_array(im1.array[k])
+        tmp, ref = helpers.new_like(plane), helpers.new_like(plane)
+        L.sfo_convolve_horiz(tmp.ptr(), plane.ptr(), 2, (C.c_float * 5)(*c5))
+        L.sfo_convolve_vert(ref.ptr(), tmp.ptr(), 1, (C.c_float * 3)(*c3))
+        assert relerr(g.array[k], ref.array) <= 2e-6
+    # the eight derivative images of variational_aux.c:55-78
+    outs = ctx.get_derivatives(im1, im2)
+    refs = [helpers.new_color_like(im1) for _ in range(8)]
+    L.sfo_get_derivatives(im1.ptr(), im2.ptr(), *[x.ptr() for x in refs])
+    for name, a, b in zip("dx dy dt dxx dxy dyy dxt dyt".split(), outs, refs):
+        assert relerr(a.array, b.array) <= 5e-6, (name, relerr(a.array, b.array))
