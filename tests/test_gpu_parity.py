@@ -265,3 +265,24 @@ def test_color_image_convolve_hv_and_get_derivatives(ctx, oracle):
     L.sfo_get_derivatives(im1.ptr(), im2.ptr(), *[x.ptr() for x in refs])
     for name, a, b in zip("dx dy dt dxx dxy dyy dxt dyt".split(), outs, refs):
         assert relerr(a.array, b.array) <= 5e-6, (name, relerr(a.array, b.array))
+
+
+@pytest.mark.parametrize("w,h", [(5, 5), (6, 9), (8, 8), (9, 31), (64, 6), (17, 5), (65, 65), (127, 5), (5, 127), (130, 67), (7, 40)])
+def test_two_frame_small_and_ragged_geometries(ctx, oracle, w, h):
+    """Edge geometries: narrower than a SOR tile / a marching strip, odd strides, a handful of rows.  Images this
+    small are all border, so the comparison runs over every pixel (border=0) with the field-level gate."""
+    p = variational_params_default()
+    p.niter_outer = 2
+    (gx, gy), (ox, oy), _ = _run_pair(ctx, oracle, w, h, p)
+    assert np.isfinite(gx.array).all() and np.isfinite(gy.array).all()
+    mean, mx = epe(gx.array, gy.array, ox.array, oy.array, border=0)
+    assert mean <= MEAN_TOL and mx <= MAX_TOL, (w, h, mean, mx)
+
+
+@pytest.mark.parametrize("w,h", [(17, 3), (3, 40), (4, 4)])
+def test_images_smaller_than_the_derivative_filter_are_rejected(ctx, w, h):
+    """The reference's 5-tap vertical filter reads rows j+-2 unconditionally (image.c:425-458): below 5x5 it reads out
+    of bounds.  The GPU path reports an error instead."""
+    im1, im2, wx, wy = helpers.pair(w, h)
+    with pytest.raises(RuntimeError, match="at least 5x5"):
+        ctx.variational(wx, wy, im1, im2, None)
