@@ -2,7 +2,7 @@
 // against the reference-shaped C++ shim (include/variational_mt_gpu.hpp) and the C ABI only: no CUDA, no OpenCV.
 //
 //   slow_flow_gpu --frames 'seq/frame_%d.ppm' --start 10 --jets 4 --out out/ [--S 3] [--skip 1] [--gpus N]
-//                 [--scale 0.5] [--occlusions] [--set key=value ...]
+//                 [--threads-per-gpu T] [--scale 0.5] [--occlusions] [--set key=value ...]
 //
 // What it reproduces of the reference (and what it does not):
 //   * frame indexing: frames = 1 + (Jets + 2)*steps images with index start - ref*skip + k*skip (slow_flow.cpp:411, 446-450);
@@ -21,6 +21,7 @@
 #include <string.h>
 #include <sys/stat.h>
 
+#include <chrono>
 #include <map>
 #include <sstream>
 #include <string>
@@ -117,7 +118,7 @@ static void make_dir(const std::string &d) {
 
 int main(int argc, char **argv) {
     std::string frames_fmt, out;
-    int start = 0, jets = 1, skip = 1, gpus = 0;
+    int start = 0, jets = 1, skip = 1, gpus = 0, per_gpu = 1;
     float scale = 1.0f;
     ParameterList cfg;
     cfg.insert("slow_flow_S", "3", true);
@@ -130,6 +131,7 @@ int main(int argc, char **argv) {
         else if (a == "--jets") jets = atoi(next().c_str());
         else if (a == "--skip") skip = atoi(next().c_str());
         else if (a == "--gpus") gpus = atoi(next().c_str());
+        else if (a == "--threads-per-gpu") per_gpu = atoi(next().c_str());
         else if (a == "--scale") scale = (float)atof(next().c_str());
         else if (a == "--S") cfg.insert("slow_flow_S", next(), true);
         else if (a == "--occlusions") cfg.insert("slow_flow_output_occlusions", "1", true);
@@ -146,6 +148,11 @@ int main(int argc, char **argv) {
     if (n_dev <= 0) die("no CUDA device (this path has no CPU fallback)");
     if (gpus <= 0 || gpus > n_dev) gpus = n_dev;
     if (gpus > jets) gpus = jets;
+    // more than one host thread per device keeps the GPU busy while another window sits in its host-side steps
+    // (occlusion min-cut, early-exit read-backs); every thread has its own context and stream
+    if (per_gpu < 1) per_gpu = 1;
+    int workers = gpus * per_gpu;
+    if (workers > jets) workers = jets;
 
     const int steps = cfg.parameter<int>("slow_flow_S", "2") - 1, ref = steps; // slow_flow.cpp:208-209
     if (steps < 1) die("slow_flow_S must be >= 2");
@@ -188,12 +195,13 @@ int main(int argc, char **argv) {
     name = name.substr(0, name.find_last_of('.'));
 
     // ---- one host thread per device, contiguous jet ranges (the reference's omp parallel for over jets, :706)
+    const auto t_loop = std::chrono::steady_clock::now();
     std::vector<std::thread> pool;
-    std::vector<int> done(gpus, 0);
-    for (int t = 0; t < gpus; t++) {
+    std::vector<int> done(workers, 0);
+    for (int t = 0; t < workers; t++) {
         pool.emplace_back([&, t]() {
-            if (sfgpu_set_device(t) != SFGPU_OK) die(sfgpu_last_error());
-            const int base = jets / gpus, extra = jets % gpus;
+            if (sfgpu_set_device(t % gpus) != SFGPU_OK) die(sfgpu_last_error());
+            const int base = jets / workers, extra = jets % workers;
             const int lo = t * base + (t < extra ? t : extra), hi = lo + base + (t < extra ? 1 : 0);
             Variational_MT minimzer_f, minimzer_b; // contexts are created on this thread's device at first use
             minimzer_f.setChannelWeights(channel_weights);
@@ -229,6 +237,8 @@ int main(int argc, char **argv) {
         });
     }
     for (auto &th : pool) th.join();
+    const double loop_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
+    printf("window loop: %.3f s, %.2f jets/s (forward + backward flow each)\n", loop_s, jets / loop_s);
 
     // ---- config.cfg for the next stage (:684-688)
     {
@@ -241,11 +251,11 @@ int main(int argc, char **argv) {
         fclose(f);
     }
     int total = 0;
-    for (int t = 0; t < gpus; t++) {
-        printf("device %d: %d jets\n", t, done[t]);
+    for (int t = 0; t < workers; t++) {
+        printf("worker %d (device %d): %d jets\n", t, t % gpus, done[t]);
         total += done[t];
     }
-    printf("%d jets, %dx%d, S=%d, %d device(s)\n", total, W, H, steps + 1, gpus);
+    printf("%d jets, %dx%d, S=%d, %d device(s), %d host thread(s) per device\n", total, W, H, steps + 1, gpus, per_gpu);
     for (auto im : seq) free_color_image(im);
     free_color_image(channel_weights);
     return total == jets ? 0 : 1;
