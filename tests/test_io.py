@@ -9,6 +9,8 @@ from slowflow_b200 import Image
 from slowflow_b200.api import read_flo, write_flo, write_occlusion_pbm
 from slowflow_b200.image import image_t
 
+pytestmark = pytest.mark.usefixtures("built")
+
 
 @pytest.mark.parametrize("w,h", [(64, 48), (61, 45), (1, 7), (130, 3)])
 def test_flo_bytes_match_reference_writer_and_round_trip(oracle, tmp_path, w, h):

@@ -12,6 +12,7 @@ import pytest
 
 from slowflow_b200.api import load_library
 
+pytestmark = pytest.mark.usefixtures("built")
 FP, IP = C.POINTER(C.c_float), C.POINTER(C.c_int)
 
 
