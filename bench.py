@@ -255,9 +255,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     affinity = _bind_to_gpu_numa_node(local)  # before any pinned allocation (first touch decides the NUMA node)
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner and warnings (NCCL_DEBUG=VERSION/WARN/INFO write to
+        # stdout by default) go to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # this level printf()s its banner straight to stdout
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     W, H, B = args.width, args.height, args.pairs
