@@ -166,6 +166,22 @@ def _cpu_worker(job):
     return float(x.array[0, 0])
 
 
+def _data_term_roofline(prof, peak_gbs, pixels, clocks_mhz):
+    """Second kernel of the path (k_prep_two_frame: warp + derivatives + data term + Laplacian + block inverse).  It sits
+    on the instruction-issue side of its ridge, so both ceilings are reported: HBM (52 B/px algorithmic) and
+    issue slots (warp instructions per launch from the committed ncu capture, profiles/r1e_ncu_full.csv: 49.6 M at
+    2560x1440 = 13.46 per pixel; 148 SMs x 4 schedulers x 1 instruction / clock)."""
+    if prof.data_ms <= 0 or prof.data_launches <= 0:
+        return None
+    t = prof.data_ms * 1e-3 / prof.data_launches
+    gbs = DATA_BYTES_PER_PX * prof.data_pixels / (prof.data_ms * 1e-3) / 1e9
+    warp_inst = 49604378.0 / (2560 * 1440) * pixels
+    issue_s = warp_inst / (148 * 4 * clocks_mhz * 1e6)
+    return {"kernel": "k_prep_two_frame", "achieved": gbs, "unit": "GB/s", "frac": gbs / peak_gbs, "avg_launch_ms": t * 1e3,
+            "hbm_bound_ms": DATA_BYTES_PER_PX * pixels / (peak_gbs * 1e9) * 1e3, "issue_bound_ms": issue_s * 1e3,
+            "issue_frac": issue_s / t, "bound": "issue"}
+
+
 def _bind_to_gpu_numa_node(index):
     """One host thread per device (north star): pin this process to the CPUs NVML reports as local to the GPU, so
     that its pinned staging buffers are allocated on the GPU's own NUMA node and H2D/D2H copies do not cross the
@@ -401,8 +417,7 @@ def run_ours(args):
         "avg_launch_ms": prof.sor_ms / max(1, prof.sor_launches), "launches": int(prof.sor_launches),
         "sor_share_of_step": prof.sor_ms / ms_local if ms_local > 0 else None,
         "instrumented_ms_per_step": ms_local / args.steps,
-        "data_term": {"achieved": (DATA_BYTES_PER_PX * prof.data_pixels / (prof.data_ms * 1e-3) / 1e9)
-                      if prof.data_ms > 0 else 0.0, "unit": "GB/s", "avg_launch_ms": prof.data_ms / max(1, prof.data_launches)},
+        "data_term": _data_term_roofline(prof, peak, W * H, clocks_mhz=1965.0),
     }
 
     line = {
