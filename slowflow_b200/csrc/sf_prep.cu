@@ -10,19 +10,23 @@
 // HBM traffic: read wx,wy (8 B/px) + im1 (12) + im2 through L1/L2 gathers (12) + psi_h,psi_v (8); write the five
 // system planes (20).  SURVEY 8(d) counts 52 B/px for this step.
 //
-// Work decomposition (no shared memory, no CTA barrier):
+// Work decomposition (no CTA barrier):
 //   * one WARP owns a strip of 64 columns (lane l = columns 2l, 2l+1) and marches down a segment of rows;
 //   * every per-row quantity is a packed (column 2l, column 2l+1) pair in one 64-bit register, so the vertical
 //     stencils, the robust weights and the 2x2 system run on FFMA2 (sf_pack.cuh);
-//   * vertical taps come from rolling 4-row register windows (m, z, Ix, Iy, Iyz per channel), horizontal taps from
-//     the neighbouring lanes by warp shuffle.  The 5-tap-of-5-tap stencil needs +-4 columns = 2 lanes, so lanes
-//     2..29 (56 columns) produce output and consecutive strips overlap by 8 columns;
+//   * vertical taps come from rolling 4-row windows (m, z, Ix, Iy, Iyz per channel = 60 packed values per lane) that
+//     live in the warp's PRIVATE slice of shared memory ([array][channel][slot][lane]: conflict-free 8-byte accesses, no
+//     synchronisation); horizontal taps come from the neighbouring lanes by warp shuffle.  The 5-tap-of-5-tap stencil
+//     needs +-4 columns = 2 lanes, so lanes 2..29 (56 columns) produce output and consecutive strips overlap by 8;
 //   * row r is loaded (and im2 warped) at step r; the output row of step r is o = r - 4.
+// Why shared-memory windows: with the windows in registers the slot of a row had to be a compile-time index, i.e. the
+// marching step was unrolled four times -- 255 registers (8 warps per SM) and a loop body of ~77 KB that thrashed the
+// instruction cache (ncu: 11 % of the stall samples "no instruction").  A run-time slot index into shared memory gives
+// a rolled loop, 168 registers, 12 resident warps per SM: 135.7 us -> 112.7 us per launch at 2560x1440.
 // Border semantics follow image.c:400-526: rows / columns outside the image are clamped at load time, which
 // reproduces the replicate border of the first derivative stage; the second stage (d/dx of Ix, d/dy of Iy)
 // replicates the first-stage VALUE, which is patched explicitly in edge strips / segments.
 #include <atomic>
-#include <type_traits>
 
 #include "sf_internal.cuh"
 #include "sf_pack.cuh"
@@ -32,11 +36,12 @@ namespace sf {
 
 constexpr int PR_OUT_LO = 2, PR_OUT_HI = 29;            // output lanes
 constexpr int PR_OUT_W = 2 * (PR_OUT_HI - PR_OUT_LO + 1); // 56 output columns per strip
-constexpr int PR_WARPS = 4;                             // warps per CTA (independent)
+constexpr int PR_WARPS = 2;                             // warps per CTA (independent; 2 x 15 KB of window storage)
+#ifndef SF_PREP_MINB
+#define SF_PREP_MINB 6 // resident CTAs per SM the register allocation aims at (6 x 2 warps, 6 x 30 KB of windows)
+#endif
+constexpr int PR_RING = 60 * 32;                        // packed values of one warp's windows
 
-struct Ring {
-    p64 m[3][4], z[3][4], ix[3][4], iy[3][4], iyz[3][4];
-};
 
 // per-lane geometry of the strip
 struct Lane {
@@ -122,7 +127,7 @@ __device__ __forceinline__ float warp_fetch(const float *__restrict__ src, const
 
 // One warp marches down its (strip, segment).  EDGE: the strip touches the left or right image border.
 template <bool COLOR, bool EDGE>
-__device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, const int seg, const int lane) {
+__device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, const int seg, const int lane, p64 *ring_sm) {
     const Geom g = a.g;
     const int W = g.W, H = g.H, H1 = H - 1, S = g.S;
     const int P = (int)g.plane();
@@ -149,11 +154,13 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
     const float eps_color = 0.001f * 0.001f, eps_grad = 0.001f * 0.001f;
     const float Wm1 = (float)(W - 1), Hm1 = (float)H1;
 
-    Ring R;
+    // rolling windows in the warp's slice of shared memory; the slot of a row is a run-time index
+    enum { RG_M = 0, RG_Z = 1, RG_IX = 2, RG_IYZ = 3, RG_IY = 4 };
+    p64 *const sm = ring_sm + lane;
+    auto rd = [&](int arr, int c, int s) -> p64 { return sm[((arr * 3 + c) * 4 + s) * 32]; };
+    auto wr = [&](int arr, int c, int s, p64 v) { sm[((arr * 3 + c) * 4 + s) * 32] = v; };
 #pragma unroll
-    for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int s = 0; s < 4; s++) R.m[c][s] = R.z[c][s] = R.ix[c][s] = R.iy[c][s] = R.iyz[c][s] = zero2;
+    for (int k = 0; k < 60; k++) sm[k * 32] = zero2;
 
     // software pipeline: im1 and the flow of the NEXT row to be warped are loaded one step ahead
     p64 An[3], fx, fy;
@@ -169,9 +176,8 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
 
     // one marching step; U = (r - Rbase) & 3 is the ring slot of row r.  Everything is computed unconditionally
     // (rows are clamped); only the stores are predicated, so every shuffle sits in straight-line code.
-    auto step = [&](auto Utag, const int r) {
-        constexpr int U = decltype(Utag)::value;
-        constexpr int U1 = (U + 1) & 3, U2 = (U + 2) & 3, U3 = (U + 3) & 3;
+    auto step = [&](const int U, const int r) {
+        const int U1 = (U + 1) & 3, U2 = (U + 2) & 3, U3 = (U + 3) & 3;
         const int rr = clampi(r, 0, H1);
         const int o = r - 4, oc = clampi(o, 0, H1);
         const bool out_row = (o >= Y0) && (o < Yend); // warp-uniform
@@ -205,11 +211,12 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
         p64 ix_new[3], ixx[3], ixz[3], ixy[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            ix_new[c] = hconv_pair(R.m[c][U2]);
+            ix_new[c] = hconv_pair(rd(RG_M, c, U2));
             if (EDGE) ix_new[c] = xedge_fix(ix_new[c], L, W);
-            ixx[c] = hconv_pair(R.ix[c][U]); // (columns outside the image were patched in Ix itself)
-            ixz[c] = hconv_pair(R.z[c][U]);
-            ixy[c] = vconv_pair(R.ix[c][U2], R.ix[c][U3], R.ix[c][U1], ix_new[c]);
+            ixx[c] = hconv_pair(rd(RG_IX, c, U)); // (columns outside the image were patched in Ix itself)
+            ixz[c] = hconv_pair(rd(RG_Z, c, U));
+            ixy[c] = vconv_pair(rd(RG_IX, c, U2), rd(RG_IX, c, U3), rd(RG_IX, c, U1), ix_new[c]);
+            wr(RG_IX, c, U2, ix_new[c]); // Ix of row r-6 is not needed any more: its slot takes row r-2
         }
         // psi_h of the left edge from the neighbouring lane (0 at column 0), psi_v of the row above (0 at row 0),
         // flow neighbours in row o, mask of the warp at row o
@@ -229,20 +236,20 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
         // ---- row r: m = (B + A)/2, z = B - A; first-stage y-derivatives of row r-2; Iyy of the output row; data term
         p64 n = zero2, s11 = zero2, s12 = zero2, s22 = zero2, sb1 = zero2, sb2 = zero2;
         p64 cn = zero2, c11 = zero2, c12 = zero2, c22 = zero2, cb1 = zero2, cb2 = zero2;
-        p64 iy_keep[3], iyz_keep[3], m_keep[3], z_keep[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const p64 m_new = mul2(add2(B[c], A[c]), half2);
             const p64 z_new = fma2(A[c], mone2, B[c]);
-            p64 iy_new = vconv_pair(R.m[c][U], R.m[c][U1], R.m[c][U3], m_new);
-            const p64 iyz_new = vconv_pair(R.z[c][U], R.z[c][U1], R.z[c][U3], z_new);
+            p64 iy_new = vconv_pair(rd(RG_M, c, U), rd(RG_M, c, U1), rd(RG_M, c, U3), m_new);
+            const p64 iyz_new = vconv_pair(rd(RG_Z, c, U), rd(RG_Z, c, U1), rd(RG_Z, c, U3), z_new);
             // second-stage replicate border in y: Iy of rows beyond the last row is Iy(H-1)
-            if (r - 2 > H1) iy_new = R.iy[c][U1];
-            p64 iy_m2 = R.iy[c][U2], iy_m1 = R.iy[c][U3];
-            if (o == 0) iy_m2 = iy_m1 = R.iy[c][U];     // rows -2, -1 take Iy(0)
-            else if (o == 1) iy_m2 = R.iy[c][U3];       // row -1 takes Iy(0)
-            const p64 iyy = vconv_pair(iy_m2, iy_m1, R.iy[c][U1], iy_new);
-            const p64 iyz = R.iyz[c][U];
+            const p64 iy_c = rd(RG_IY, c, U), iy_p1 = rd(RG_IY, c, U1), iy_b = rd(RG_IY, c, U3);
+            if (r - 2 > H1) iy_new = iy_p1;
+            p64 iy_m2 = rd(RG_IY, c, U2), iy_m1 = iy_b;
+            if (o == 0) iy_m2 = iy_m1 = iy_c;           // rows -2, -1 take Iy(0)
+            else if (o == 1) iy_m2 = iy_b;              // row -1 takes Iy(0)
+            const p64 iyy = vconv_pair(iy_m2, iy_m1, iy_p1, iy_new);
+            const p64 iyz = rd(RG_IYZ, c, U);
             // gradient constancy (variational_aux.c:268-296)
             const p64 ivx = rcp2(fma2(ixx[c], ixx[c], fma2(ixy[c], ixy[c], dnorm2)));
             const p64 ivy = rcp2(fma2(iyy, iyy, fma2(ixy[c], ixy[c], dnorm2)));
@@ -257,7 +264,7 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
             sb1 = fma2(qy, iyz, fma2(px, ixz[c], sb1));
             sb2 = fma2(sx, ixz[c], fma2(ty, iyz, sb2));
             if (COLOR) { // colour constancy (variational_aux.c:241-266)
-                const p64 ix = R.ix[c][U], iy = R.iy[c][U], iz = R.z[c][U];
+                const p64 ix = rd(RG_IX, c, U), iy = iy_c, iz = rd(RG_Z, c, U);
                 const p64 inv = rcp2(fma2(iy, iy, fma2(ix, ix, dnorm2)));
                 const p64 rc = fma2(iy, v, fma2(ix, u, iz));
                 cn = fma2(mul2(rc, rc), inv, cn);
@@ -268,7 +275,11 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
                 cb1 = fma2(gx, iz, cb1);
                 cb2 = fma2(gy, iz, cb2);
             }
-            iy_keep[c] = iy_new; iyz_keep[c] = iyz_new; m_keep[c] = m_new; z_keep[c] = z_new;
+            // rotate this channel's windows (every value of the slots being overwritten has been consumed above)
+            wr(RG_M, c, U, m_new);
+            wr(RG_Z, c, U, z_new);
+            wr(RG_IY, c, U2, iy_new);
+            wr(RG_IYZ, c, U2, iyz_new);
         }
         // ---- robust weights, system, Laplacian, block inverse
         const p64 tg = pk(mk0 * a.hg * rsqrtf(lo_of(n) + eps_grad), mk1 * a.hg * rsqrtf(hi_of(n) + eps_grad));
@@ -314,15 +325,7 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
             *reinterpret_cast<float2 *>(a.b2 + off) = make_float2(v0 ? lo_of(b2) : 0.0f, v1 ? hi_of(b2) : 0.0f);
         }
 
-        // ---- rotate the windows
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            R.m[c][U] = m_keep[c];
-            R.z[c][U] = z_keep[c];
-            R.ix[c][U2] = ix_new[c];
-            R.iy[c][U2] = iy_keep[c];
-            R.iyz[c][U2] = iyz_keep[c];
-        }
+        // ---- rotate the row windows of the Laplacian
         vt = vb;
         lu_m = lu_0; lu_0 = lu_p;
         lv_m = lv_0; lv_0 = lv_p;
@@ -330,24 +333,21 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
 
     const int Rend = Yend + 4; // last loaded row is Yend + 3
 #pragma unroll 1
-    for (int r = Rbase; r < Rend; r += 4) {
-        step(std::integral_constant<int, 0>{}, r);
-        step(std::integral_constant<int, 1>{}, r + 1);
-        step(std::integral_constant<int, 2>{}, r + 2);
-        step(std::integral_constant<int, 3>{}, r + 3);
-    }
+    for (int r = Rbase; r < Rend; r++) step((r - Rbase) & 3, r);
 }
 
 template <bool COLOR>
-__global__ void __launch_bounds__(PR_WARPS * 32) k_prep_two_frame(PrepArgs a) {
+__global__ void __launch_bounds__(PR_WARPS * 32, SF_PREP_MINB) k_prep_two_frame(PrepArgs a) {
     pdl_enter();
+    __shared__ p64 ring[PR_WARPS * PR_RING];
     const int lane = threadIdx.x & 31;
     const int work = blockIdx.x * PR_WARPS + (threadIdx.x >> 5);
     if (work >= a.nwork) return; // whole warp
     const int strip = work % a.strips, seg = work / a.strips;
     const int X0 = strip * PR_OUT_W - 2 * PR_OUT_LO;
-    if ((X0 < 0) || (X0 + 63 > a.g.W - 1)) prep_march<COLOR, true>(a, strip, seg, lane);
-    else prep_march<COLOR, false>(a, strip, seg, lane);
+    p64 *ring_sm = ring + (threadIdx.x >> 5) * PR_RING;
+    if ((X0 < 0) || (X0 + 63 > a.g.W - 1)) prep_march<COLOR, true>(a, strip, seg, lane, ring_sm);
+    else prep_march<COLOR, false>(a, strip, seg, lane, ring_sm);
 }
 
 // rows per segment: the largest number of (strip, segment) work items that is still ONE wave of resident warps
@@ -361,6 +361,25 @@ static int prep_seg_rows(Geom g, int num_sms, int resident_warps_per_sm) {
     return (rows + 3) & ~3;
 }
 
+template <bool COLOR>
+static void launch_prep_variant(cudaStream_t st, Geom g, int num_sms, PrepArgs &a) {
+    // resident warps per SM (the same on every device of the box: all are sm_100a; relaxed atomics because one host
+    // thread per device may get here at the same time)
+    static std::atomic<int> resident{0};
+    int res = resident.load(std::memory_order_relaxed);
+    if (!res) {
+        int blocks_per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_prep_two_frame<COLOR>, PR_WARPS * 32, 0);
+        res = (blocks_per_sm > 0 ? blocks_per_sm : 1) * PR_WARPS;
+        resident.store(res, std::memory_order_relaxed);
+    }
+    a.seg_rows = prep_seg_rows(g, num_sms, res);
+    const int segs = (g.H + a.seg_rows - 1) / a.seg_rows;
+    a.nwork = a.strips * segs;
+    const int blocks = (a.nwork + PR_WARPS - 1) / PR_WARPS;
+    launch_pdl(k_prep_two_frame<COLOR>, dim3(blocks), dim3(PR_WARPS * 32), 0, st, a);
+}
+
 void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im1, const float *im2, const float *wx,
                            const float *wy, const float *du, const float *dv, const float *ph, const float *pv,
                            float half_delta_over3, float half_gamma_over3, float *a11, float *a12, float *a22, float *b1,
@@ -371,24 +390,8 @@ void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im
     a.a11 = a11; a.a12 = a12; a.a22 = a22; a.b1 = b1; a.b2 = b2;
     a.hd = half_delta_over3; a.hg = half_gamma_over3;
     a.strips = (g.S + PR_OUT_W - 1) / PR_OUT_W;
-    // resident warps per SM of the two instantiations (the same on every device of the box: all are sm_100a;
-    // relaxed atomics because one host thread per device may get here at the same time)
-    static std::atomic<int> resident[2];
-    const int color = half_delta_over3 != 0.0f ? 1 : 0;
-    int res = resident[color].load(std::memory_order_relaxed);
-    if (!res) {
-        int blocks_per_sm = 0;
-        if (color) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_prep_two_frame<true>, PR_WARPS * 32, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_prep_two_frame<false>, PR_WARPS * 32, 0);
-        res = (blocks_per_sm > 0 ? blocks_per_sm : 1) * PR_WARPS;
-        resident[color].store(res, std::memory_order_relaxed);
-    }
-    a.seg_rows = prep_seg_rows(g, num_sms, res);
-    const int segs = (g.H + a.seg_rows - 1) / a.seg_rows;
-    a.nwork = a.strips * segs;
-    const int blocks = (a.nwork + PR_WARPS - 1) / PR_WARPS;
-    if (half_delta_over3 != 0.0f) launch_pdl(k_prep_two_frame<true>, dim3(blocks), dim3(PR_WARPS * 32), 0, st, a);
-    else launch_pdl(k_prep_two_frame<false>, dim3(blocks), dim3(PR_WARPS * 32), 0, st, a);
+    if (half_delta_over3 != 0.0f) launch_prep_variant<true>(st, g, num_sms, a);
+    else launch_prep_variant<false>(st, g, num_sms, a);
 }
 
 } // namespace sf
