@@ -169,13 +169,13 @@ def _cpu_worker(job):
 def _data_term_roofline(prof, peak_gbs, pixels, clocks_mhz):
     """Second kernel of the path (k_prep_two_frame: warp + derivatives + data term + Laplacian + block inverse).  It sits
     on the instruction-issue side of its ridge, so both ceilings are reported: HBM (52 B/px algorithmic) and
-    issue slots (warp instructions per launch from the committed ncu capture, profiles/r1e_ncu_full.csv: 49.6 M at
-    2560x1440 = 13.46 per pixel; 148 SMs x 4 schedulers x 1 instruction / clock)."""
+    issue slots (warp instructions per launch from the committed ncu capture, profiles/r1f_ncu_full.csv: 61.4 M at
+    2560x1440 = 16.66 per pixel; 148 SMs x 4 schedulers x 1 instruction / clock)."""
     if prof.data_ms <= 0 or prof.data_launches <= 0:
         return None
     t = prof.data_ms * 1e-3 / prof.data_launches
     gbs = DATA_BYTES_PER_PX * prof.data_pixels / (prof.data_ms * 1e-3) / 1e9
-    warp_inst = 49604378.0 / (2560 * 1440) * pixels
+    warp_inst = 61426542.0 / (2560 * 1440) * pixels
     issue_s = warp_inst / (148 * 4 * clocks_mhz * 1e6)
     return {"kernel": "k_prep_two_frame", "achieved": gbs, "unit": "GB/s", "frac": gbs / peak_gbs, "avg_launch_ms": t * 1e3,
             "hbm_bound_ms": DATA_BYTES_PER_PX * pixels / (peak_gbs * 1e9) * 1e3, "issue_bound_ms": issue_s * 1e3,
