@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Secondary measurement (not the bench.py metric): the multi-frame path on BASELINE configs 3 and 4.
+"""Secondary measurement (not the bench.py metric; lives under tests/ because --cpu times the oracle's reference objects): the multi-frame path on BASELINE configs 3 and 4.
 
-    python tools/mt_bench.py [--config 3|4] [--reps N] [--cpu]
+    python tests/bench_mt.py [--config 3|4] [--reps N] [--cpu]
 
 config 3: Variational_MT at 1280x1024, S=3 (5 frames), Geman-McClure eps 0.5, occlusion reasoning, 2 alternations x
           10 outer x 1 inner x 30 SOR, thresholds 1e-5
