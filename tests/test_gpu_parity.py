@@ -286,3 +286,33 @@ def test_images_smaller_than_the_derivative_filter_are_rejected(ctx, w, h):
     im1, im2, wx, wy = helpers.pair(w, h)
     with pytest.raises(RuntimeError, match="at least 5x5"):
         ctx.variational(wx, wy, im1, im2, None)
+
+
+# ------------------------------------------------------------------ size-independent properties at the bench geometry
+def test_full_size_properties_2560x1440(ctx):
+    """Properties that need no CPU run at 2560x1440: (1) identical frames with a zero initial flow are a fixed point of
+    the refinement (data term and smoothness both vanish); (2) the refinement of a sequence does not depend on how the
+    pairs are batched (one call vs. two calls over the same frames); (3) re-running on the same inputs is bit-identical
+    (no atomics / no run-to-run nondeterminism anywhere on the path)."""
+    w, h = 2560, 1440
+    f0 = ColorImage.from_array(synth.frame(w, h, 0))
+    zx, zy = Image(w, h), Image(w, h)
+    zx.buf[:] = 0
+    zy.buf[:] = 0
+    ctx.variational(zx, zy, f0, f0, None)
+    assert float(np.abs(zx.array).max()) <= 1e-5 and float(np.abs(zy.array).max()) <= 1e-5
+    frames = [f0] + [ColorImage.from_array(synth.frame(w, h, t)) for t in (1, 2)]
+    u0, v0 = synth.initial_flow(w, h)
+    a = [Image.from_array(u0) for _ in range(2)], [Image.from_array(v0) for _ in range(2)]
+    ctx.variational_sequence(frames, a[0], a[1], None)
+    b = [Image.from_array(u0) for _ in range(2)], [Image.from_array(v0) for _ in range(2)]
+    ctx.variational_sequence(frames[:2], b[0][:1], b[1][:1], None)
+    ctx.variational_sequence(frames[1:], b[0][1:], b[1][1:], None)
+    for j in range(2):
+        assert np.array_equal(a[0][j].array, b[0][j].array) and np.array_equal(a[1][j].array, b[1][j].array)
+    c = [Image.from_array(u0) for _ in range(2)], [Image.from_array(v0) for _ in range(2)]
+    ctx.variational_sequence(frames, c[0], c[1], None)
+    assert np.array_equal(a[0][1].array, c[0][1].array) and np.array_equal(a[1][0].array, c[1][0].array)
+    # the refinement moved the noisy initial flow towards the ground truth
+    gu, gv = synth.gt_flow(w, h)
+    assert epe(a[0][0].array, a[1][0].array, gu, gv, border=8)[0] < 0.5 * epe(u0, v0, gu, gv, border=8)[0]
