@@ -291,6 +291,7 @@ int sfgpu_create(int device, void *stream, sfgpu_ctx **out) {
     sfgpu_ctx *c = new sfgpu_ctx();
     c->device = device;
     if (const char *e = getenv("SLOWFLOW_GPU_DATA_VARIANT")) c->data_variant = atoi(e); // A/B switch for benchmarking
+    if (const char *e = getenv("SLOWFLOW_GPU_STAGED_COPIES")) c->staged_host_copies = atoi(e) != 0;
     c->num_sms = prop.multiProcessorCount;
     if (stream) {
         c->stream = (cudaStream_t)stream;
@@ -313,6 +314,7 @@ void sfgpu_destroy(sfgpu_ctx *c) {
     for (auto &p : c->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->ev_free) cudaEventDestroy(e);
     if (c->mtw) sf::mt_work_free(c->mtw);
+    if (c->stager) sf::host_stager_free(c->stager);
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
     if (c->h2d) cudaStreamDestroy(c->h2d);
@@ -429,14 +431,14 @@ int sfgpu_variational(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_image_
     if (rc != SFGPU_OK) return rc;
     float *d_im1 = c->io, *d_im2 = c->io + 3 * P, *d_wx = c->io + 6 * P, *d_wy = c->io + 7 * P;
     cudaStream_t st = c->stream;
-    SF_CUDA(cudaMemcpyAsync(d_im1, im1->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st));
-    SF_CUDA(cudaMemcpyAsync(d_im2, im2->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st));
-    SF_CUDA(cudaMemcpyAsync(d_wx, wx->data, P * sizeof(float), cudaMemcpyHostToDevice, st));
-    SF_CUDA(cudaMemcpyAsync(d_wy, wy->data, P * sizeof(float), cudaMemcpyHostToDevice, st));
+    // ordinary malloc'ed caller images (image.c:17-33) take the multi-threaded staged path of sf_hostcopy.cu
+    rc = host_copies(c, {{d_im1, im1->c1, 3 * P * sizeof(float)}, {d_im2, im2->c1, 3 * P * sizeof(float)},
+                         {d_wx, wx->data, P * sizeof(float)}, {d_wy, wy->data, P * sizeof(float)}}, true);
+    if (rc != SFGPU_OK) return rc;
     rc = run_two_frame(c, g, d_wx, d_wy, d_im1, d_im2, params);
     if (rc != SFGPU_OK) return rc;
-    SF_CUDA(cudaMemcpyAsync(wx->data, d_wx, P * sizeof(float), cudaMemcpyDeviceToHost, st));
-    SF_CUDA(cudaMemcpyAsync(wy->data, d_wy, P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    rc = host_copies(c, {{d_wx, wx->data, P * sizeof(float)}, {d_wy, wy->data, P * sizeof(float)}}, false);
+    if (rc != SFGPU_OK) return rc;
     SF_CUDA(cudaStreamSynchronize(st));
     return SFGPU_OK;
 }

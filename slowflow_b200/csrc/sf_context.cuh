@@ -7,6 +7,13 @@
 namespace sf {
 struct MtWork; // multi-frame workspace (sf_mt.cu), kept between calls
 void mt_work_free(MtWork *w);
+struct HostStager; // pinned bounce buffers for pageable caller memory (sf_hostcopy.cu)
+void host_stager_free(HostStager *h);
+struct HostCopy {
+    void *dev;
+    void *host;
+    size_t bytes;
+};
 } // namespace sf
 
 struct sfgpu_ctx {
@@ -45,6 +52,8 @@ struct sfgpu_ctx {
 
     sfgpu_mt_stats_t mt_stats{};
     sf::MtWork *mtw = nullptr;
+    sf::HostStager *stager = nullptr;
+    bool staged_host_copies = true; // env SLOWFLOW_GPU_STAGED_COPIES=0 switches the multi-threaded staging off
 
     // helpers
     int ensure_workspace(sf::Geom geom);
@@ -56,6 +65,8 @@ struct sfgpu_ctx {
 };
 
 namespace sf {
+// copies between caller (host) buffers and the device for one call, one direction (sf_hostcopy.cu)
+int host_copies(sfgpu_ctx *c, const std::vector<HostCopy> &list, bool h2d);
 // two-frame refinement on device planes (variational.c:19-82 + :101-143)
 int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d_im1, const float *d_im2,
                   const variational_params_t *params);

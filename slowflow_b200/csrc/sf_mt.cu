@@ -801,11 +801,15 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
     float *chw = channel_w ? take(3) : nullptr;
 
     // ---- upload
-    for (int f = 0; f < F; f++)
-        SF_CUDA(cudaMemcpyAsync(levels[0].frames[f], im[f]->c1, 3 * P0 * sizeof(float), cudaMemcpyHostToDevice, st));
-    SF_CUDA(cudaMemcpyAsync(wxa, wx->data, P0 * sizeof(float), cudaMemcpyHostToDevice, st));
-    SF_CUDA(cudaMemcpyAsync(wya, wy->data, P0 * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (chw) SF_CUDA(cudaMemcpyAsync(chw, channel_w->c1, 3 * P0 * sizeof(float), cudaMemcpyHostToDevice, st));
+    {
+        std::vector<HostCopy> up;
+        for (int f = 0; f < F; f++) up.push_back(HostCopy{levels[0].frames[f], im[f]->c1, 3 * P0 * sizeof(float)});
+        up.push_back(HostCopy{wxa, wx->data, P0 * sizeof(float)});
+        up.push_back(HostCopy{wya, wy->data, P0 * sizeof(float)});
+        if (chw) up.push_back(HostCopy{chw, channel_w->c1, 3 * P0 * sizeof(float)});
+        const int rcu = host_copies(c, up, true); // pageable caller frames: multi-threaded staging (sf_hostcopy.cu)
+        if (rcu != SFGPU_OK) return rcu;
+    }
 
     // ---- pyramid: GaussianBlur(sigma) + resize per frame and level (:604-614)
     if (L > 1) {
@@ -874,10 +878,15 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
     }
     if (rc != SFGPU_OK) return rc;
 
-    SF_CUDA(cudaMemcpyAsync(wx->data, cur_x, P0 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    SF_CUDA(cudaMemcpyAsync(wy->data, cur_y, P0 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (occlusions_out && occlusions_out->data && occlusions_out->width == W0 && occlusions_out->height == H0)
-        SF_CUDA(cudaMemcpyAsync(occlusions_out->data, occ, P0 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    {
+        std::vector<HostCopy> down;
+        down.push_back(HostCopy{cur_x, wx->data, P0 * sizeof(float)});
+        down.push_back(HostCopy{cur_y, wy->data, P0 * sizeof(float)});
+        if (occlusions_out && occlusions_out->data && occlusions_out->width == W0 && occlusions_out->height == H0)
+            down.push_back(HostCopy{occ, occlusions_out->data, P0 * sizeof(float)});
+        const int rcd = host_copies(c, down, false);
+        if (rcd != SFGPU_OK) return rcd;
+    }
     SF_CUDA(cudaStreamSynchronize(st));
     if (avg_change_out) { avg_change_out[0] = avg_change[0]; avg_change_out[1] = avg_change[1]; }
     c->mt_stats.total_ms = now_ms() - t_call;
