@@ -182,3 +182,14 @@ def test_normalize_streaming_path_equals_resident(ctx, monkeypatch):
     for x, y in zip(a, b):
         assert np.array_equal(x.array, y.array)
     assert list(pa.img_norm_avg) == list(pb.img_norm_avg) and list(pa.img_norm_std) == list(pb.img_norm_std)
+
+
+def test_mt_config4_2560x1440_three_layers_bounded(ctx, mt_checker):
+    """BASELINE config 4 geometry: 2560x1440, zero initial flow, 3 pyramid layers (2560x1440 -> 2304x1296 -> 2073x1166,
+    stride 2076), bounded to one outer iteration per level so that the CPU reference finishes in about a minute."""
+    ims, wx, wy = mh.window(2560, 1440, 3, zero_flow=True)
+    p = mh.params(3, layers=3, niter_alter=1, niter_outer=1, robust_color=4, robust_color_eps=0.5)
+    r = mh.run_cpu(*mt_checker, ims, wx, wy, p, SOR_REDBLACK)
+    g = mh.run_gpu(ctx, ims, wx, wy, p)
+    assert g["stats"].levels == 3
+    check(g, r, "config 4 (bounded)")
