@@ -267,21 +267,25 @@ __global__ void __launch_bounds__(256) k_data_term(Geom g, DataTermDesc t, DataC
                           (y0 + DT_TH + DT_HALO <= g.H);
     const float zs = (t.zsign > 0) ? 1.0f : -1.0f;
 
-    // ---- stage 1
+    // ---- stage 1 (interior tiles: 2-D thread mapping, no per-element index division: lane = channel * 10 + float4
+    // column, warp ty takes rows ty, ty+8, ...)
+    const int tx = threadIdx.x, ty = threadIdx.y;
     if (interior) {
         constexpr int Q = DT_MW / 4; // float4 per row
-        for (int idx = tid; idx < 3 * DT_MH * Q; idx += 256) {
-            const int c = idx / (DT_MH * Q);
-            const int rem = idx - c * (DT_MH * Q);
-            const int ry = rem / Q, q = rem - ry * Q;
-            const size_t o = (size_t)c * P + (size_t)(y0 - DT_HALO + ry) * g.S + (x0 - DT_HALO + 4 * q);
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(t.A + o));
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(t.B + o));
-            const int so = (c * DT_MH + ry) * DT_MW + 4 * q;
-            *reinterpret_cast<float4 *>(sm_m + so) =
-                make_float4(0.5f * (b.x + a.x), 0.5f * (b.y + a.y), 0.5f * (b.z + a.z), 0.5f * (b.w + a.w));
-            *reinterpret_cast<float4 *>(sm_z + so) =
-                make_float4(zs * (b.x - a.x), zs * (b.y - a.y), zs * (b.z - a.z), zs * (b.w - a.w));
+        if (tx < 3 * Q) {
+            const int c = tx / Q, q = tx - c * Q;
+            const size_t base = (size_t)c * P + (size_t)(y0 - DT_HALO) * g.S + (x0 - DT_HALO + 4 * q);
+#pragma unroll
+            for (int ry = ty; ry < DT_MH; ry += 8) {
+                const size_t o = base + (size_t)ry * g.S;
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(t.A + o));
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(t.B + o));
+                const int so = (c * DT_MH + ry) * DT_MW + 4 * q;
+                *reinterpret_cast<float4 *>(sm_m + so) =
+                    make_float4(0.5f * (b.x + a.x), 0.5f * (b.y + a.y), 0.5f * (b.z + a.z), 0.5f * (b.w + a.w));
+                *reinterpret_cast<float4 *>(sm_z + so) =
+                    make_float4(zs * (b.x - a.x), zs * (b.y - a.y), zs * (b.z - a.z), zs * (b.w - a.w));
+            }
         }
     } else {
         for (int idx = tid; idx < 3 * DT_MH * DT_MW; idx += 256) {
@@ -299,28 +303,30 @@ __global__ void __launch_bounds__(256) k_data_term(Geom g, DataTermDesc t, DataC
 
     // ---- stage 2: Ix on (tile+2)^2 -- columns outside the image take the value at the clamped column
     // (the reference convolves Ix itself with replicate borders, image.c:475-516) -- and Iy on tile columns.
-    for (int idx = tid; idx < 3 * DT_XH * DT_XW; idx += 256) {
-        const int c = idx / (DT_XH * DT_XW);
-        const int rem = idx - c * (DT_XH * DT_XW);
-        const int ry = rem / DT_XW, rx = rem - ry * DT_XW;
+    // Columns 0..31 of a row go to the 32 lanes of a warp, rows ty, ty+8, ...; the 4 remaining Ix columns of 8 rows
+    // make one more warp-wide pass per channel.
+    auto ix_at = [&](int c, int ry, int rx) {
         const int gx = interior ? (x0 - 2 + rx) : clampi(x0 - 2 + rx, 0, W1);
         const int mx = gx - (x0 - DT_HALO);
         const float *row = sm_m + (c * DT_MH + (ry + 2)) * DT_MW;
         sm_ix[(c * DT_XH + ry) * DT_XW + rx] = hconv5(row[mx - 2], row[mx - 1], row[mx], row[mx + 1], row[mx + 2]);
-    }
-    for (int idx = tid; idx < 3 * DT_XH * DT_TW; idx += 256) {
-        const int c = idx / (DT_XH * DT_TW);
-        const int rem = idx - c * (DT_XH * DT_TW);
-        const int ry = rem / DT_TW, rx = rem - ry * DT_TW;
-        const float *col = sm_m + (c * DT_MH + (ry + 2)) * DT_MW + (rx + DT_HALO);
-        sm_iy[(c * DT_XH + ry) * DT_TW + rx] =
-            interior ? hconv5(col[-2 * DT_MW], col[-DT_MW], col[0], col[DT_MW], col[2 * DT_MW])
-                     : vconv5(col[-2 * DT_MW], col[-DT_MW], col[0], col[DT_MW], col[2 * DT_MW], y0 - 2 + ry, g.H);
+    };
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        for (int ry = ty; ry < DT_XH; ry += 8) {
+            ix_at(c, ry, tx);
+            const float *col = sm_m + (c * DT_MH + (ry + 2)) * DT_MW + (tx + DT_HALO);
+            sm_iy[(c * DT_XH + ry) * DT_TW + tx] =
+                interior ? hconv5(col[-2 * DT_MW], col[-DT_MW], col[0], col[DT_MW], col[2 * DT_MW])
+                         : vconv5(col[-2 * DT_MW], col[-DT_MW], col[0], col[DT_MW], col[2 * DT_MW], y0 - 2 + ry, g.H);
+        }
+        // Ix columns 32..35: lane -> (row within a group of 8, column); warp ty takes row groups ty, ty+8, ...
+        for (int ry = ty * 8 + (tx >> 2); ry < DT_XH; ry += 64) ix_at(c, ry, DT_TW + (tx & 3));
     }
     __syncthreads();
 
     // ---- stage 3
-    const int lx = threadIdx.x;
+    const int lx = tx;
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
         const int ly = threadIdx.y + 8 * k;
