@@ -21,7 +21,7 @@ with tempfile.TemporaryDirectory() as d:
         with open(os.path.join(d, "frame_%d.ppm" % k), "wb") as fh:
             fh.write(b"P6\n%d %d\n255\n" % (W, H))
             fh.write(np.ascontiguousarray(f.transpose(1, 2, 0)).tobytes())
-    for tpg in (1, 2, 3):
+    for tpg in (1, 2):
         out = os.path.join(d, "out%d" % tpg)
         r = subprocess.run([os.path.join(ROOT, "slowflow_b200", "lib", "slow_flow_gpu"), "--frames", os.path.join(d, "frame_%d.ppm"),
                             "--out", out, "--start", str(steps), "--jets", str(JETS), "--S", str(S), "--threads-per-gpu", str(tpg),
