@@ -109,8 +109,17 @@ static int staged_batch(sfgpu_ctx *c, const std::vector<HostCopy> &list, bool h2
         for (auto &pr : pending) memcpy(pr.second->host, hs.slot[w][pr.first], pr.second->bytes);
     };
     std::vector<std::thread> pool;
-    for (int w = 1; w < HC_WORKERS; w++) pool.emplace_back(work, w);
+    int inline_from = HC_WORKERS; // workers that could not get a thread run on the calling thread
+    for (int w = 1; w < HC_WORKERS; w++) {
+        try {
+            pool.emplace_back(work, w);
+        } catch (...) {
+            inline_from = w;
+            break;
+        }
+    }
     work(0);
+    for (int w = inline_from; w < HC_WORKERS; w++) work(w);
     for (auto &t : pool) t.join();
     for (int w = 0; w < HC_WORKERS; w++)
         if (failed[w]) {
