@@ -14,8 +14,8 @@
 
 namespace sf {
 
-constexpr size_t HC_CHUNK = (size_t)4 << 20; // bytes per slot
-constexpr int HC_WORKERS = 4, HC_SLOTS = 2;
+constexpr size_t HC_CHUNK = (size_t)1 << 20; // bytes per slot
+constexpr int HC_WORKERS = 4, HC_SLOTS = 4;
 
 struct HostStager {
     unsigned char *slot[HC_WORKERS][HC_SLOTS] = {};
