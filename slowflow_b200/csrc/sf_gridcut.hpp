@@ -11,7 +11,7 @@
 // sink only: a forest T of pixels with a non-saturated path to the sink grows over residual arcs; touching a pixel that
 // still has source capacity closes an augmenting path source -> pixel -> ... -> root -> sink.  Orphans are re-attached
 // as in Boykov-Kolmogorov (sink tree only, with their time-stamp / distance heuristics).  Work is proportional to the
-// explored forest, not to W*H; per call the O(W*H) part is four memsets.
+// explored forest, not to W*H; per call the O(W*H) part is four memsets (32-bit flows, no time-stamp clearing).
 //   * arcs are implicit: f_right[p], f_down[p] = net flow p -> right / lower neighbour in [-cap, cap];
 //     residual(p -> q) = cap - f(p -> q).  No capacity arrays to initialise.
 //   * labels are canonical: label 1 <=> the pixel can still reach the sink in the residual graph of a maximum flow
@@ -33,22 +33,36 @@ public:
     // On return in_forest()[p] != P_NONE  <=>  label 1.  tr is modified in place (residual terminal capacities).
     cap_t solve(int w, int h, cap_t *tr_io, cap_t pair_cap) {
         W = w; H = h; N = w * h; tr = tr_io; cap = pair_cap;
-        fr.assign((size_t)N, 0);
-        fd.assign((size_t)N, 0);
+        // net flows fit 32 bits whenever the neighbour capacity does (|f| <= cap): half the memory to clear
+        narrow = pair_cap >= 0 && pair_cap < ((cap_t)1 << 30);
+        if (narrow) {
+            fr32.assign((size_t)N, 0);
+            fd32.assign((size_t)N, 0);
+        } else {
+            fr64.assign((size_t)N, 0);
+            fd64.assign((size_t)N, 0);
+        }
         parent.assign((size_t)N, (uint8_t)P_NONE);
-        ts.assign((size_t)N, 0);
+        // time stamps keep counting across calls, so stale stamps of an earlier solve can never equal the current time
+        // and the stamp array needs no clearing (it is cleared when it grows or before the counter could wrap)
+        if (ts.size() != (size_t)N || time_ > (1 << 30)) {
+            ts.assign((size_t)N, 0);
+            time_ = 0;
+        }
         dist.resize((size_t)N);
         queued.assign((size_t)N, 0);
         active.clear();
         head = 0;
         orphans.clear();
         ohead = 0;
-        time_ = 0;
+        time_++; // roots are stamped with the time of this solve's start
         flow_ = 0;
+        const int t0 = time_;
         for (int p = 0; p < N; p++)
             if (tr[p] < 0) {
                 parent[p] = P_TERMINAL;
                 dist[p] = 1;
+                ts[p] = t0;
                 push_active(p);
             }
         for (;;) {
@@ -65,7 +79,9 @@ private:
     int W = 0, H = 0, N = 0;
     cap_t *tr = nullptr;
     cap_t cap = 0, flow_ = 0;
-    std::vector<cap_t> fr, fd;   // net flow towards the right / lower neighbour
+    bool narrow = true;
+    std::vector<int32_t> fr32, fd32; // net flow towards the right / lower neighbour (|f| <= cap < 2^30)
+    std::vector<cap_t> fr64, fd64;   // the same for larger capacities
     std::vector<uint8_t> parent; // direction of the parent arc (towards the sink), or a P_* marker
     std::vector<int> ts, dist;   // BK distance-to-terminal cache
     std::vector<uint8_t> queued;
@@ -85,19 +101,37 @@ private:
     }
     // residual capacity of the arc p -> nb(p, d) (the neighbour must exist)
     inline cap_t res(int p, int d) const {
+        if (narrow) {
+            switch (d) {
+            case P_LEFT: return cap + fr32[p - 1];
+            case P_RIGHT: return cap - fr32[p];
+            case P_UP: return cap + fd32[p - W];
+            default: return cap - fd32[p];
+            }
+        }
         switch (d) {
-        case P_LEFT: return cap + fr[p - 1];
-        case P_RIGHT: return cap - fr[p];
-        case P_UP: return cap + fd[p - W];
-        default: return cap - fd[p];
+        case P_LEFT: return cap + fr64[p - 1];
+        case P_RIGHT: return cap - fr64[p];
+        case P_UP: return cap + fd64[p - W];
+        default: return cap - fd64[p];
         }
     }
     inline void send(int p, int d, cap_t x) { // x units along p -> nb(p, d)
+        if (narrow) {
+            const int32_t y = (int32_t)x;
+            switch (d) {
+            case P_LEFT: fr32[p - 1] -= y; break;
+            case P_RIGHT: fr32[p] += y; break;
+            case P_UP: fd32[p - W] -= y; break;
+            default: fd32[p] += y; break;
+            }
+            return;
+        }
         switch (d) {
-        case P_LEFT: fr[p - 1] -= x; break;
-        case P_RIGHT: fr[p] += x; break;
-        case P_UP: fd[p - W] -= x; break;
-        default: fd[p] += x; break;
+        case P_LEFT: fr64[p - 1] -= x; break;
+        case P_RIGHT: fr64[p] += x; break;
+        case P_UP: fd64[p - W] -= x; break;
+        default: fd64[p] += x; break;
         }
     }
     void push_active(int i) {

@@ -86,3 +86,14 @@ def test_mincut_matches_oracle_labels(oracle, w, h, seed, kind):
     assert np.array_equal(a, b), "labels differ at %d of %d pixels" % (int((a != b).sum()), n)
     if kind in ("occlusion", "blobs"):
         assert 0 < a.sum() < n  # both labels occur
+
+
+def test_reused_cut_object_equals_fresh_ones(tmp_path):
+    """tests/cpp_mincut_reuse.cpp: 300 solves on one reused object vs fresh objects (sizes and capacities change)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "reuse")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(root, "tests", "cpp_mincut_reuse.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout + r.stderr
