@@ -21,6 +21,8 @@
 #ifndef SLOWFLOW_GPU_H_
 #define SLOWFLOW_GPU_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -128,10 +130,31 @@ int sfgpu_variational_dev(sfgpu_ctx *ctx, float *d_wx, float *d_wy, const float 
 /* Pipelined sequence refinement (config 5; the shard loop of slow_flow.cpp:706 / adaptiveFR.cpp:496):
  * n_pairs consecutive frame pairs (pair j = frames[j], frames[j+1]); wx[j], wy[j] in/out.
  * Host buffers; uploads of pair j+1 and downloads of pair j-1 overlap the solve of pair j, and a
- * frame shared by two pairs is uploaded once.  Pinned host memory is used as given if the buffers
- * were registered with sfgpu_host_register, otherwise staged. */
+ * frame shared by two pairs is uploaded once.  Page-locked host memory (cudaMallocHost / sfgpu_host_register) is
+ * pipelined as given; ordinary pageable memory (the reference's image_new) is staged pair by pair through the context's
+ * page-locked slots by a few host threads (fast, but without overlap between pairs). */
 int sfgpu_variational_sequence(sfgpu_ctx *ctx, int n_pairs, const color_image_t *const *frames,
                                image_t *const *wx, image_t *const *wy, const variational_params_t *params);
+
+/* The same pipeline fed with the INTEGER images the reference holds before its float conversion: 8-bit frames as
+ * adaptiveFR.cpp:450-464 has them (cv::Mat CV_8UC1 / CV_8UC3 -> mat2colorImg<uchar> / colorMat2colorImg<Vec3b>,
+ * utils/utils.h:122-160) and 16-bit frames as slow_flow.cpp:470-477 loads them (CV_16UC1/3 -> convertTo(CV_32F)).
+ * The fields are the cv::Mat fields those converters read.  channels == 1: the grey value goes to all three planes;
+ * channels == 3: interleaved sample c of a pixel goes to plane c.  The conversion runs on the device and is exact
+ * (every 8-/16-bit integer is a float), so results are identical to converting on the host and calling
+ * sfgpu_variational_sequence -- but a 2560x1440 frame crosses PCIe as 11 (22) MB instead of 44 MB.
+ * continue_from_previous != 0: frames[0] is the last frame of the previous sequence call on this context (same
+ * geometry, no other call in between); it is still resident in the device ring and is not uploaded again. */
+typedef struct sf_frame_int_s {
+    int width, height;
+    int channels;       /* 1 or 3 */
+    size_t step;        /* bytes per row (cv::Mat::step) */
+    const void *data;   /* unsigned char (u8 entry) or unsigned short (u16 entry) samples */
+} sf_frame_int_t;
+int sfgpu_variational_sequence_u8(sfgpu_ctx *ctx, int n_pairs, const sf_frame_int_t *frames, image_t *const *wx,
+                                  image_t *const *wy, const variational_params_t *params, int continue_from_previous);
+int sfgpu_variational_sequence_u16(sfgpu_ctx *ctx, int n_pairs, const sf_frame_int_t *frames, image_t *const *wx,
+                                   image_t *const *wy, const variational_params_t *params, int continue_from_previous);
 
 /* page-lock / unlock a host range so transfers are asynchronous (cudaHostRegister) */
 int sfgpu_host_register(void *ptr, unsigned long long bytes);
@@ -221,6 +244,15 @@ int sfgpu_compute_data_and_match(sfgpu_ctx *ctx, image_t *a11, image_t *a12, ima
                                  image_t *b2, const image_t *mask, const image_t *du, const image_t *dv,
                                  const color_image_t *im1, const color_image_t *im2w,
                                  float half_delta_over3, float half_gamma_over3);
+/* The PRODUCTION kernel of the default two-frame path (k_prep_two_frame) as an operator: one outer iteration's
+ * image_warp -> get_derivatives -> compute_data_and_match -> sub_laplacian x2 (variational_aux.c:18-78, 153-180, 215-302)
+ * followed by the in-place block inverse of sor_coupled's first sweep (solver.c:101-106).  im2 is the UNWARPED second
+ * image; wx, wy warp it and are the argument of the Laplacian; du, dv may be NULL (zero increment).  Whole planes are
+ * written, stride padding included (zeros). */
+int sfgpu_prep_two_frame(sfgpu_ctx *ctx, image_t *a11, image_t *a12, image_t *a22, image_t *b1, image_t *b2,
+                         const color_image_t *im1, const color_image_t *im2, const image_t *wx, const image_t *wy,
+                         const image_t *du, const image_t *dv, const image_t *dpsis_horiz, const image_t *dpsis_vert,
+                         float half_delta_over3, float half_gamma_over3);
 /* variational_aux.c:153 */
 int sfgpu_sub_laplacian(sfgpu_ctx *ctx, image_t *dst, const image_t *src, const image_t *weight_horiz,
                         const image_t *weight_vert);

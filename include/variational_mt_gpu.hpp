@@ -80,12 +80,29 @@ template <class Params> inline void sf_mt_params_from_list(Params &p, sf_mt_para
     }
 }
 
+// One context per host thread and device, shared by every Variational_MT object and normalize() call of that thread:
+// the unmodified call sites construct a minimiser per jet (slow_flow.cpp:875, :1018) and call normalize() per window
+// (:673); with a context per object each window would pay context creation and a ~1 GB workspace allocation.  The
+// contexts are destroyed when the thread exits.
+inline sfgpu_ctx *sf_shim_thread_context() {
+    struct Cache {
+        enum { MAXDEV = 64 };
+        sfgpu_ctx *ctx[MAXDEV];
+        Cache() { for (int k = 0; k < MAXDEV; k++) ctx[k] = NULL; }
+        ~Cache() { for (int k = 0; k < MAXDEV; k++) if (ctx[k]) sfgpu_destroy(ctx[k]); }
+    };
+    static thread_local Cache cache;
+    int dev = sfgpu_get_device();
+    if (dev < 0 || dev >= Cache::MAXDEV) dev = 0;
+    if (!cache.ctx[dev] && sfgpu_create(dev, NULL, &cache.ctx[dev]) != SFGPU_OK) return NULL;
+    return cache.ctx[dev];
+}
+
 class Variational_MT {
 public:
-    Variational_MT() : one_direction(false), ctx_(NULL), channel_w_(NULL) { occ_.data = NULL; }
+    Variational_MT() : one_direction(false), channel_w_(NULL) { occ_.data = NULL; }
     ~Variational_MT() {
         if (occ_.data) free(occ_.data);
-        if (ctx_) sfgpu_destroy(ctx_);
     }
     void setChannelWeights(color_image_t *weights) { channel_w_ = weights; }
     image_t *getOcclusions() { return occ_.data ? &occ_ : NULL; }
@@ -96,15 +113,18 @@ public:
         params.insert("final", "0", true);
         sf_mt_params_t m;
         sf_mt_params_from_list(params, &m);
+        // the reference latches the member once the key says "forward" (variational_mt.cpp:548-549): it stays set for
+        // later calls on the same object even if their parameters lack the key
+        if (m.one_direction) one_direction = true;
         if (one_direction) m.one_direction = 1;
-        if (!ctx_) { // on the calling thread's current device: one host thread per device (slow_flow.cpp:706)
-            if (sfgpu_create(-1, NULL, &ctx_) != SFGPU_OK) fail();
-        }
+        // on the calling thread's current device: one host thread per device (slow_flow.cpp:706)
+        sfgpu_ctx *ctx = sf_shim_thread_context();
+        if (!ctx) fail();
         if (occ_.data) free(occ_.data);
         occ_.width = wx->width; occ_.height = wx->height; occ_.stride = wx->stride;
         occ_.data = (float *)calloc((size_t)wx->stride * wx->height, sizeof(float));
         float avg[2] = {0.f, 0.f};
-        if (sfgpu_variational_mt(ctx_, wx, wy, im, &m, channel_w_, &occ_, avg) != SFGPU_OK) fail();
+        if (sfgpu_variational_mt(ctx, wx, wy, im, &m, channel_w_, &occ_, avg) != SFGPU_OK) fail();
         sf_point2f r = {avg[0], avg[1]};
         return r;
     }
@@ -116,21 +136,19 @@ private:
         fprintf(stderr, "error in Variational_MT::variational(): %s\n", sfgpu_last_error());
         exit(1);
     }
-    sfgpu_ctx *ctx_;
     color_image_t *channel_w_;
     image_t occ_;
 };
 
 // normalize() of variational_mt.cpp:17-85 with the reference's signature shape
 template <class Params> inline void normalize(color_image_t **seq, unsigned F, Params &params) {
-    sfgpu_ctx *ctx = NULL;
+    sfgpu_ctx *ctx = sf_shim_thread_context();
     sf_mt_params_t m;
     sf_mt_params_from_list(params, &m);
-    if (sfgpu_create(-1, NULL, &ctx) != SFGPU_OK || sfgpu_normalize(ctx, seq, (int)F, &m) != SFGPU_OK) {
+    if (!ctx || sfgpu_normalize(ctx, seq, (int)F, &m) != SFGPU_OK) {
         fprintf(stderr, "error in normalize(): %s\n", sfgpu_last_error());
         exit(1);
     }
-    sfgpu_destroy(ctx);
     const char *avg[3] = {"slow_flow_img_norm_avg_1", "slow_flow_img_norm_avg_2", "slow_flow_img_norm_avg_3"};
     const char *sd[3] = {"slow_flow_img_norm_std_1", "slow_flow_img_norm_std_2", "slow_flow_img_norm_std_3"};
     for (int k = 0; k < 3; k++) {

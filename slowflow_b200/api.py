@@ -27,6 +27,12 @@ class Profile(C.Structure):
                 ("data_pixels", C.c_longlong), ("kernel_launches", C.c_longlong)]
 
 
+class FrameInt(C.Structure):
+    """sf_frame_int_t: the cv::Mat fields of an 8-/16-bit frame (include/slowflow_gpu.h)."""
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("step", C.c_size_t),
+                ("data", C.c_void_p)]
+
+
 class MTStats(C.Structure):
     _fields_ = [("levels", C.c_int), ("outer_iterations", C.c_int), ("sor_calls", C.c_int),
                 ("graphcut_calls", C.c_int), ("setup_ms", C.c_double), ("graphcut_ms", C.c_double),
@@ -37,10 +43,11 @@ class MTStats(C.Structure):
 ABI_SYMBOLS = [
     "variational_params_default", "variational", "sf_mt_params_default", "sfgpu_create", "sfgpu_destroy",
     "sfgpu_last_error", "sfgpu_device_count", "sfgpu_synchronize", "sfgpu_set_sor_variant", "sfgpu_set_sor_fuse",
-    "sfgpu_variational", "sfgpu_variational_dev", "sfgpu_variational_sequence", "sfgpu_host_register",
+    "sfgpu_variational", "sfgpu_variational_dev", "sfgpu_variational_sequence", "sfgpu_variational_sequence_u8",
+    "sfgpu_variational_sequence_u16", "sfgpu_host_register",
     "sfgpu_host_unregister", "sfgpu_variational_mt", "sfgpu_normalize", "sfgpu_get_mt_stats", "sfgpu_profile_enable",
     "sfgpu_profile_reset", "sfgpu_profile_get", "sfgpu_image_warp", "sfgpu_compute_dpsis_weight",
-    "sfgpu_compute_smoothness", "sfgpu_compute_data_and_match", "sfgpu_sub_laplacian", "sfgpu_sor_coupled",
+    "sfgpu_compute_smoothness", "sfgpu_compute_data_and_match", "sfgpu_prep_two_frame", "sfgpu_sub_laplacian", "sfgpu_sor_coupled",
     "sfgpu_version", "sfgpu_grid_mincut", "sfgpu_prescale_size", "sfgpu_prescale", "sfgpu_raw_weighting",
     "sfgpu_write_flo", "sfgpu_read_flo_size", "sfgpu_read_flo", "sfgpu_write_occlusion_pbm", "sfgpu_set_device", "sfgpu_get_device",
     "sfgpu_convolve_horiz", "sfgpu_convolve_vert", "sfgpu_color_image_convolve_hv", "sfgpu_get_derivatives",
@@ -78,6 +85,8 @@ def load_library(path=None):
     lib.sfgpu_variational_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_int, C.c_int, VP]
     lib.sfgpu_variational_sequence.argtypes = [C.c_void_p, C.c_int, C.POINTER(CP), C.POINTER(IP), C.POINTER(IP), VP]
+    for name in ("sfgpu_variational_sequence_u8", "sfgpu_variational_sequence_u16"):
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_int, C.POINTER(FrameInt), C.POINTER(IP), C.POINTER(IP), VP, C.c_int]
     lib.sfgpu_host_register.argtypes = [C.c_void_p, C.c_ulonglong]
     lib.sfgpu_host_unregister.argtypes = [C.c_void_p]
     lib.sfgpu_variational_mt.argtypes = [C.c_void_p, IP, IP, C.POINTER(CP), C.POINTER(MTParams), CP, IP, FP]
@@ -92,6 +101,7 @@ def load_library(path=None):
                                              C.c_float, C.c_int]
     lib.sfgpu_compute_data_and_match.argtypes = [C.c_void_p, IP, IP, IP, IP, IP, IP, IP, IP, CP, CP, C.c_float,
                                                  C.c_float]
+    lib.sfgpu_prep_two_frame.argtypes = [C.c_void_p, IP, IP, IP, IP, IP, CP, CP, IP, IP, IP, IP, IP, IP, C.c_float, C.c_float]
     lib.sfgpu_sub_laplacian.argtypes = [C.c_void_p, IP, IP, IP, IP]
     lib.sfgpu_sor_coupled.argtypes = [C.c_void_p, IP, IP, IP, IP, IP, IP, IP, IP, IP, C.c_int, C.c_float]
     lib.sfgpu_prescale_size.argtypes = [C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -193,6 +203,26 @@ class Context:
                                                              C.byref(params) if params is not None else None),
                "sfgpu_variational_sequence")
 
+    def variational_sequence_int(self, frames, wxs, wys, params=None, continue_from_previous=False):
+        """frames: numpy uint8 / uint16 arrays of shape (H, W) or (H, W, 3) (a cv::Mat as the reference's loaders hold
+        it before the float conversion, adaptiveFR.cpp:450-464 / slow_flow.cpp:470-477); rows may be strided."""
+        import numpy as np
+        n = len(wxs)
+        assert len(frames) == n + 1 and len(wys) == n
+        depth = frames[0].dtype.itemsize * 8
+        assert depth in (8, 16) and all(f.dtype == frames[0].dtype for f in frames)
+        fa = (FrameInt * (n + 1))()
+        for k, f in enumerate(frames):
+            ch = 1 if f.ndim == 2 else f.shape[2]
+            assert f.strides[1] == ch * f.dtype.itemsize and (f.ndim == 2 or f.strides[2] == f.dtype.itemsize)
+            fa[k] = FrameInt(f.shape[1], f.shape[0], ch, f.strides[0], f.ctypes.data)
+        IP = C.POINTER(image_t)
+        xa = (IP * n)(*[C.pointer(w.c) for w in wxs])
+        ya = (IP * n)(*[C.pointer(w.c) for w in wys])
+        fn = self.lib.sfgpu_variational_sequence_u8 if depth == 8 else self.lib.sfgpu_variational_sequence_u16
+        _check(self.lib, fn(self.h, n, fa, xa, ya, C.byref(params) if params is not None else None,
+                            1 if continue_from_previous else 0), "sfgpu_variational_sequence_u%d" % depth)
+
     # --- multi-frame
     def normalize(self, seq, params):
         CP = C.POINTER(color_image_t)
@@ -247,6 +277,11 @@ class Context:
         _check(self.lib, self.lib.sfgpu_compute_data_and_match(self.h, a11.ptr(), a12.ptr(), a22.ptr(), b1.ptr(),
                                                                b2.ptr(), mask.ptr(), du.ptr(), dv.ptr(), im1.ptr(),
                                                                im2w.ptr(), hd, hg), "sfgpu_compute_data_and_match")
+
+    def prep_two_frame(self, a11, a12, a22, b1, b2, im1, im2, wx, wy, du, dv, ph, pv, hd, hg):
+        _check(self.lib, self.lib.sfgpu_prep_two_frame(self.h, a11.ptr(), a12.ptr(), a22.ptr(), b1.ptr(), b2.ptr(), im1.ptr(),
+                                                       im2.ptr(), wx.ptr(), wy.ptr(), _ip(du), _ip(dv), ph.ptr(), pv.ptr(), hd, hg),
+               "sfgpu_prep_two_frame")
 
     def convolve(self, dst, src, coeffs, vertical=False):
         """convolve_horiz / convolve_vert (image.c:400-645) with 3 or 5 taps."""

@@ -67,6 +67,7 @@ int sfgpu_ctx::ensure_workspace(Geom geom) {
 }
 
 int sfgpu_ctx::ensure_io(size_t floats) {
+    seq_last_slot = -1; // every user of the io area overwrites the frame ring a sequence call may have left there
     if (floats <= io_floats) return SFGPU_OK;
     if (io) cudaFree(io);
     io = nullptr;
@@ -245,6 +246,29 @@ int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d
 
 } // namespace sf
 
+bool sf::check_pair(const image_t *wx, const image_t *wy, const color_image_t *im1, const color_image_t *im2) {
+    if (!wx || !wy || !im1 || !im2 || !wx->data || !wy->data || !im1->c1 || !im2->c1) {
+        set_error("null image argument");
+        return false;
+    }
+    const int w = wx->width, h = wx->height, s = wx->stride;
+    if (s != ((w + 3) / 4) * 4) {
+        set_error("stride must be ceil4(width) (image.c:25)");
+        return false;
+    }
+    if (wy->width != w || wy->height != h || wy->stride != s || im1->width != w || im1->height != h ||
+        im1->stride != s || im2->width != w || im2->height != h || im2->stride != s) {
+        set_error("flow planes and images must share width/height/stride");
+        return false;
+    }
+    const size_t P = (size_t)s * h;
+    if (im1->c2 != im1->c1 + P || im1->c3 != im1->c2 + P || im2->c2 != im2->c1 + P || im2->c3 != im2->c2 + P) {
+        set_error("colour images must be planar and contiguous (image.c:80-87)");
+        return false;
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------ ABI: basics
 extern "C" {
 
@@ -317,6 +341,10 @@ void sfgpu_destroy(sfgpu_ctx *c) {
     if (c->stager) sf::host_stager_free(c->stager);
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
+    for (auto &ring : c->seq_ev)
+        for (auto e : ring)
+            if (e) cudaEventDestroy(e);
+    if (c->seq_raw) cudaFree(c->seq_raw);
     if (c->h2d) cudaStreamDestroy(c->h2d);
     if (c->d2h) cudaStreamDestroy(c->d2h);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -383,29 +411,6 @@ void variational_params_default(variational_params_t *params) {
     params->sor_omega = 1.9f;
 }
 
-static bool check_pair(const image_t *wx, const image_t *wy, const color_image_t *im1, const color_image_t *im2) {
-    if (!wx || !wy || !im1 || !im2 || !wx->data || !wy->data || !im1->c1 || !im2->c1) {
-        set_error("null image argument");
-        return false;
-    }
-    const int w = wx->width, h = wx->height, s = wx->stride;
-    if (s != ((w + 3) / 4) * 4) {
-        set_error("stride must be ceil4(width) (image.c:25)");
-        return false;
-    }
-    if (wy->width != w || wy->height != h || wy->stride != s || im1->width != w || im1->height != h ||
-        im1->stride != s || im2->width != w || im2->height != h || im2->stride != s) {
-        set_error("flow planes and images must share width/height/stride");
-        return false;
-    }
-    const size_t P = (size_t)s * h;
-    if (im1->c2 != im1->c1 + P || im1->c3 != im1->c2 + P || im2->c2 != im2->c1 + P || im2->c3 != im2->c2 + P) {
-        set_error("colour images must be planar and contiguous (image.c:80-87)");
-        return false;
-    }
-    return true;
-}
-
 int sfgpu_variational_dev(sfgpu_ctx *c, float *d_wx, float *d_wy, const float *d_im1, const float *d_im2, int width,
                           int height, int stride, const variational_params_t *params) {
     if (!c || !d_wx || !d_wy || !d_im1 || !d_im2) {
@@ -465,81 +470,6 @@ void variational(image_t *wx, image_t *wy, const color_image_t *im1, const color
         fprintf(stderr, "error in variational(): %s\n", sfgpu_last_error());
         exit(1);
     }
-}
-
-// ------------------------------------------------------------------------------------------ ABI: sequence
-int sfgpu_variational_sequence(sfgpu_ctx *c, int n_pairs, const color_image_t *const *frames, image_t *const *wx,
-                               image_t *const *wy, const variational_params_t *params) {
-    if (!c || n_pairs < 0 || !frames || !wx || !wy) {
-        set_error("sfgpu_variational_sequence: bad argument");
-        return SFGPU_ERR_ARG;
-    }
-    if (n_pairs == 0) return SFGPU_OK;
-    for (int j = 0; j < n_pairs; j++)
-        if (!check_pair(wx[j], wy[j], frames[j], frames[j + 1])) return SFGPU_ERR_ARG;
-    SF_CUDA(cudaSetDevice(c->device));
-    const Geom g{wx[0]->width, wx[0]->height, wx[0]->stride};
-    for (int j = 1; j < n_pairs; j++)
-        if (wx[j]->width != g.W || wx[j]->height != g.H) {
-            set_error("sfgpu_variational_sequence: all pairs must share one geometry");
-            return SFGPU_ERR_ARG;
-        }
-    const size_t P = g.plane();
-    // device ring: 3 frame slots (frame f -> slot f%3), 3 flow slots (pair j -> slot j%3)
-    int rc = c->ensure_io((3 * 3 + 3 * 2) * P);
-    if (rc != SFGPU_OK) return rc;
-    rc = c->ensure_workspace(g);
-    if (rc != SFGPU_OK) return rc;
-    if (!c->h2d) SF_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
-    if (!c->d2h) SF_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
-    auto frame_slot = [&](int f) { return c->io + (size_t)(f % 3) * 3 * P; };
-    auto flow_slot = [&](int j) { return c->io + 9 * P + (size_t)(j % 3) * 2 * P; };
-
-    std::vector<cudaEvent_t> up(n_pairs + 1), done(n_pairs), down(n_pairs);
-    for (auto &e : up) SF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto &e : done) SF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto &e : down) SF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    int status = SFGPU_OK;
-    auto upload = [&](int j) -> bool { // inputs of pair j: frame j+1 (and frame 0 for j == 0) + initial flow j
-        if (j >= 2 && !cuda_ok(cudaStreamWaitEvent(c->h2d, done[j - 2], 0), "wait done")) return false;   // frame slot (j+1)%3 last read by pair j-2
-        if (j >= 3 && !cuda_ok(cudaStreamWaitEvent(c->h2d, down[j - 3], 0), "wait down")) return false;   // flow slot j%3 last drained for pair j-3
-        if (j == 0 && !cuda_ok(cudaMemcpyAsync(frame_slot(0), frames[0]->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, c->h2d), "h2d frame")) return false;
-        if (!cuda_ok(cudaMemcpyAsync(frame_slot(j + 1), frames[j + 1]->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, c->h2d), "h2d frame")) return false;
-        if (!cuda_ok(cudaMemcpyAsync(flow_slot(j), wx[j]->data, P * sizeof(float), cudaMemcpyHostToDevice, c->h2d), "h2d wx")) return false;
-        if (!cuda_ok(cudaMemcpyAsync(flow_slot(j) + P, wy[j]->data, P * sizeof(float), cudaMemcpyHostToDevice, c->h2d), "h2d wy")) return false;
-        return cuda_ok(cudaEventRecord(up[j], c->h2d), "record up");
-    };
-    auto download = [&](int j) -> bool {
-        if (!cuda_ok(cudaStreamWaitEvent(c->d2h, done[j], 0), "wait done")) return false;
-        if (!cuda_ok(cudaMemcpyAsync(wx[j]->data, flow_slot(j), P * sizeof(float), cudaMemcpyDeviceToHost, c->d2h), "d2h wx")) return false;
-        if (!cuda_ok(cudaMemcpyAsync(wy[j]->data, flow_slot(j) + P, P * sizeof(float), cudaMemcpyDeviceToHost, c->d2h), "d2h wy")) return false;
-        return cuda_ok(cudaEventRecord(down[j], c->d2h), "record down");
-    };
-    // the previous work on the compute stream may still use the io ring
-    {
-        cudaEvent_t e0;
-        if (cuda_ok(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming), "event")) {
-            cudaEventRecord(e0, c->stream);
-            cudaStreamWaitEvent(c->h2d, e0, 0);
-            cudaEventDestroy(e0);
-        }
-    }
-    if (!upload(0)) status = SFGPU_ERR_CUDA;
-    for (int j = 0; j < n_pairs && status == SFGPU_OK; j++) {
-        if (!cuda_ok(cudaStreamWaitEvent(c->stream, up[j], 0), "wait up")) { status = SFGPU_ERR_CUDA; break; }
-        status = run_two_frame(c, g, flow_slot(j), flow_slot(j) + P, frame_slot(j), frame_slot(j + 1), params);
-        if (status != SFGPU_OK) break;
-        if (!cuda_ok(cudaEventRecord(done[j], c->stream), "record done")) { status = SFGPU_ERR_CUDA; break; }
-        if (j + 1 < n_pairs && !upload(j + 1)) { status = SFGPU_ERR_CUDA; break; }
-        if (!download(j)) { status = SFGPU_ERR_CUDA; break; }
-    }
-    cudaStreamSynchronize(c->h2d);
-    cudaStreamSynchronize(c->stream);
-    if (!cuda_ok(cudaStreamSynchronize(c->d2h), "sync d2h") && status == SFGPU_OK) status = SFGPU_ERR_CUDA;
-    for (auto e : up) cudaEventDestroy(e);
-    for (auto e : done) cudaEventDestroy(e);
-    for (auto e : down) cudaEventDestroy(e);
-    return status;
 }
 
 // ------------------------------------------------------------------------------------------ ABI: operator twins
@@ -714,6 +644,42 @@ int sfgpu_compute_data_and_match(sfgpu_ctx *c, image_t *a11, image_t *a12, image
     cm.accumulate = false; cm.fuse_system = false;
     cm.a11 = o; cm.a12 = o + P; cm.a22 = o + 2 * P; cm.b1 = o + 3 * P; cm.b2 = o + 4 * P;
     launch_data_term(st, g, term, cm);
+    D2H(a11->data, o, P); D2H(a12->data, o + P, P); D2H(a22->data, o + 2 * P, P); D2H(b1->data, o + 3 * P, P);
+    D2H(b2->data, o + 4 * P, P);
+    SF_CUDA(cudaStreamSynchronize(st));
+    SF_CUDA(cudaGetLastError());
+    return SFGPU_OK;
+}
+
+int sfgpu_prep_two_frame(sfgpu_ctx *c, image_t *a11, image_t *a12, image_t *a22, image_t *b1, image_t *b2, const color_image_t *im1,
+                         const color_image_t *im2, const image_t *wx, const image_t *wy, const image_t *du, const image_t *dv,
+                         const image_t *ph, const image_t *pv, float half_delta_over3, float half_gamma_over3) {
+    if (!c || !a11 || !a12 || !a22 || !b1 || !b2 || !ph || !pv || (du == nullptr) != (dv == nullptr)) {
+        set_error("sfgpu_prep_two_frame: null argument");
+        return SFGPU_ERR_ARG;
+    }
+    if (!check_pair(wx, wy, im1, im2)) return SFGPU_ERR_ARG;
+    const int w = wx->width, h = wx->height, sd = wx->stride;
+    const image_t *planes[9] = {a11, a12, a22, b1, b2, ph, pv, du, dv};
+    for (int k = 0; k < 9; k++)
+        if (planes[k] && !same_geom(planes[k], w, h, sd)) { set_error("sfgpu_prep_two_frame: geometry"); return SFGPU_ERR_ARG; }
+    if (w < 5 || h < 5) { set_error("image must be at least 5x5 (5-tap derivative filter, image.c:425)"); return SFGPU_ERR_ARG; }
+    SF_CUDA(cudaSetDevice(c->device));
+    const Geom g{w, h, sd};
+    const size_t P = g.plane();
+    cudaStream_t st = c->stream;
+    DevPlanes d;
+    int rc = d.alloc(17 * P);
+    if (rc) return rc;
+    float *i1 = d.p, *i2 = d.p + 3 * P, *fx = d.p + 6 * P, *fy = d.p + 7 * P, *u = d.p + 8 * P, *v = d.p + 9 * P,
+          *dh = d.p + 10 * P, *dvv = d.p + 11 * P, *o = d.p + 12 * P;
+    H2D(i1, im1->c1, 3 * P); H2D(i2, im2->c1, 3 * P); H2D(fx, wx->data, P); H2D(fy, wy->data, P);
+    H2D(dh, ph->data, P); H2D(dvv, pv->data, P);
+    if (du) { H2D(u, du->data, P); H2D(v, dv->data, P); }
+    SF_CUDA(cudaMemsetAsync(o, 0xff, 5 * P * sizeof(float), st)); // NaN pattern: every element must be written by the kernel
+    launch_prep_two_frame(st, g, c->num_sms, i1, i2, fx, fy, du ? u : nullptr, du ? v : nullptr, dh, dvv, half_delta_over3,
+                          half_gamma_over3, o, o + P, o + 2 * P, o + 3 * P, o + 4 * P);
+    c->prof_acc.kernel_launches++;
     D2H(a11->data, o, P); D2H(a12->data, o + P, P); D2H(a22->data, o + 2 * P, P); D2H(b1->data, o + 3 * P, P);
     D2H(b2->data, o + 4 * P, P);
     SF_CUDA(cudaStreamSynchronize(st));

@@ -40,8 +40,13 @@ struct sfgpu_ctx {
     float *io = nullptr; // im1(3) im2(3) wx wy   [+ ring for the sequence API]
     size_t io_floats = 0;
 
-    // ---- sequence pipeline
+    // ---- sequence pipeline (sf_sequence.cu)
     cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t seq_ev[3][4] = {}; // rings of "uploaded" / "solved" / "downloaded" events, created at first use
+    unsigned char *seq_raw = nullptr; // 3 slots of packed 8-/16-bit frames awaiting their on-device conversion
+    size_t seq_raw_bytes = 0;        // bytes per slot
+    sf::Geom seq_geom{0, 0, 0};      // geometry of the frame ring left by the last sequence call
+    int seq_last_slot = -1;          // ring slot that holds the last frame of that call (-1: none)
 
     // ---- profiling
     bool prof = false;
@@ -70,6 +75,9 @@ int host_copies(sfgpu_ctx *c, const std::vector<HostCopy> &list, bool h2d);
 // two-frame refinement on device planes (variational.c:19-82 + :101-143)
 int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d_im1, const float *d_im2,
                   const variational_params_t *params);
+// argument check shared by the host-buffer entries: one geometry, stride = ceil4(width), planar contiguous colour
+bool check_pair(const image_t *wx, const image_t *wy, const color_image_t *im1, const color_image_t *im2);
+bool is_pageable(const void *p);
 // one sor_coupled call on the context's SOR arena (profiled)
 int run_sor(sfgpu_ctx *c, int iterations, float omega, int *cur, bool zero_init);
 } // namespace sf

@@ -50,7 +50,7 @@ struct HostStager {
 
 void host_stager_free(HostStager *h) { delete h; }
 
-static bool is_pageable(const void *p) {
+bool is_pageable(const void *p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         cudaGetLastError();

@@ -380,8 +380,8 @@ void launch_invert_blocks(cudaStream_t st, Geom g, float *a11, float *a12, float
     k_invert_blocks<<<grid, b, 0, st>>>(g, a11, a12, a22, ph, pv);
 }
 
-__global__ void __launch_bounds__(256) k_add4(size_t n4, float4 *__restrict__ dst, const float4 *__restrict__ a,
-                                              const float4 *__restrict__ b) {
+// dst may alias a (the callers update a flow plane in place), so neither carries __restrict__
+__global__ void __launch_bounds__(256) k_add4(size_t n4, float4 *dst, const float4 *a, const float4 *__restrict__ b) {
     pdl_enter();
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (size_t)gridDim.x * blockDim.x) {
         const float4 x = a[k], y = b[k];

@@ -214,8 +214,9 @@ __global__ void __launch_bounds__(256) k_raw_weights(Geom g, float *__restrict__
     w3[o + 2 * P] = measured == 2 ? weight : other;
 }
 
-// normalize(): per-channel sums in double (variational_mt.cpp:27-46), then (I - avg) / std (:61-69)
-__global__ void __launch_bounds__(256) k_norm_sums(Geom g, const float *__restrict__ im, double *__restrict__ sums /*6*/) {
+// normalize(): per-channel sums in double (variational_mt.cpp:27-46), then (I - avg) / std (:61-69).  Every block writes
+// its six partial sums to sums[block*6 + k]; the host adds them in block order (deterministic: no atomics on the path).
+__global__ void __launch_bounds__(256) k_norm_sums(Geom g, const float *__restrict__ im, double *__restrict__ sums /*gridDim.x * 6*/) {
     double s[6] = {0, 0, 0, 0, 0, 0};
     const size_t P = g.plane();
     for (int j = blockIdx.x; j < g.H; j += gridDim.x)
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(256) k_norm_sums(Geom g, const float *__restri
             for (int q = 0; q < 6; q++) red[q][threadIdx.x] += red[q][threadIdx.x + k];
         __syncthreads();
     }
-    if (threadIdx.x < 6) atomicAdd(&sums[threadIdx.x], red[threadIdx.x][0]);
+    if (threadIdx.x < 6) sums[(size_t)blockIdx.x * 6 + threadIdx.x] = red[threadIdx.x][0];
 }
 __global__ void __launch_bounds__(256) k_norm_apply(Geom g, float *__restrict__ im, double a0, double a1, double a2, double s0,
                                                     double s1, double s2) {
@@ -598,6 +599,19 @@ int sfgpu_normalize(sfgpu_ctx *c, color_image_t *const *seq, int F, sf_mt_params
         set_error("sfgpu_normalize: bad argument");
         return SFGPU_ERR_ARG;
     }
+    for (int f = 0; f < F; f++) { // every frame like check_pair: same geometry, planar, contiguous
+        const color_image_t *q = seq[f];
+        if (!q || !q->c1 || q->width != seq[0]->width || q->height != seq[0]->height || q->stride != seq[0]->stride ||
+            q->stride != ((q->width + 3) / 4) * 4 || q->width < 1 || q->height < 1) {
+            set_error("sfgpu_normalize: frames must be non-null and share one geometry with stride = ceil4(width)");
+            return SFGPU_ERR_ARG;
+        }
+        const size_t Pq = (size_t)q->stride * q->height;
+        if (q->c2 != q->c1 + Pq || q->c3 != q->c2 + Pq) {
+            set_error("sfgpu_normalize: colour images must be planar and contiguous (image.c:80-87)");
+            return SFGPU_ERR_ARG;
+        }
+    }
     SF_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const Geom g{seq[0]->width, seq[0]->height, seq[0]->stride};
@@ -608,35 +622,43 @@ int sfgpu_normalize(sfgpu_ctx *c, color_image_t *const *seq, int F, sf_mt_params
     if (const char *e = getenv("SLOWFLOW_GPU_NORMALIZE_RESIDENT_BYTES")) resident_limit = (size_t)strtoull(e, nullptr, 10); // tests
     const bool resident = (size_t)F * 3 * P * sizeof(float) <= resident_limit;
     const size_t fstride = resident ? 3 * P : 0;
-    float *dev = nullptr;
-    double *dsum = nullptr;
-    SF_CUDA(cudaMalloc(&dev, (resident ? (size_t)F : 1) * 3 * P * sizeof(float)));
-    if (!cuda_ok(cudaMalloc(&dsum, (size_t)F * 6 * sizeof(double)), "cudaMalloc")) { cudaFree(dev); return SFGPU_ERR_CUDA; }
-    cudaMemsetAsync(dsum, 0, (size_t)F * 6 * sizeof(double), st);
+    const int nblk = std::min(g.H, 592);
+    struct Bufs { // freed on every path
+        float *dev = nullptr;
+        double *dsum = nullptr;
+        ~Bufs() { if (dev) cudaFree(dev); if (dsum) cudaFree(dsum); }
+    } b;
+    SF_CUDA(cudaMalloc(&b.dev, (resident ? (size_t)F : 1) * 3 * P * sizeof(float)));
+    SF_CUDA(cudaMalloc(&b.dsum, (size_t)F * nblk * 6 * sizeof(double)));
+    float *dev = b.dev;
+    double *dsum = b.dsum;
     for (int f = 0; f < F; f++) {
-        cudaMemcpyAsync(dev + (size_t)f * fstride, seq[f]->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st);
-        k_norm_sums<<<std::min(g.H, 592), 256, 0, st>>>(g, dev + (size_t)f * fstride, dsum + f * 6);
+        SF_CUDA(cudaMemcpyAsync(dev + (size_t)f * fstride, seq[f]->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st));
+        k_norm_sums<<<nblk, 256, 0, st>>>(g, dev + (size_t)f * fstride, dsum + (size_t)f * nblk * 6);
     }
-    std::vector<double> hs((size_t)F * 6);
-    cudaMemcpyAsync(hs.data(), dsum, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
-    if (!cuda_ok(cudaStreamSynchronize(st), "normalize sums")) { cudaFree(dev); cudaFree(dsum); return SFGPU_ERR_CUDA; }
+    SF_CUDA(cudaGetLastError());
+    std::vector<double> hs((size_t)F * nblk * 6);
+    SF_CUDA(cudaMemcpyAsync(hs.data(), dsum, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaStreamSynchronize(st));
     double avg[3] = {0, 0, 0}, sd[3] = {0, 0, 0};
     const double n = (double)g.H * g.W;
-    for (int f = 0; f < F; f++)
-        for (int k = 0; k < 3; k++) { avg[k] += hs[f * 6 + k] / n; sd[k] += hs[f * 6 + 3 + k] / n; }
+    for (int f = 0; f < F; f++) {
+        double fs[6] = {0, 0, 0, 0, 0, 0};
+        for (int blk = 0; blk < nblk; blk++)
+            for (int k = 0; k < 6; k++) fs[k] += hs[((size_t)f * nblk + blk) * 6 + k];
+        for (int k = 0; k < 3; k++) { avg[k] += fs[k] / n; sd[k] += fs[3 + k] / n; }
+    }
     for (int k = 0; k < 3; k++) {
         avg[k] /= F;
         sd[k] = sqrt((sd[k] / F) - avg[k] * avg[k]) / 255.0f; // :48-51
     }
     for (int f = 0; f < F; f++) {
-        if (!resident) cudaMemcpyAsync(dev, seq[f]->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (!resident) SF_CUDA(cudaMemcpyAsync(dev, seq[f]->c1, 3 * P * sizeof(float), cudaMemcpyHostToDevice, st));
         k_norm_apply<<<grid2d(g.W, g.H), dim3(32, 8), 0, st>>>(g, dev + (size_t)f * fstride, avg[0], avg[1], avg[2], sd[0], sd[1], sd[2]);
-        cudaMemcpyAsync(seq[f]->c1, dev + (size_t)f * fstride, 3 * P * sizeof(float), cudaMemcpyDeviceToHost, st);
+        SF_CUDA(cudaMemcpyAsync(seq[f]->c1, dev + (size_t)f * fstride, 3 * P * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
-    const bool ok = cuda_ok(cudaStreamSynchronize(st), "normalize apply");
-    cudaFree(dev);
-    cudaFree(dsum);
-    if (!ok) return SFGPU_ERR_CUDA;
+    SF_CUDA(cudaGetLastError());
+    SF_CUDA(cudaStreamSynchronize(st));
     for (int k = 0; k < 3; k++) {
         // the reference publishes the values through a stringstream with 6 significant digits (:72-84)
         char buf[64];

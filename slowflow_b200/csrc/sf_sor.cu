@@ -500,7 +500,15 @@ int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int 
     float *A = plan.arena;
     const size_t P = g.plane();
     int launches = 0;
-    if (iterations <= 0) return 0;
+    if (iterations <= 0) {
+        // the reference erases du,dv and then runs a 0-iteration sor_coupled (variational.c:44-45, solver.c:20): the
+        // increment the callers add to the flow must be a defined 0, not whatever the arena held
+        if (zero_init) {
+            cudaMemsetAsync(A + (size_t)(*cur ? SP_DUB : SP_DUA) * P, 0, P * sizeof(float), st);
+            cudaMemsetAsync(A + (size_t)(*cur ? SP_DVB : SP_DVA) * P, 0, P * sizeof(float), st);
+        }
+        return 0;
+    }
     if (variant == 1 || !plan.tmap_valid) {
         float *du = A + (size_t)(*cur ? SP_DUB : SP_DUA) * P, *dv = A + (size_t)(*cur ? SP_DVB : SP_DVA) * P;
         if (zero_init) {

@@ -37,8 +37,8 @@ def write_ppm(path, rgb_u8):
         f.write(rgb_u8.tobytes())
 
 
-@pytest.mark.parametrize("S,jets,gpus", [(2, 3, 1), (3, 2, 1), (2, 4, 2)])
-def test_driver_outputs_equal_api_results(ctx, tmp_path, S, jets, gpus):
+@pytest.mark.parametrize("S,jets,gpus,hbit", [(2, 3, 1, 0), (3, 2, 1, 0), (2, 4, 2, 0), (2, 2, 1, 1)])
+def test_driver_outputs_equal_api_results(ctx, tmp_path, S, jets, gpus, hbit):
     lib = load_library()
     if gpus > lib.sfgpu_device_count():
         pytest.skip("needs %d GPUs" % gpus)
@@ -52,7 +52,7 @@ def test_driver_outputs_equal_api_results(ctx, tmp_path, S, jets, gpus):
         frames_u8.append(f)
         write_ppm(seqdir / ("frame_%d.ppm" % (start - steps + k)), np.ascontiguousarray(f.transpose(1, 2, 0)))
     p = mt_params_default()
-    p.S, p.hbit, p.niter_alter, p.niter_outer = S, 0, 2, 3
+    p.S, p.hbit, p.niter_alter, p.niter_outer = S, hbit, 2, 3  # hbit = 1: the shipped cfg default (16bit)
     for a in range(S - 1):
         p.rho[a], p.omega[a] = 1.0, 1.0 + a
     args = [DRIVER, "--frames", str(seqdir / "frame_%d.ppm"), "--out", str(out), "--start", str(start), "--jets", str(jets),
@@ -90,3 +90,29 @@ def test_driver_outputs_equal_api_results(ctx, tmp_path, S, jets, gpus):
                 assert pbm == b"P4\n%d %d\n" % (w, h) + bits.tobytes()
     cfg = (out / "config.cfg").read_text()
     assert "slow_flow_S\t%d" % S in cfg and "Jets\t\t%d" % jets in cfg
+
+
+def test_driver_resume_skips_finished_windows(tmp_path):
+    """-resume (slow_flow.cpp:178, 794, 958): a window whose .flo exists is not recomputed; a missing one is."""
+    w, h, start, S, jets = 96, 64, 3, 2, 2
+    steps = S - 1
+    seqdir, out = tmp_path / "seq", tmp_path / "out"
+    seqdir.mkdir()
+    for k in range(1 + (jets + 2) * steps):
+        f = np.clip(np.rint(synth.frame(w, h, k - steps)), 0, 255).astype(np.uint8)
+        write_ppm(seqdir / ("frame_%d.ppm" % (start - steps + k)), np.ascontiguousarray(f.transpose(1, 2, 0)))
+    args = [DRIVER, "--frames", str(seqdir / "frame_%d.ppm"), "--out", str(out), "--start", str(start), "--jets", str(jets),
+            "--S", str(S), "--gpus", "1", "--set", "slow_flow_niter_alter=1", "--set", "slow_flow_niter_outer=2"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    first = {p.name: p.read_bytes() for p in out.glob("*.flo")}
+    assert len(first) == 2 * jets
+    victim = out / ("frame_%d_back.flo" % (start + steps))
+    victim.unlink()
+    marker = out / ("frame_%d.flo" % start)
+    marker.write_bytes(b"kept")  # a finished file is never touched, whatever it holds
+    r = subprocess.run(args + ["--resume"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "3 finished flow files skipped" in r.stdout
+    assert marker.read_bytes() == b"kept"
+    assert victim.read_bytes() == first[victim.name]

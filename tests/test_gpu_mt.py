@@ -56,9 +56,18 @@ def test_normalize_matches_reference(ctx, mt_checker):
     ("unnormalised_dataterm_succ_only", dict(niter_alter=1, niter_outer=2, dataterm=0, omega=[0, 0])),
     ("smoothing0_inner2", dict(niter_alter=1, niter_outer=2, niter_inner=2, smoothing=0)),
     ("separate_grad_penalty", dict(niter_alter=1, niter_outer=2, robust_grad=2, robust_grad_eps=0.5)),
+    # 16bit = 1 is what the shipped cfgs/slow_flow.cfg and sf_mt_params_default select: the smoothness weight divides the
+    # de-normalised luminance by 65535 (variational_aux_mt.cpp:673-719).  Once on 16-bit intensities (0..65535), once on
+    # 8-bit intensities (the flat-weight case a user gets who leaves the flag at its default)
+    ("hbit16_modl1_occ", dict(niter_alter=2, niter_outer=4, hbit=1)),
+    ("hbit16_geman_mcclure_eps0.5", dict(niter_alter=2, niter_outer=3, hbit=1, robust_color=4, robust_color_eps=0.5)),
+    ("hbit_flag_on_8bit_data", dict(niter_alter=2, niter_outer=3, hbit=1)),
 ])
 def test_mt_parity_small(ctx, mt_checker, name, kw):
     ims, wx, wy = mh.window(256, 160, 3)
+    if name.startswith("hbit16"):
+        for f in ims:
+            f.buf[:] = np.rint(f.buf * 257.0)  # 0..255 -> 0..65535, integer valued like a 16-bit image
     p = mh.params(3, **kw)
     r = mh.run_cpu(*mt_checker, ims, wx, wy, p, SOR_REDBLACK)
     g = mh.run_gpu(ctx, ims, wx, wy, p)
@@ -94,6 +103,22 @@ def test_mt_config3_1280x1024(ctx, mt_checker):
     check(g, r, "config 3 (bounded)")
     lex = mh.run_cpu(*mt_checker, ims, wx, wy, p, SOR_LEX)
     print("reported: GPU vs CPU-lex mean %.3e max %.3e" % epe(g["wx"].array, g["wy"].array, lex["wx"].array, lex["wy"].array))
+
+
+def test_mt_config3_full_iteration_count(ctx, mt_checker, oracle):
+    """BASELINE config 3 with its FULL iteration count: 1280x1024, S=3, Geman-McClure eps 0.5, occlusion reasoning,
+    2 alternations x 10 outer iterations x 30 SOR sweeps against the reference's own unmodified driver (CPU red-black).
+    The executed outer-iteration counts must agree too (the early exits of variational_mt.cpp:407,436)."""
+    ims, wx, wy = mh.window(1280, 1024, 3)
+    p = mh.params(3, niter_alter=2, niter_outer=10, robust_color=4, robust_color_eps=0.5)
+    r = mh.run_cpu(*mt_checker, ims, wx, wy, p, SOR_REDBLACK)
+    g = mh.run_gpu(ctx, ims, wx, wy, p)
+    check(g, r, "config 3 (2 x 10 outer iterations)")
+    assert abs(g["avg"][0] - r["avg"][0]) < 1e-4 and abs(g["avg"][1] - r["avg"][1]) < 1e-4
+    # the reference driver does not count its iterations; the restatement (bit-identical to it, test_oracle_pin_mt.py) does
+    o = mh.run_cpu(oracle.lib, "sfo_", ims, wx, wy, p, SOR_REDBLACK)
+    print("outer iterations executed: gpu %d, cpu %d" % (g["stats"].outer_iterations, o["stats"][0]))
+    assert g["stats"].outer_iterations == o["stats"][0]
 
 
 def test_mt_early_exit_iteration_counts(ctx, mt_checker):

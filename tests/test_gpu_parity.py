@@ -78,6 +78,62 @@ def test_data_term_fused_derivatives(ctx, oracle, w, h, hd):
         assert err.max() <= 2e-2 * np.abs(ref).max(), name
 
 
+@pytest.mark.parametrize("w,h,hd,with_increment", [
+    (61, 45, 0.0, False), (61, 45, 0.05, True), (333, 211, 0.0, True), (333, 211, 0.05, False),
+    (2073, 1166, 0.0, False),  # level 2 of config 4: stride 2076 != width
+    (2560, 1440, 0.0, False), (2560, 1440, 0.05, True),
+])
+def test_prep_two_frame_production_kernel(ctx, oracle, w, h, hd, with_increment):
+    """k_prep_two_frame -- the kernel the default two-frame path launches (22 % of a field) -- at operator level: its
+    five output planes against the oracle chain image_warp -> get_derivatives -> compute_data_and_match ->
+    sub_laplacian x2 -> block inverse (variational_aux.c:18-302, solver.c:101-106), separately over the interior and over
+    the first/last 8 rows and columns (hand-patched replicate borders, strip / segment seams), plus the stride padding."""
+    im1, im2, wx, wy = helpers.pair(w, h)
+    wx.array[3, 5] = -40.0   # a flow that leaves the image on the left: clamped gather, mask 0
+    wy.array[h - 2, w - 3] = 500.0
+    du = helpers.rng_plane(w, h, 1, -0.3, 0.3) if with_increment else None
+    dv = helpers.rng_plane(w, h, 2, -0.3, 0.3) if with_increment else None
+    s = helpers.oracle_system(oracle, im1, im2, wx, wy, du, dv, hd=hd)
+    # inverted blocks exactly as the first sweep of sor_coupled leaves them (solver.c:101-106)
+    Ar = [a.copy() for a in s["A"]]
+    z0, z1 = Image(w, h), Image(w, h)
+    oracle.lib.sfo_sor_coupled(z0.ptr(), z1.ptr(), *[a.ptr() for a in Ar], s["sh"].ptr(), s["sv"].ptr(), 1, 1.9, SOR_REDBLACK)
+    ref = [Ar[0], Ar[1], Ar[2], s["A"][3], s["A"][4]]
+    G = [Image(w, h) for _ in range(5)]
+    ctx.prep_two_frame(*G, im1, im2, wx, wy, du, dv, s["sh"], s["sv"], hd, 0.71 * 0.5 / 3.0)
+    border = np.ones((h, w), bool)
+    border[8:-8, 8:-8] = False
+    for k, name in enumerate(["a11'", "a12'", "a22'", "b1", "b2"]):
+        g, r = G[k], ref[k]
+        assert np.isfinite(g.full).all(), name                       # every element was written (the twin pre-fills NaN)
+        assert not g.full[:, w:].any(), name + " stride padding"      # defined zeros in the padding columns
+        err = np.abs(g.array.astype(np.float64) - r.array)
+        scale = np.abs(r.array).max()
+        for region, sel in (("interior", ~border), ("border", border)):
+            e = err[sel]
+            # robust weights are 1/sqrt(residual^2 + 1e-6): a 1e-6 relative change of a derivative is amplified where
+            # the residual vanishes, so the bulk is gated tightly and the worst pixel loosely
+            assert np.percentile(e, 99) <= 2e-4 * scale, (name, region, float(np.percentile(e, 99)), scale)
+            assert e.max() <= 2e-2 * scale, (name, region, float(e.max()), scale)
+
+
+def test_two_frame_zero_solver_iterations(ctx, oracle):
+    """niter_solver = 0: the reference erases du,dv and runs a 0-iteration sor_coupled (variational.c:44-45,
+    solver.c:20), so the flow comes back unchanged -- not with stale arena contents added to it."""
+    w, h = 160, 96
+    im1, im2, wx0, wy0 = helpers.pair(w, h)
+    warm_x, warm_y = wx0.copy(), wy0.copy()
+    ctx.variational(warm_x, warm_y, im1, im2, None)  # leaves non-zero increments in the context's arena
+    p = variational_params_default()
+    p.niter_solver, p.niter_outer, p.niter_inner = 0, 2, 2
+    gx, gy = wx0.copy(), wy0.copy()
+    ctx.variational(gx, gy, im1, im2, p)
+    ox, oy = wx0.copy(), wy0.copy()
+    oracle.variational(ox, oy, im1, im2, p, SOR_REDBLACK)
+    assert np.array_equal(gx.array, ox.array) and np.array_equal(gy.array, oy.array)
+    assert np.array_equal(gx.array, wx0.array)
+
+
 def test_sub_laplacian(ctx, oracle):
     w, h = 77, 50
     b, src = helpers.rng_plane(w, h, 3), helpers.rng_plane(w, h, 4, -3, 3)
@@ -200,6 +256,69 @@ def test_sequence_equals_individual_pairs(ctx):
         a, b = Image.from_array(u0), Image.from_array(v0)
         ctx.variational(a, b, frames[j], frames[j + 1], None)
         assert np.array_equal(a.array, wxs[j].array) and np.array_equal(b.array, wys[j].array), j
+
+
+@pytest.mark.parametrize("dtype,channels", [(np.uint8, 3), (np.uint8, 1), (np.uint16, 3)])
+def test_integer_frame_sequence_equals_float_sequence(ctx, dtype, channels):
+    """sfgpu_variational_sequence_u8/_u16: frames cross PCIe as the integer images the reference holds before
+    mat2colorImg / convertTo (adaptiveFR.cpp:450-464, slow_flow.cpp:470-477) and are converted on the device.  Bit-exact
+    against converting on the host; rows carry a cv::Mat-like step; continue_from_previous re-uses the resident frame."""
+    w, h, n = 322, 200, 4
+    top = 255 if dtype == np.uint8 else 65535
+    raws = []
+    for t in range(n + 1):
+        f = np.rint(synth.frame(w, h, t) * (top / 255.0)).astype(dtype)       # (3, H, W)
+        canvas = np.zeros((h, w + 5, channels), dtype)                          # step > width * channels
+        canvas[:, :w, :] = np.moveaxis(f, 0, 2)[:, :, :channels]
+        raws.append(canvas[:, :w, :] if channels == 3 else canvas[:, :w, 0])
+    floats = []
+    for r in raws:
+        a = np.repeat(r[None].astype(np.float32), 3, axis=0) if channels == 1 else np.moveaxis(r, 2, 0).astype(np.float32)
+        floats.append(ColorImage.from_array(a))
+    u0, v0 = synth.initial_flow(w, h)
+    scale_params = variational_params_default()
+    if dtype == np.uint16:
+        scale_params.gamma = 0.71 / 257.0  # 16-bit intensities: keep the data term in the regime of the 8-bit case
+    ax, ay = [Image.from_array(u0) for _ in range(n)], [Image.from_array(v0) for _ in range(n)]
+    ctx.variational_sequence(floats, ax, ay, scale_params)
+    bx, by = [Image.from_array(u0) for _ in range(n)], [Image.from_array(v0) for _ in range(n)]
+    ctx.variational_sequence_int(raws, bx, by, scale_params)
+    for j in range(n):
+        assert np.array_equal(ax[j].array, bx[j].array) and np.array_equal(ay[j].array, by[j].array), j
+    # the same sequence in two calls, the second continuing from the frame the first one left on the device
+    cx, cy = [Image.from_array(u0) for _ in range(n)], [Image.from_array(v0) for _ in range(n)]
+    ctx.variational_sequence_int(raws[:3], cx[:2], cy[:2], scale_params)
+    ctx.variational_sequence_int(raws[2:], cx[2:], cy[2:], scale_params, continue_from_previous=True)
+    for j in range(n):
+        assert np.array_equal(ax[j].array, cx[j].array) and np.array_equal(ay[j].array, cy[j].array), j
+    # continuing without a resident frame is an error, not a silent re-use of stale memory
+    a, b = Image.from_array(u0), Image.from_array(v0)
+    ctx.variational(a, b, floats[0], floats[1], None)  # any other call invalidates the ring
+    with pytest.raises(RuntimeError, match="continue_from_previous"):
+        ctx.variational_sequence_int(raws[2:], cx[2:], cy[2:], scale_params, continue_from_previous=True)
+
+
+def test_sequence_pageable_buffers_are_staged(ctx):
+    """Ordinary (pageable) caller memory takes the staged copies of sf_hostcopy.cu pair by pair; same results."""
+    w, h, n = 1024, 600, 3  # planes of 2.4 MB: above the staging threshold
+    frames = [ColorImage.from_array(synth.frame(w, h, t)) for t in range(n + 1)]
+    u0, v0 = synth.initial_flow(w, h)
+    ax, ay = [Image.from_array(u0) for _ in range(n)], [Image.from_array(v0) for _ in range(n)]
+    ctx.variational_sequence(frames, ax, ay, None)  # numpy memory is pageable
+    lib = ctx.lib
+    regs = [f.buf for f in frames] + [x.buf for x in ax] + [y.buf for y in ay]
+    bx, by = [Image.from_array(u0) for _ in range(n)], [Image.from_array(v0) for _ in range(n)]
+    pinned = [f.buf for f in frames] + [x.buf for x in bx] + [y.buf for y in by]
+    for b in pinned:
+        assert lib.sfgpu_host_register(b.ctypes.data, b.nbytes) == 0
+    try:
+        ctx.variational_sequence(frames, bx, by, None)  # page-locked: the pipelined path
+    finally:
+        for b in pinned:
+            lib.sfgpu_host_unregister(b.ctypes.data)
+    for j in range(n):
+        assert np.array_equal(ax[j].array, bx[j].array) and np.array_equal(ay[j].array, by[j].array), j
+    del regs
 
 
 def test_device_resident_entry(ctx):

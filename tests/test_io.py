@@ -29,6 +29,33 @@ def test_flo_bytes_match_reference_writer_and_round_trip(oracle, tmp_path, w, h)
     assert np.array_equal(rx.array, wx.array) and np.array_equal(ry.array, wy.array)
 
 
+@pytest.mark.parametrize("w,h", [(64, 48), (61, 45), (1, 7)])
+def test_flo_against_the_reference_io_functions(reference, tmp_path, w, h):
+    """writeFlowFile / readFlowFile of the reference's own io.c (:50-96), compiled into oracle/_ref: our writer's bytes
+    equal the reference writer's, and the reference reader reads our file back."""
+    r = np.random.RandomState(w * 31 + h)
+    wx, wy = Image.from_array(r.randn(h, w).astype(np.float32) * 5), Image.from_array(r.randn(h, w).astype(np.float32) * 5)
+    wx.buf.reshape(h, -1)[:, w:] = 777.0
+    a, b = tmp_path / "ours.flo", tmp_path / "ref.flo"
+    write_flo(a, wx, wy)
+    L = reference.lib
+    IP = C.POINTER(image_t)
+    L.writeFlowFile.argtypes = [C.c_char_p, IP, IP]
+    L.writeFlowFile.restype = None
+    L.writeFlowFile(str(b).encode(), wx.ptr(), wy.ptr())
+    assert a.read_bytes() == b.read_bytes()
+    L.readFlowFile.argtypes = [C.c_char_p]
+    L.readFlowFile.restype = C.POINTER(IP)
+    flow = L.readFlowFile(str(a).encode())  # (leaks two small images: the reference's own ownership rule)
+    for k, src in enumerate((wx, wy)):
+        im = flow[k].contents
+        assert (im.width, im.height) == (w, h)
+        got = np.ctypeslib.as_array(im.data, shape=(h, im.stride))[:, :w]
+        assert np.array_equal(got, src.array)
+    ox, oy = read_flo(b)  # and our reader reads the reference writer's file
+    assert np.array_equal(ox.array, wx.array) and np.array_equal(oy.array, wy.array)
+
+
 def test_flo_reader_rejects_garbage(tmp_path):
     p = tmp_path / "bad.flo"
     p.write_bytes(b"PIEH" + b"\0" * 20)

@@ -20,6 +20,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <map>
@@ -120,6 +121,7 @@ int main(int argc, char **argv) {
     std::string frames_fmt, out;
     int start = 0, jets = 1, skip = 1, gpus = 0, per_gpu = 1;
     float scale = 1.0f;
+    bool resume = false; // -resume: a window whose .flo already exists is skipped (slow_flow.cpp:794, :958)
     ParameterList cfg;
     cfg.insert("slow_flow_S", "3", true);
     for (int i = 1; i < argc; i++) {
@@ -135,6 +137,7 @@ int main(int argc, char **argv) {
         else if (a == "--scale") scale = (float)atof(next().c_str());
         else if (a == "--S") cfg.insert("slow_flow_S", next(), true);
         else if (a == "--occlusions") cfg.insert("slow_flow_output_occlusions", "1", true);
+        else if (a == "--resume" || a == "-resume") resume = true; // slow_flow.cpp:178-179
         else if (a == "--set") {
             const std::string kv = next();
             const size_t eq = kv.find('=');
@@ -197,7 +200,7 @@ int main(int argc, char **argv) {
     // ---- one host thread per device, contiguous jet ranges (the reference's omp parallel for over jets, :706)
     const auto t_loop = std::chrono::steady_clock::now();
     std::vector<std::thread> pool;
-    std::vector<int> done(workers, 0);
+    std::vector<int> done(workers, 0), skipped(workers, 0);
     for (int t = 0; t < workers; t++) {
         pool.emplace_back([&, t]() {
             if (sfgpu_set_device(t % gpus) != SFGPU_OK) die(sfgpu_last_error());
@@ -212,7 +215,9 @@ int main(int argc, char **argv) {
                 color_image_t **im = &seq[f];
                 color_image_t **im_back = &seq_back[frames - 1 - f - 3 * steps];
                 char path[1200];
-                {   // forward
+                snprintf(path, sizeof(path), (out + name + ".flo").c_str(), start + f * skip);
+                if (resume && access(path, F_OK) == 0) skipped[t]++; // skip finished frames (slow_flow.cpp:794)
+                else {   // forward
                     image_t *wx = new_image(W, H), *wy = new_image(W, H); // zero initial flow (:865-868)
                     minimzer_f.variational(wx, wy, im, thread_params);
                     if (write_occ) {
@@ -224,7 +229,9 @@ int main(int argc, char **argv) {
                     if (sfgpu_write_flo(path, wx, wy) != SFGPU_OK) die(sfgpu_last_error());
                     free_image(wx); free_image(wy);
                 }
-                {   // backward
+                snprintf(path, sizeof(path), (out + name + "_back.flo").c_str(), start + f * skip + steps * skip);
+                if (resume && access(path, F_OK) == 0) skipped[t]++; // (slow_flow.cpp:958)
+                else {   // backward
                     image_t *wx = new_image(W, H), *wy = new_image(W, H);
                     minimzer_b.variational(wx, wy, im_back, thread_params);
                     for (size_t k = 0; k < (size_t)wx->stride * H; k++) { wx->data[k] *= steps; wy->data[k] *= steps; } // :1026-1027
@@ -252,7 +259,7 @@ int main(int argc, char **argv) {
     }
     int total = 0;
     for (int t = 0; t < workers; t++) {
-        printf("worker %d (device %d): %d jets\n", t, t % gpus, done[t]);
+        printf("worker %d (device %d): %d jets, %d finished flow files skipped\n", t, t % gpus, done[t], skipped[t]);
         total += done[t];
     }
     printf("%d jets, %dx%d, S=%d, %d device(s), %d host thread(s) per device\n", total, W, H, steps + 1, gpus, per_gpu);
