@@ -181,6 +181,7 @@ typedef struct sfgpu_mt_stats_s {
     double setup_ms;       /* workspace, uploads, pyramid (until the coarsest level starts) */
     double graphcut_ms;    /* optimizeOcc: data costs + labelling, all calls */
     double total_ms;
+    long long pixel_outer_iterations; /* sum over the executed outer iterations of width*height of their level */
 } sfgpu_mt_stats_t;
 int sfgpu_get_mt_stats(sfgpu_ctx *ctx, sfgpu_mt_stats_t *out);
 

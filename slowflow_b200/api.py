@@ -36,7 +36,7 @@ class FrameInt(C.Structure):
 class MTStats(C.Structure):
     _fields_ = [("levels", C.c_int), ("outer_iterations", C.c_int), ("sor_calls", C.c_int),
                 ("graphcut_calls", C.c_int), ("setup_ms", C.c_double), ("graphcut_ms", C.c_double),
-                ("total_ms", C.c_double)]
+                ("total_ms", C.c_double), ("pixel_outer_iterations", C.c_longlong)]
 
 
 # every symbol include/slowflow_gpu.h declares (checked by tests/test_abi.py)

@@ -463,6 +463,7 @@ static int compute_one_level(LevelCtx &L, float avg_change[2]) { // variational_
         for (int outer = 0; outer < p->niter_outer; outer++) {
             if (outer > 0) warp_all(L); // :289-290
             c->mt_stats.outer_iterations++;
+            c->mt_stats.pixel_outer_iterations += (long long)g.W * g.H;
             int cur = 0;
             bool broke_inner = false;
             int inner_done = 0;

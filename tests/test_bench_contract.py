@@ -23,6 +23,12 @@ def test_reference_arm_prints_one_json_line(built):
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["gpu_launches"] == 0
+    # whole fields, and the workload string of our own arm (the driver compares the two arms' configs)
+    assert "whole fields" in d["config"]["workload"] and "192x288" in d["config"]["workload"]
+    assert "288 = 1.000 field" in d["cpu_baseline"]["sample"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"]["workload"] == bench.WORKLOAD % (192, 288)
 
 
 def test_reference_arm_other_ranks_exit_silently(built):
