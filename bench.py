@@ -62,6 +62,25 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class _StdoutToStderr:
+    """The reference's CPU driver prints progress with cout ("layer 2:" ...); bench.py's stdout carries ONE JSON line, so the
+    C-level stdout is pointed at stderr while reference code runs."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -336,10 +355,11 @@ def run_mt_secondary(ctx, torch, with_cpu, reps=3):
             arr = (CP * 5)(*[C.pointer(f.c) for f in raw])
             cx, cy, occ = Image.from_array(u0), Image.from_array(v0), Image(w, h)
             avg, st = (C.c_float * 2)(), (C.c_int * 2)()
-            t0 = time.perf_counter()
-            getattr(lib, prefix + "normalize")(arr, 5, C.byref(pc))
-            getattr(lib, prefix + "variational_mt")(cx.ptr(), cy.ptr(), arr, C.byref(pc), None, occ.ptr(), avg, 0, st)
-            cpu_s = time.perf_counter() - t0
+            with _StdoutToStderr():
+                t0 = time.perf_counter()
+                getattr(lib, prefix + "normalize")(arr, 5, C.byref(pc))
+                getattr(lib, prefix + "variational_mt")(cx.ptr(), cy.ptr(), arr, C.byref(pc), None, occ.ptr(), avg, 0, st)
+                cpu_s = time.perf_counter() - t0
             per_outer_cpu = cpu_s / (n_outer * layers)
             line["cpu_baseline"] = {
                 "value": per_outer_cpu, "unit": "s per outer iteration (1 core)", "cores": 1, "kind": kind,

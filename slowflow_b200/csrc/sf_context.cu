@@ -157,13 +157,6 @@ int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d
     c->prof_acc.kernel_launches++;
 
     const bool fused_prep = c->data_variant == 0; // 1: separate warp kernel + tile-based data-term kernel (A/B reference)
-    // the fused kernel gathers the warped image from a pixel-interleaved copy of im2 (im2 is constant over the outer
-    // iterations): it lives in the 4 planes that hold the warped image + mask of the A/B variant
-    float *im2q = c->wim;
-    if (fused_prep) {
-        launch_interleave3(st, g, d_im2, im2q);
-        c->prof_acc.kernel_launches++;
-    }
     if (fused_prep && params->niter_inner == 1 && params->niter_solver > 0) {
         // Default shape of the loop (one inner iteration): per outer iteration the flow update of the previous
         // iteration (variational.c:60-69 collapsed to w += du) is folded into the smoothness pass, so an outer
@@ -182,7 +175,7 @@ int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d
             }
             cudaEvent_t ev;
             c->prof_begin(PROF_DATA, ev);
-            launch_prep_two_frame(st, g, c->num_sms, d_im1, d_im2, im2q, fx, fy, nullptr, nullptr, A + SP_PH * P, A + SP_PV * P,
+            launch_prep_two_frame(st, g, c->num_sms, d_im1, d_im2, fx, fy, nullptr, nullptr, A + SP_PH * P, A + SP_PV * P,
                                   half_delta_over3, half_gamma_over3, A + SP_A11 * P, A + SP_A12 * P, A + SP_A22 * P,
                                   A + SP_B1 * P, A + SP_B2 * P);
             c->prof_end(PROF_DATA, ev);
@@ -226,7 +219,7 @@ int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d
             cm.a11 = A + SP_A11 * P; cm.a12 = A + SP_A12 * P; cm.a22 = A + SP_A22 * P; cm.b1 = A + SP_B1 * P;
             cm.b2 = A + SP_B2 * P;
             if (fused_prep)
-                launch_prep_two_frame(st, g, c->num_sms, d_im1, d_im2, im2q, d_wx, d_wy, du, dv, cm.ph, cm.pv, half_delta_over3,
+                launch_prep_two_frame(st, g, c->num_sms, d_im1, d_im2, d_wx, d_wy, du, dv, cm.ph, cm.pv, half_delta_over3,
                                       half_gamma_over3, cm.a11, cm.a12, cm.a22, cm.b1, cm.b2);
             else
                 launch_data_term(st, g, term, cm);
@@ -676,18 +669,17 @@ int sfgpu_prep_two_frame(sfgpu_ctx *c, image_t *a11, image_t *a12, image_t *a22,
     const size_t P = g.plane();
     cudaStream_t st = c->stream;
     DevPlanes d;
-    int rc = d.alloc(21 * P);
+    int rc = d.alloc(17 * P);
     if (rc) return rc;
     float *i1 = d.p, *i2 = d.p + 3 * P, *fx = d.p + 6 * P, *fy = d.p + 7 * P, *u = d.p + 8 * P, *v = d.p + 9 * P,
-          *dh = d.p + 10 * P, *dvv = d.p + 11 * P, *o = d.p + 12 * P, *i2q = d.p + 17 * P;
+          *dh = d.p + 10 * P, *dvv = d.p + 11 * P, *o = d.p + 12 * P;
     H2D(i1, im1->c1, 3 * P); H2D(i2, im2->c1, 3 * P); H2D(fx, wx->data, P); H2D(fy, wy->data, P);
     H2D(dh, ph->data, P); H2D(dvv, pv->data, P);
     if (du) { H2D(u, du->data, P); H2D(v, dv->data, P); }
     SF_CUDA(cudaMemsetAsync(o, 0xff, 5 * P * sizeof(float), st)); // NaN pattern: every element must be written by the kernel
-    launch_interleave3(st, g, i2, i2q);
-    launch_prep_two_frame(st, g, c->num_sms, i1, i2, i2q, fx, fy, du ? u : nullptr, du ? v : nullptr, dh, dvv, half_delta_over3,
+    launch_prep_two_frame(st, g, c->num_sms, i1, i2, fx, fy, du ? u : nullptr, du ? v : nullptr, dh, dvv, half_delta_over3,
                           half_gamma_over3, o, o + P, o + 2 * P, o + 3 * P, o + 4 * P);
-    c->prof_acc.kernel_launches += 2;
+    c->prof_acc.kernel_launches++;
     D2H(a11->data, o, P); D2H(a12->data, o + P, P); D2H(a22->data, o + 2 * P, P); D2H(b1->data, o + 3 * P, P);
     D2H(b2->data, o + 4 * P, P);
     SF_CUDA(cudaStreamSynchronize(st));

@@ -252,6 +252,7 @@ __device__ __forceinline__ void term_mt_ref(const Derivs &d, float u, float v, f
 template <int KIND>
 __global__ void __launch_bounds__(256) k_data_term(Geom g, DataTermDesc t, DataCommon cm) {
     pdl_enter();
+    if (g.cancelled()) return;
     extern __shared__ float smem[];
     float *sm_m = smem;                       // [3][DT_MH][DT_MW]
     float *sm_z = sm_m + 3 * DT_MH * DT_MW;   // [3][DT_MH][DT_MW]

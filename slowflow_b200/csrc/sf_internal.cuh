@@ -15,9 +15,17 @@ namespace sf {
 // ---------------------------------------------------------------------------------------------
 // geometry of one pyramid level: W valid columns, H rows, S = ceil4(W) floats per row (image.c:25).
 // Device planes use exactly the host layout, so a plane moves with one cudaMemcpyAsync.
+// skip: optional device flag.  When it is set every kernel of the refinement chain returns at once: this is how the
+// data-dependent early exit of the multi-frame outer loop (variational_mt.cpp:436-437) works without a host round trip --
+// the host queues all outer iterations of an alternation, the reduction kernel that closes an iteration raises the flag,
+// and the launches queued behind it fall through (sf_mt.cu).  NULL everywhere else.
 struct Geom {
     int W, H, S;
+    const int *skip = nullptr;
     __host__ __device__ size_t plane() const { return (size_t)S * H; }
+#ifdef __CUDACC__
+    __device__ __forceinline__ bool cancelled() const { return skip != nullptr && *reinterpret_cast<const volatile int *>(skip) != 0; }
+#endif
 };
 static inline Geom make_geom(int w, int h) { return Geom{w, h, ((w + 3) / 4) * 4}; }
 
@@ -111,12 +119,9 @@ struct DataCommon {
 void launch_data_term(cudaStream_t st, Geom g, const DataTermDesc &t, const DataCommon &cm);
 // K1+K2 fused, marching form (sf_prep.cu): warp + derivatives + two-frame data term + Laplacian + block inverse.
 // Writes the same five planes as launch_warp + launch_data_term(fuse_system) without the warped image in HBM.
-// im2q: the pixel-interleaved copy of im2 made by launch_interleave3 (4 floats per pixel: c1 c2 c3 0), once per field.
-void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im1, const float *im2, const float *im2q,
-                           const float *wx, const float *wy, const float *du, const float *dv, const float *ph, const float *pv,
+void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im1, const float *im2, const float *wx, const float *wy, const float *du, const float *dv, const float *ph, const float *pv,
                            float half_delta_over3, float half_gamma_over3, float *a11, float *a12, float *a22, float *b1,
                            float *b2);
-void launch_interleave3(cudaStream_t st, Geom g, const float *im3, float *out4);
 // convolve_horiz / convolve_vert over `planes` planes (operator twins; order 1 = 3 taps, 2 = 5 taps)
 void launch_convolve(cudaStream_t st, Geom g, const float *src, float *dst, bool vertical, int order, const float *coeffs,
                      int planes);

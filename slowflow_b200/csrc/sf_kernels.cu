@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256) k_warp(Geom g, const float *__restrict__ 
                                               const float *__restrict__ wy, float factor, float *__restrict__ dst,
                                               float *__restrict__ mask) {
     pdl_enter();
+    if (g.cancelled()) return;
     const int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i4 >= g.S || j >= g.H) return;
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(256) k_flow_smooth(Geom g, const float *__rest
                                                      float *__restrict__ wx_out, float *__restrict__ wy_out,
                                                      float *__restrict__ ph, float *__restrict__ pv) {
     pdl_enter();
+    if (g.cancelled()) return;
     const int lane = threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (j >= g.H) return; // warp-uniform (a warp is one row segment)
@@ -342,6 +344,7 @@ void launch_mean_diff(cudaStream_t st, size_t n, const float *im1, const float *
 // ------------------------------------------------------------------------------------------ small operators
 __global__ void __launch_bounds__(256) k_sub_laplacian(Geom g, float *__restrict__ dst, const float *__restrict__ src,
                                                        const float *__restrict__ ph, const float *__restrict__ pv) {
+    if (g.cancelled()) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= g.W || j >= g.H) return;
@@ -362,6 +365,7 @@ void launch_sub_laplacian(cudaStream_t st, Geom g, float *dst, const float *src,
 __global__ void __launch_bounds__(256) k_invert_blocks(Geom g, float *__restrict__ a11, float *__restrict__ a12,
                                                        float *__restrict__ a22, const float *__restrict__ ph,
                                                        const float *__restrict__ pv) {
+    if (g.cancelled()) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= g.W || j >= g.H) return;

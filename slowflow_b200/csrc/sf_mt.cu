@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) k_mt_update(Geom g, float *__restrict__ w
                                                    const float *__restrict__ odu, const float *__restrict__ odv,
                                                    float *__restrict__ uu, float *__restrict__ vv, int finalize,
                                                    float *__restrict__ part) {
+    if (g.cancelled()) return;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     const int i = blockIdx.x * 32 + threadIdx.x;
     for (int j = blockIdx.y * 8 + threadIdx.y; j < g.H; j += gridDim.y * 8) {
@@ -68,6 +69,43 @@ __global__ void __launch_bounds__(256) k_mt_update(Geom g, float *__restrict__ w
         __syncthreads();
     }
     if (t < 4) part[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 4 + t] = red[t][0];
+}
+
+// Device-side end of an outer iteration (niter_inner == 1): adds the block partials of k_mt_update in a fixed order
+// (double, deterministic), publishes the mean absolute change of the iteration (variational_mt.cpp:412-429) and raises
+// the skip flag when it is below thres_outer (:436-437) -- the launches of the remaining outer iterations of this
+// alternation, already queued behind this kernel, then fall through.
+struct MtLoopState {
+    int stop;              // Geom::skip points here
+    int outer_done;        // outer iterations executed since the level started
+    float avg_change[2];   // of the last executed outer iteration
+};
+__global__ void __launch_bounds__(256) k_mt_close_iteration(Geom g, const float *__restrict__ part, int nblocks, double inv_n,
+                                                            float thres_outer, MtLoopState *state) {
+    if (g.cancelled()) return;
+    __shared__ double red[2][256];
+    double a = 0.0, b = 0.0;
+    for (int k = threadIdx.x; k < nblocks; k += 256) { // fixed assignment of blocks to threads, fixed tree below
+        a += (double)part[(size_t)k * 4 + 2];
+        b += (double)part[(size_t)k * 4 + 3];
+    }
+    red[0][threadIdx.x] = a;
+    red[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + k];
+            red[1][threadIdx.x] += red[1][threadIdx.x + k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float cx = (float)(red[0][0] * inv_n), cy = (float)(red[1][0] * inv_n);
+        state->avg_change[0] = cx;
+        state->avg_change[1] = cy;
+        state->outer_done += 1;
+        if (fmaxf(cx, cy) < thres_outer) state->stop = 1;
+    }
 }
 
 // per-pixel data costs of the binary occlusion labelling (variational_aux_mt.cpp:786-848).
@@ -265,6 +303,8 @@ struct MtWork {
     long long *tr_host = nullptr; // pinned: terminal capacities of the occlusion min-cut
     unsigned char *lab_dev = nullptr;
     size_t cut_nodes = 0;
+    MtLoopState *loop_dev = nullptr;  // device-side outer-loop state (skip flag, counters)
+    MtLoopState *loop_host = nullptr; // pinned read-back
     SinkForestCut cut;
     ~MtWork() { release(); }
     void release() {
@@ -273,12 +313,19 @@ struct MtWork {
         if (part_host) cudaFreeHost(part_host);
         if (tr_host) cudaFreeHost(tr_host);
         if (lab_dev) cudaFree(lab_dev);
+        if (loop_dev) cudaFree(loop_dev);
+        if (loop_host) cudaFreeHost(loop_host);
+        loop_dev = loop_host = nullptr;
         pool = part_dev = part_host = nullptr;
         tr_host = nullptr;
         lab_dev = nullptr;
         pool_floats = part_cap = cut_nodes = 0;
     }
     int reserve(size_t floats, size_t partials, size_t nodes) {
+        if (!loop_dev) {
+            SF_CUDA(cudaMalloc(&loop_dev, sizeof(MtLoopState)));
+            SF_CUDA(cudaMallocHost(&loop_host, sizeof(MtLoopState)));
+        }
         if (floats > pool_floats) {
             if (pool) cudaFree(pool);
             pool = nullptr; pool_floats = 0;
@@ -454,6 +501,86 @@ static int compute_one_level(LevelCtx &L, float avg_change[2]) { // variational_
     avg_change[0] = avg_change[1] = 0.f;
     const double inv_n = 1.0 / ((double)g.H * g.W);
 
+    if (p->niter_inner == 1) {
+        // ---- default shape (one inner iteration): no host round trip inside the level.  Every kernel of the outer loop
+        // carries the skip flag; the host reads the loop state back once, after the last alternation (and whenever the
+        // occlusion step synchronises anyway).
+        MtLoopState *state = L.work->loop_dev;
+        SF_CUDA(cudaMemsetAsync(state, 0, sizeof(MtLoopState), st));
+        const int *flag = &state->stop;
+        const int nblocks = (int)(ugrid.x * ugrid.y);
+        for (int alter = 0; alter < p->niter_alter; alter++) {
+            SF_CUDA(cudaMemsetAsync(&state->stop, 0, sizeof(int), st)); // a break leaves the outer loop, not the alternation loop
+            L.g.skip = nullptr;
+            c->sor.g.skip = nullptr;
+            warp_all(L); // :266
+            if (alter > 0 && p->occlusion_reasoning && !L.one_direction) { // :269-272
+                int rc = optimize_occ(L);
+                if (rc != SFGPU_OK) return rc;
+            }
+            L.g.skip = flag;
+            c->sor.g.skip = flag;
+            const Geom gs = L.g;
+            for (int outer = 0; outer < p->niter_outer; outer++) {
+                if (outer > 0) warp_all(L); // :289-290
+                int cur = 0;
+                launch_smoothness(st, gs, L.wx, L.wy, L.dpsis, L.alpha, L.preg, p->smoothing, A + SP_PH * P, A + SP_PV * P); // :333
+                c->prof_acc.kernel_launches++;
+                DataCommon cm{};
+                cm.du = nullptr; cm.dv = nullptr;
+                cm.chw = L.chw;
+                cm.chw_pstride = L.chw_pstride;
+                cm.occ = L.occ;
+                cm.data_norm = data_norm;
+                cm.dt_norm = p->dataterm;
+                cm.pc = L.pc;
+                cm.pg = L.pg;
+                cm.ph = A + SP_PH * P; cm.pv = A + SP_PV * P;
+                cm.lap_u = L.wx; cm.lap_v = L.wy; // uu == wx at the start of an outer iteration (:364-365)
+                cm.a11 = A + SP_A11 * P; cm.a12 = A + SP_A12 * P; cm.a22 = A + SP_A22 * P;
+                cm.b1 = A + SP_B1 * P; cm.b2 = A + SP_B2 * P;
+                cudaEvent_t ev;
+                c->prof_begin(1, ev);
+                if (terms.empty()) { // no active data term: the system is the smoothness term alone
+                    launch_fill(st, cm.a11, 5 * P, 0.0f);
+                    launch_sub_laplacian(st, gs, cm.b1, L.wx, cm.ph, cm.pv);
+                    launch_sub_laplacian(st, gs, cm.b2, L.wy, cm.ph, cm.pv);
+                    launch_invert_blocks(st, gs, cm.a11, cm.a12, cm.a22, cm.ph, cm.pv);
+                    c->prof_acc.kernel_launches += 4;
+                }
+                for (size_t k = 0; k < terms.size(); k++) {
+                    cm.accumulate = (k > 0);
+                    cm.fuse_system = (k + 1 == terms.size());
+                    launch_data_term(st, gs, terms[k], cm);
+                    c->prof_acc.kernel_launches++;
+                    c->prof_acc.data_launches++;
+                    c->prof_acc.data_pixels += (long long)g.W * g.H;
+                }
+                c->prof_end(1, ev);
+                int rc = run_sor(c, p->niter_solver, p->sor_omega, &cur, true); // :368
+                if (rc != SFGPU_OK) { c->sor.g.skip = nullptr; return rc; }
+                const float *ndu = A + (size_t)(cur ? SP_DUB : SP_DUA) * P, *ndv = A + (size_t)(cur ? SP_DVB : SP_DVA) * P;
+                k_mt_update<<<ugrid, dim3(32, 8), 0, st>>>(gs, L.wx, L.wy, ndu, ndv, nullptr, nullptr, nullptr, nullptr, 1, L.work->part_dev);
+                k_mt_close_iteration<<<1, 256, 0, st>>>(gs, L.work->part_dev, nblocks, inv_n, p->thres_outer, state);
+                c->prof_acc.kernel_launches += 2;
+            }
+        }
+        L.g.skip = nullptr;
+        c->sor.g.skip = nullptr;
+        SF_CUDA(cudaMemcpyAsync(L.work->loop_host, state, sizeof(MtLoopState), cudaMemcpyDeviceToHost, st));
+        SF_CUDA(cudaStreamSynchronize(st));
+        const int done = L.work->loop_host->outer_done;
+        c->mt_stats.outer_iterations += done;
+        c->mt_stats.pixel_outer_iterations += (long long)done * g.W * g.H;
+        c->mt_stats.sor_calls += done;
+        if (done > 0) { // (niter_outer == 0 leaves the previous level's value, like the reference's member variable)
+            avg_change[0] = L.work->loop_host->avg_change[0];
+            avg_change[1] = L.work->loop_host->avg_change[1];
+        }
+        // (prof_acc's launch / pixel counters were accumulated per QUEUED iteration; the event times are of what really ran)
+        SF_CUDA(cudaGetLastError());
+        return SFGPU_OK;
+    }
     for (int alter = 0; alter < p->niter_alter; alter++) {
         warp_all(L); // :266
         if (alter > 0 && p->occlusion_reasoning && !L.one_direction) { // :269-272

@@ -91,14 +91,9 @@ __device__ __forceinline__ p64 rcp2(p64 x) {
     return fma2(r, e, r);
 }
 
-#ifndef SF_PREP_RGBA
-#define SF_PREP_RGBA 1 // the warped image is gathered from a pixel-interleaved copy of im2 (one 16-byte load per tap)
-#endif
-
 struct PrepArgs {
     Geom g;
     const float *im1, *im2; // 3 planes each
-    const float4 *im2q;     // im2 interleaved (c1, c2, c3, 0) per pixel, row stride S pixels (SF_PREP_RGBA)
     const float *wx, *wy;   // flow: warps im2 and is the argument of the Laplacian
     const float *du, *dv;   // current increment (nullable: 0)
     const float *ph, *pv;   // smoothness diffusivities
@@ -129,36 +124,6 @@ __device__ __forceinline__ Taps warp_taps(const Geom &g, float xx, float yy) {
 __device__ __forceinline__ float warp_fetch(const float *__restrict__ src, const Taps &t) {
     return __ldg(src + t.o11) * t.w11 + __ldg(src + t.o12) * t.w12 + __ldg(src + t.o21) * t.w21 + __ldg(src + t.o22) * t.w22;
 }
-// the three channels of one warped pixel from the interleaved copy: 4 x LDG.128 instead of 12 x LDG.32; per channel the
-// same expression (and rounding) as warp_fetch
-struct Px3 { float c[3]; };
-__device__ __forceinline__ Px3 warp_fetch3(const float4 *__restrict__ q, const Taps &t) {
-    const float4 s11 = __ldg(q + t.o11), s12 = __ldg(q + t.o12), s21 = __ldg(q + t.o21), s22 = __ldg(q + t.o22);
-    Px3 r;
-    r.c[0] = s11.x * t.w11 + s12.x * t.w12 + s21.x * t.w21 + s22.x * t.w22;
-    r.c[1] = s11.y * t.w11 + s12.y * t.w12 + s21.y * t.w21 + s22.y * t.w22;
-    r.c[2] = s11.z * t.w11 + s12.z * t.w12 + s21.z * t.w21 + s22.z * t.w22;
-    return r;
-}
-// im2 (3 planes) -> (c1, c2, c3, 0) per pixel; once per field: im2 does not change over the outer iterations
-__global__ void __launch_bounds__(256) k_interleave3(size_t n4, const float4 *__restrict__ c1, const float4 *__restrict__ c2,
-                                                     const float4 *__restrict__ c3, float4 *__restrict__ out) {
-    pdl_enter();
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (size_t)gridDim.x * blockDim.x) {
-        const float4 a = __ldg(c1 + k), b = __ldg(c2 + k), c = __ldg(c3 + k);
-        out[4 * k + 0] = make_float4(a.x, b.x, c.x, 0.f);
-        out[4 * k + 1] = make_float4(a.y, b.y, c.y, 0.f);
-        out[4 * k + 2] = make_float4(a.z, b.z, c.z, 0.f);
-        out[4 * k + 3] = make_float4(a.w, b.w, c.w, 0.f);
-    }
-}
-void launch_interleave3(cudaStream_t st, Geom g, const float *im3, float *out4) {
-    const size_t P = g.plane(), n4 = P / 4;
-    const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
-    launch_pdl(k_interleave3, dim3(blocks), dim3(256), 0, st, n4, reinterpret_cast<const float4 *>(im3),
-               reinterpret_cast<const float4 *>(im3 + P), reinterpret_cast<const float4 *>(im3 + 2 * P), reinterpret_cast<float4 *>(out4));
-}
-
 // One warp marches down its (strip, segment).  EDGE: the strip touches the left or right image border.
 template <bool COLOR, bool EDGE>
 __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, const int seg, const int lane, p64 *ring_sm) {
@@ -220,22 +185,11 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
         const Taps t0 = warp_taps(g, fxc0 + lo_of(fx), (float)rr + lo_of(fy));
         const Taps t1 = warp_taps(g, fxc1 + hi_of(fx), (float)rr + hi_of(fy));
         p64 A[3], B[3];
-#if SF_PREP_RGBA
-        {
-            const Px3 g0 = warp_fetch3(a.im2q, t0), g1 = warp_fetch3(a.im2q, t1);
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                A[c] = An[c];
-                B[c] = pk(g0.c[c], g1.c[c]);
-            }
-        }
-#else
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             A[c] = An[c];
             B[c] = pk(warp_fetch(a.im2 + c * P, t0), warp_fetch(a.im2 + c * P, t1));
         }
-#endif
         {
             const int rn = clampi(r + 1, 0, H1) * S;
 #pragma unroll
@@ -386,22 +340,11 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
         const Taps t0 = warp_taps(g, fxc0 + lo_of(fx), (float)rr + lo_of(fy));
         const Taps t1 = warp_taps(g, fxc1 + hi_of(fx), (float)rr + hi_of(fy));
         p64 A[3], B[3];
-#if SF_PREP_RGBA
-        {
-            const Px3 g0 = warp_fetch3(a.im2q, t0), g1 = warp_fetch3(a.im2q, t1);
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                A[c] = An[c];
-                B[c] = pk(g0.c[c], g1.c[c]);
-            }
-        }
-#else
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             A[c] = An[c];
             B[c] = pk(warp_fetch(a.im2 + c * P, t0), warp_fetch(a.im2 + c * P, t1));
         }
-#endif
         {
             const int rn = clampi(r + 1, 0, H1) * S;
 #pragma unroll
@@ -492,13 +435,11 @@ static void launch_prep_variant(cudaStream_t st, Geom g, int num_sms, PrepArgs &
     launch_pdl(k_prep_two_frame<COLOR>, dim3(blocks), dim3(PR_WARPS * 32), 0, st, a);
 }
 
-void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im1, const float *im2, const float *im2q,
-                           const float *wx, const float *wy, const float *du, const float *dv, const float *ph, const float *pv,
+void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im1, const float *im2, const float *wx, const float *wy, const float *du, const float *dv, const float *ph, const float *pv,
                            float half_delta_over3, float half_gamma_over3, float *a11, float *a12, float *a22, float *b1,
                            float *b2) {
     PrepArgs a;
     a.g = g;
-    a.im2q = reinterpret_cast<const float4 *>(im2q);
     a.im1 = im1; a.im2 = im2; a.wx = wx; a.wy = wy; a.du = du; a.dv = dv; a.ph = ph; a.pv = pv;
     a.a11 = a11; a.a12 = a12; a.a22 = a22; a.b1 = b1; a.b2 = b2;
     a.hd = half_delta_over3; a.hg = half_gamma_over3;

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) k_sor_half_global(Geom g, const float *__
                                                          const float *__restrict__ a22, const float *__restrict__ b1,
                                                          const float *__restrict__ b2, const float *__restrict__ ph,
                                                          const float *__restrict__ pv, float *du, float *dv, float omega) {
+    if (g.cancelled()) return;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (j >= g.H) return;
     const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x) + ((j + COLOUR) & 1);
@@ -261,6 +262,7 @@ k_sor_tiled(const __grid_constant__ CUtensorMap tmap_coef, const __grid_constant
     // barrier set-up above touches no global memory
     pdl_enter();
 #endif
+    if (a.g.cancelled()) return; // (nothing is in flight yet: the first TMA is issued below)
     int tile = blockIdx.x;
     uint32_t phase = 0;
     int npub = 0; // publications of this warp so far (= of every warp it is in step with)

@@ -264,7 +264,8 @@ def test_integer_frame_sequence_equals_float_sequence(ctx, dtype, channels):
     mat2colorImg / convertTo (adaptiveFR.cpp:450-464, slow_flow.cpp:470-477) and are converted on the device.  Bit-exact
     against converting on the host; rows carry a cv::Mat-like step; continue_from_previous re-uses the resident frame."""
     w, h, n = 322, 200, 4
-    top = 255 if dtype == np.uint8 else 65535
+    top = 255 if dtype == np.uint8 else 1020  # 10-bit data in a 16-bit container (full-range 16-bit intensities drive the
+    # two-frame smoothness weight exp(-5 |grad lum / 255|) to 0 and the REFERENCE itself to NaN)
     raws = []
     for t in range(n + 1):
         f = np.rint(synth.frame(w, h, t) * (top / 255.0)).astype(dtype)       # (3, H, W)
@@ -277,13 +278,12 @@ def test_integer_frame_sequence_equals_float_sequence(ctx, dtype, channels):
         floats.append(ColorImage.from_array(a))
     u0, v0 = synth.initial_flow(w, h)
     scale_params = variational_params_default()
-    if dtype == np.uint16:
-        scale_params.gamma = 0.71 / 257.0  # 16-bit intensities: keep the data term in the regime of the 8-bit case
     ax, ay = [Image.from_array(u0) for _ in range(n)], [Image.from_array(v0) for _ in range(n)]
     ctx.variational_sequence(floats, ax, ay, scale_params)
     bx, by = [Image.from_array(u0) for _ in range(n)], [Image.from_array(v0) for _ in range(n)]
     ctx.variational_sequence_int(raws, bx, by, scale_params)
     for j in range(n):
+        assert np.isfinite(ax[j].array).all()
         assert np.array_equal(ax[j].array, bx[j].array) and np.array_equal(ay[j].array, by[j].array), j
     # the same sequence in two calls, the second continuing from the frame the first one left on the device
     cx, cy = [Image.from_array(u0) for _ in range(n)], [Image.from_array(v0) for _ in range(n)]

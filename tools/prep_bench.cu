@@ -15,7 +15,7 @@ int main(int argc, char **argv) {
     const float hd = argc > 4 ? (float)atof(argv[4]) : 0.0f;
     sf::Geom g = sf::make_geom(W, H);
     const size_t P = g.plane();
-    std::vector<float> h(19 * P, 0.f); // im1(3) im2(3) wx wy ph pv | out(5) | im2 interleaved (4)
+    std::vector<float> h(15 * P, 0.f); // im1(3) im2(3) wx wy ph pv | out(5)
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++) {
             const size_t o = (size_t)y * g.S + x;
@@ -33,10 +33,9 @@ int main(int argc, char **argv) {
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     auto run = [&](float *b) {
-        sf::launch_prep_two_frame(0, g, sms, b, b + 3 * P, b + 15 * P, b + 6 * P, b + 7 * P, nullptr, nullptr, b + 8 * P, b + 9 * P, hd, 0.71f * 0.5f / 3.f,
+        sf::launch_prep_two_frame(0, g, sms, b, b + 3 * P, b + 6 * P, b + 7 * P, nullptr, nullptr, b + 8 * P, b + 9 * P, hd, 0.71f * 0.5f / 3.f,
                                   b + 10 * P, b + 11 * P, b + 12 * P, b + 13 * P, b + 14 * P);
     };
-    for (int k = 0; k < 2; k++) sf::launch_interleave3(0, g, d[k] + 3 * P, d[k] + 15 * P);
     for (int k = 0; k < 4; k++) run(d[k & 1]);
     cudaDeviceSynchronize();
     cudaEventRecord(e0);
