@@ -328,7 +328,7 @@ def run_mt_secondary(ctx, torch, with_cpu, reps=3):
         times.sort()
         t_win = times[len(times) // 2]
         model_bytes = MT_BYTES_PER_PX_OUTER * stats.pixel_outer_iterations
-        host_ms = stats.setup_ms + stats.graphcut_ms
+        host_ms = stats.setup_ms + stats.graphcut_ms + prof.graphcut_ms
         line = {
             "workload": "Variational_MT %dx%d, S=3 (5 frames), %d pyramid layer(s), Geman-McClure eps 0.5, occlusion reasoning, "
                         "2 alternations x 10 outer x 1 inner x 30 SOR, %s initial flow (BASELINE config %d)"
@@ -336,7 +336,8 @@ def run_mt_secondary(ctx, torch, with_cpu, reps=3):
             "ms_per_window": 1e3 * t_win, "windows_per_sec": 1.0 / t_win, "reps": reps, "levels": stats.levels,
             "outer_iterations_executed": stats.outer_iterations, "sor_calls": stats.sor_calls,
             "graphcut_calls": stats.graphcut_calls, "ms_per_outer_iteration": 1e3 * t_win / max(1, stats.outer_iterations),
-            "split_ms": {"upload_and_pyramid": stats.setup_ms, "occlusion_labelling": stats.graphcut_ms,
+            "split_ms": {"upload_and_pyramid": stats.setup_ms, "occlusion_labelling_device": prof.graphcut_ms,
+                         "occlusion_labelling_host": stats.graphcut_ms,
                          "sor_kernels": prof.sor_ms, "data_term_kernels": prof.data_ms,
                          "other": max(0.0, stats.total_ms - host_ms - prof.sor_ms - prof.data_ms), "total_in_library": stats.total_ms},
             "kernel_launches": int(prof.kernel_launches),

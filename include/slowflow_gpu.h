@@ -179,7 +179,7 @@ typedef struct sfgpu_mt_stats_s {
     int graphcut_calls;    /* optimizeOcc invocations */
     /* host wall-clock split of the call (milliseconds) */
     double setup_ms;       /* workspace, uploads, pyramid (until the coarsest level starts) */
-    double graphcut_ms;    /* optimizeOcc: data costs + labelling, all calls */
+    double graphcut_ms;    /* optimizeOcc, host wall clock of all calls (device labelling: the time to queue it) */
     double total_ms;
     long long pixel_outer_iterations; /* sum over the executed outer iterations of width*height of their level */
 } sfgpu_mt_stats_t;
@@ -211,6 +211,11 @@ int sfgpu_raw_weighting(sfgpu_ctx *ctx, color_image_t *weights, int red_x, int r
  * d0/d1 per site and Potts weight alpha) as the exact binary min-cut the GPU path uses.  Host-only operator twin for
  * tests: costs are dense w*h arrays, labels[p] in {0, 1}; int_terms selects gco's stock integer EnergyTermType. */
 int sfgpu_grid_mincut(int w, int h, const float *d0, const float *d1, float alpha, int int_terms, int *labels);
+/* The same labelling by the DEVICE solver the multi-frame path uses (sf_mincut.cu: layered push scheme on exact
+ * distances inside one cooperative kernel).  The canonical labelling is unique, so labels equal sfgpu_grid_mincut's.
+ * stats (nullable): {phases, grid-wide passes}. */
+int sfgpu_grid_mincut_dev(sfgpu_ctx *ctx, int w, int h, const float *d0, const float *d1, float alpha, int int_terms,
+                          int *labels, int stats[2]);
 
 /* ---- per-kernel timing (CUDA events on the context's stream) for bench.py's roofline ---- */
 typedef struct sfgpu_profile_s {
@@ -222,6 +227,7 @@ typedef struct sfgpu_profile_s {
     long long data_launches;
     long long data_pixels;
     long long kernel_launches; /* every kernel launched by this context since reset */
+    double graphcut_ms;   /* occlusion labelling on the device: data costs + min-cut kernel (multi-frame path) */
 } sfgpu_profile_t;
 int sfgpu_profile_enable(sfgpu_ctx *ctx, int on);   /* on=1 brackets SOR / data-term launches with events */
 int sfgpu_profile_reset(sfgpu_ctx *ctx);

@@ -24,7 +24,7 @@ def library_path():
 class Profile(C.Structure):
     _fields_ = [("sor_ms", C.c_double), ("sor_launches", C.c_longlong), ("sor_calls", C.c_longlong),
                 ("sor_pixel_sweeps", C.c_longlong), ("data_ms", C.c_double), ("data_launches", C.c_longlong),
-                ("data_pixels", C.c_longlong), ("kernel_launches", C.c_longlong)]
+                ("data_pixels", C.c_longlong), ("kernel_launches", C.c_longlong), ("graphcut_ms", C.c_double)]
 
 
 class FrameInt(C.Structure):
@@ -48,7 +48,7 @@ ABI_SYMBOLS = [
     "sfgpu_host_unregister", "sfgpu_variational_mt", "sfgpu_normalize", "sfgpu_get_mt_stats", "sfgpu_profile_enable",
     "sfgpu_profile_reset", "sfgpu_profile_get", "sfgpu_image_warp", "sfgpu_compute_dpsis_weight",
     "sfgpu_compute_smoothness", "sfgpu_compute_data_and_match", "sfgpu_prep_two_frame", "sfgpu_sub_laplacian", "sfgpu_sor_coupled",
-    "sfgpu_version", "sfgpu_grid_mincut", "sfgpu_prescale_size", "sfgpu_prescale", "sfgpu_raw_weighting",
+    "sfgpu_version", "sfgpu_grid_mincut", "sfgpu_grid_mincut_dev", "sfgpu_prescale_size", "sfgpu_prescale", "sfgpu_raw_weighting",
     "sfgpu_write_flo", "sfgpu_read_flo_size", "sfgpu_read_flo", "sfgpu_write_occlusion_pbm", "sfgpu_set_device", "sfgpu_get_device",
     "sfgpu_convolve_horiz", "sfgpu_convolve_vert", "sfgpu_color_image_convolve_hv", "sfgpu_get_derivatives",
 ]
@@ -117,6 +117,7 @@ def load_library(path=None):
     lib.sfgpu_color_image_convolve_hv.argtypes = [C.c_void_p, CP, CP, C.c_int, FP, C.c_int, FP]
     lib.sfgpu_get_derivatives.argtypes = [C.c_void_p] + [CP] * 10
     lib.sfgpu_grid_mincut.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_int, C.POINTER(C.c_int)]
+    lib.sfgpu_grid_mincut_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, FP, FP, C.c_float, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     if path is None:
         _LIB = lib
     return lib

@@ -32,7 +32,7 @@ Penalty make_penalty(int type, float eps, float trunc) {
 using namespace sf;
 
 // ------------------------------------------------------------------------------------------ context
-enum { PROF_SOR = 0, PROF_DATA = 1 };
+enum { PROF_SOR = 0, PROF_DATA = 1, PROF_CUT = 2 };
 
 int sfgpu_ctx::ensure_workspace(Geom geom) {
     if (geom.W < 5 || geom.H < 5) {
@@ -105,6 +105,7 @@ int sfgpu_ctx::prof_collect() {
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
             if (p.kind == PROF_SOR) prof_acc.sor_ms += ms;
+            else if (p.kind == PROF_CUT) prof_acc.graphcut_ms += ms;
             else prof_acc.data_ms += ms;
         }
         ev_free.push_back(p.a);
@@ -316,6 +317,7 @@ int sfgpu_create(int device, void *stream, sfgpu_ctx **out) {
     c->device = device;
     if (const char *e = getenv("SLOWFLOW_GPU_DATA_VARIANT")) c->data_variant = atoi(e); // A/B switch for benchmarking
     if (const char *e = getenv("SLOWFLOW_GPU_STAGED_COPIES")) c->staged_host_copies = atoi(e) != 0;
+    if (const char *e = getenv("SLOWFLOW_GPU_HOST_MINCUT")) c->host_mincut = atoi(e) != 0;
     c->num_sms = prop.multiProcessorCount;
     if (stream) {
         c->stream = (cudaStream_t)stream;
@@ -339,6 +341,7 @@ void sfgpu_destroy(sfgpu_ctx *c) {
     for (auto e : c->ev_free) cudaEventDestroy(e);
     if (c->mtw) sf::mt_work_free(c->mtw);
     if (c->stager) sf::host_stager_free(c->stager);
+    if (c->cut) sf::device_cut_free(c->cut);
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
     for (auto &ring : c->seq_ev)

@@ -7,6 +7,8 @@
 namespace sf {
 struct MtWork; // multi-frame workspace (sf_mt.cu), kept between calls
 void mt_work_free(MtWork *w);
+struct DeviceCut; // device-side grid min-cut workspace (sf_mincut.cu)
+void device_cut_free(DeviceCut *d);
 struct HostStager; // pinned bounce buffers for pageable caller memory (sf_hostcopy.cu)
 void host_stager_free(HostStager *h);
 struct HostCopy {
@@ -58,6 +60,8 @@ struct sfgpu_ctx {
     sfgpu_mt_stats_t mt_stats{};
     sf::MtWork *mtw = nullptr;
     sf::HostStager *stager = nullptr;
+    sf::DeviceCut *cut = nullptr;
+    bool host_mincut = false; // env SLOWFLOW_GPU_HOST_MINCUT=1: occlusion labelling on the host (sf_gridcut.hpp), A/B only
     bool staged_host_copies = true; // env SLOWFLOW_GPU_STAGED_COPIES=0 switches the multi-threaded staging off
 
     // helpers
@@ -78,6 +82,10 @@ int run_two_frame(sfgpu_ctx *c, Geom g, float *d_wx, float *d_wy, const float *d
 // argument check shared by the host-buffer entries: one geometry, stride = ceil4(width), planar contiguous colour
 bool check_pair(const image_t *wx, const image_t *wy, const color_image_t *im1, const color_image_t *im2);
 bool is_pageable(const void *p);
+// exact binary Potts min-cut on the device (sf_mincut.cu); results in occ / device_cut_labels(), status after a stream sync
+int device_grid_mincut(sfgpu_ctx *c, DeviceCut *&cut, int W, int H, long long *tr_dev, long long pair_cap, float *occ, int S);
+const int *device_cut_status(const DeviceCut *cut);       // {0 = converged, phases, grid-wide passes}
+const unsigned char *device_cut_labels(const DeviceCut *cut); // dense W*H labels (device memory)
 // one sor_coupled call on the context's SOR arena (profiled)
 int run_sor(sfgpu_ctx *c, int iterations, float omega, int *cur, bool zero_init);
 } // namespace sf

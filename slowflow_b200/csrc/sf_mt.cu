@@ -384,6 +384,7 @@ struct LevelCtx {
     std::vector<float *> warped;  // per frame (warped[ref] == frames[ref])
     std::vector<float *> masks;   // per frame (masks[ref] unused)
     float *wx, *wy, *uu, *vv, *odu, *odv, *dpsis, *occ, *d0, *d1;
+    bool cut_pending = false;     // a device min-cut was queued: its status must be read when the stream is next synchronised
     const float *chw;             // channel weights (level-0 planes; Q14: not rescaled per level)
     size_t chw_pstride;
     MtWork *work;
@@ -435,19 +436,32 @@ static int optimize_occ(LevelCtx &L) { // variational_aux_mt.cpp:758-887
     long long *tr_dev = reinterpret_cast<long long *>(L.d0);
     MtWork &wk = *L.work;
     const size_t N = (size_t)g.W * g.H;
+    cudaEvent_t ev;
+    L.c->prof_begin(2, ev);
     k_occ_costs<<<grid2d(g.W, g.H), dim3(32, 8), 0, L.c->stream>>>(g, a, nullptr, nullptr, tr_dev, int_terms ? 1 : 0);
     L.c->prof_acc.kernel_launches++;
-    SF_CUDA(cudaMemcpyAsync(wk.tr_host, tr_dev, N * sizeof(long long), cudaMemcpyDeviceToHost, L.c->stream));
-    SF_CUDA(cudaStreamSynchronize(L.c->stream));
-    // binary Potts labelling = one min-cut (gco stand-in semantics; int EnergyTermType optional)
-    const double t_flow = now_ms();
-    wk.cut.solve(g.W, g.H, reinterpret_cast<SinkForestCut::cap_t *>(wk.tr_host), occ_quantise_host((double)L.p->occlusion_alpha, int_terms));
-    if (getenv("SLOWFLOW_GPU_TRACE"))
-        fprintf(stderr, "optimize_occ %dx%d: costs+d2h %.2f ms, min-cut %.2f ms\n", g.W, g.H, t_flow - t_begin, now_ms() - t_flow);
-    SF_CUDA(cudaMemcpyAsync(wk.lab_dev, wk.cut.in_forest(), N, cudaMemcpyHostToDevice, L.c->stream));
-    k_occ_labels<<<grid2d(g.S, g.H), dim3(32, 8), 0, L.c->stream>>>(g, wk.lab_dev, (unsigned char)SinkForestCut::P_NONE, L.occ);
-    L.c->prof_acc.kernel_launches++;
-    SF_CUDA(cudaStreamSynchronize(L.c->stream)); // the forest bytes are read by the copy above
+    const SinkForestCut::cap_t pair_cap = occ_quantise_host((double)L.p->occlusion_alpha, int_terms);
+    if (!L.c->host_mincut) {
+        // binary Potts labelling = one min-cut (gco stand-in semantics), on the device: the terminal capacities never
+        // leave HBM and nothing synchronises; the solver's status is checked when the level ends
+        const int rcc = device_grid_mincut(L.c, L.c->cut, g.W, g.H, tr_dev, (long long)pair_cap, L.occ, g.S);
+        if (rcc != SFGPU_OK) return rcc;
+        L.c->prof_acc.kernel_launches++;
+        L.c->prof_end(2, ev);
+        L.cut_pending = true;
+    } else {
+        SF_CUDA(cudaMemcpyAsync(wk.tr_host, tr_dev, N * sizeof(long long), cudaMemcpyDeviceToHost, L.c->stream));
+        SF_CUDA(cudaStreamSynchronize(L.c->stream));
+        const double t_flow = now_ms();
+        wk.cut.solve(g.W, g.H, reinterpret_cast<SinkForestCut::cap_t *>(wk.tr_host), pair_cap);
+        if (getenv("SLOWFLOW_GPU_TRACE"))
+            fprintf(stderr, "optimize_occ %dx%d: costs+d2h %.2f ms, min-cut %.2f ms\n", g.W, g.H, t_flow - t_begin, now_ms() - t_flow);
+        SF_CUDA(cudaMemcpyAsync(wk.lab_dev, wk.cut.in_forest(), N, cudaMemcpyHostToDevice, L.c->stream));
+        k_occ_labels<<<grid2d(g.S, g.H), dim3(32, 8), 0, L.c->stream>>>(g, wk.lab_dev, (unsigned char)SinkForestCut::P_NONE, L.occ);
+        L.c->prof_acc.kernel_launches++;
+        L.c->prof_end(2, ev);
+        SF_CUDA(cudaStreamSynchronize(L.c->stream)); // the forest bytes are read by the copy above
+    }
     L.c->mt_stats.graphcut_calls++;
     L.c->mt_stats.graphcut_ms += now_ms() - t_begin;
     return SFGPU_OK;
@@ -569,6 +583,10 @@ static int compute_one_level(LevelCtx &L, float avg_change[2]) { // variational_
         c->sor.g.skip = nullptr;
         SF_CUDA(cudaMemcpyAsync(L.work->loop_host, state, sizeof(MtLoopState), cudaMemcpyDeviceToHost, st));
         SF_CUDA(cudaStreamSynchronize(st));
+        if (L.cut_pending && (device_cut_status(c->cut)[0] != 0 || device_cut_status(c->cut)[3] != 0)) {
+            set_error("occlusion min-cut did not converge on the device (set SLOWFLOW_GPU_HOST_MINCUT=1 to use the host solver)");
+            return SFGPU_ERR_CUDA;
+        }
         const int done = L.work->loop_host->outer_done;
         c->mt_stats.outer_iterations += done;
         c->mt_stats.pixel_outer_iterations += (long long)done * g.W * g.H;
@@ -675,6 +693,13 @@ static int compute_one_level(LevelCtx &L, float avg_change[2]) { // variational_
             if (std::max(avg_change[0], avg_change[1]) < p->thres_outer) break; // :436-437
         }
     }
+    if (L.cut_pending) {
+        SF_CUDA(cudaStreamSynchronize(st));
+        if (device_cut_status(c->cut)[0] != 0 || device_cut_status(c->cut)[3] != 0) {
+            set_error("occlusion min-cut did not converge on the device (set SLOWFLOW_GPU_HOST_MINCUT=1 to use the host solver)");
+            return SFGPU_ERR_CUDA;
+        }
+    }
     SF_CUDA(cudaGetLastError());
     return SFGPU_OK;
 }
@@ -713,6 +738,37 @@ int sfgpu_grid_mincut(int w, int h, const float *d0, const float *d1, float alph
     SinkForestCut cut;
     cut.solve(w, h, tr.data(), occ_quantise_host((double)alpha, int_terms != 0));
     for (size_t p = 0; p < n; p++) labels[p] = cut.label((int)p);
+    return SFGPU_OK;
+}
+
+int sfgpu_grid_mincut_dev(sfgpu_ctx *c, int w, int h, const float *d0, const float *d1, float alpha, int int_terms, int *labels,
+                          int stats[2]) {
+    if (!c || w <= 0 || h <= 0 || !d0 || !d1 || !labels) {
+        set_error("sfgpu_grid_mincut_dev: bad argument");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    const size_t n = (size_t)w * h;
+    std::vector<long long> tr(n);
+    for (size_t p = 0; p < n; p++) tr[p] = occ_quantise_host((double)d1[p], int_terms != 0) - occ_quantise_host((double)d0[p], int_terms != 0);
+    long long *tr_dev = nullptr;
+    SF_CUDA(cudaMalloc(&tr_dev, n * sizeof(long long)));
+    std::vector<unsigned char> lab(n);
+    int rc = SFGPU_OK;
+    if (!cuda_ok(cudaMemcpyAsync(tr_dev, tr.data(), n * sizeof(long long), cudaMemcpyHostToDevice, c->stream), "h2d")) rc = SFGPU_ERR_CUDA;
+    if (rc == SFGPU_OK) rc = device_grid_mincut(c, c->cut, w, h, tr_dev, (long long)occ_quantise_host((double)alpha, int_terms != 0), nullptr, 0);
+    if (rc == SFGPU_OK && !cuda_ok(cudaMemcpyAsync(lab.data(), device_cut_labels(c->cut), n, cudaMemcpyDeviceToHost, c->stream), "d2h")) rc = SFGPU_ERR_CUDA;
+    if (rc == SFGPU_OK && !cuda_ok(cudaStreamSynchronize(c->stream), "min-cut")) rc = SFGPU_ERR_CUDA;
+    cudaFree(tr_dev);
+    if (rc != SFGPU_OK) return rc;
+    const int *st = device_cut_status(c->cut);
+    if (stats) { stats[0] = st[1]; stats[1] = st[2]; }
+    if (st[0] != 0) {
+        set_error("sfgpu_grid_mincut_dev: the solver hit its pass bound");
+        return SFGPU_ERR_CUDA;
+    }
+    for (size_t p = 0; p < n; p++) labels[p] = lab[p];
+    c->prof_acc.kernel_launches++;
     return SFGPU_OK;
 }
 

@@ -97,3 +97,87 @@ def test_reused_cut_object_equals_fresh_ones(tmp_path):
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(root, "tests", "cpp_mincut_reuse.cpp")])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout + r.stderr
+
+
+# ------------------------------------------------------------------ the DEVICE solver (sf_mincut.cu) -- needs a GPU
+def device_cut(ctx, w, h, d0, d1, alpha, int_terms=0):
+    lab = np.full(w * h, -7, np.int32)
+    stats = (C.c_int * 2)()
+    rc = ctx.lib.sfgpu_grid_mincut_dev(ctx.h, w, h, d0.ctypes.data_as(FP), d1.ctypes.data_as(FP), C.c_float(alpha), int_terms,
+                                       lab.ctypes.data_as(IP), stats)
+    assert rc == 0, ctx.lib.sfgpu_last_error().decode()
+    return lab, (stats[0], stats[1])
+
+
+def _costs(w, h, seed, kind):
+    r = np.random.RandomState(seed)
+    n = w * h
+    if kind == "uniform":
+        d0, d1, alpha = r.rand(n), r.rand(n), 0.3 * r.rand()
+    elif kind == "ties":
+        d0, d1, alpha = r.randint(0, 3, n) * 0.25, r.randint(0, 3, n) * 0.25, 0.25
+    elif kind == "no_pairwise":
+        d0, d1, alpha = r.rand(n), r.rand(n), 0.0
+    elif kind == "all_sink":  # every pixel prefers label 1: the whole image is excess, nothing can be absorbed
+        d0, d1, alpha = 0.5 + r.rand(n), 0.1 * r.rand(n), 0.2
+    elif kind == "wide_band":  # a 60-px wide occluded band: long residual paths (many relaxation sweeps)
+        d0, d1, alpha = 0.002 * r.rand(n), 0.1 + 0.002 * r.rand(n), 0.1
+        xx = np.mgrid[0:h, 0:w][1].ravel()
+        d0[(xx > w // 2 - 30) & (xx < w // 2 + 30)] += 0.103 + 0.01 * r.rand(int(((xx > w // 2 - 30) & (xx < w // 2 + 30)).sum()))
+    else:
+        d0 = 0.002 * r.rand(n)
+        d1 = 0.1 + 0.002 * r.rand(n)
+        yy, xx = np.mgrid[0:h, 0:w]
+        for _ in range(6 if kind == "occlusion" else 25):
+            cx, cy, rad = r.randint(0, w), r.randint(0, h), r.randint(2, max(3, min(w, h) // 5))
+            m = ((xx - cx) ** 2 + (yy - cy) ** 2 <= rad * rad).ravel()
+            d0[m] += r.rand() * (0.6 if kind == "occlusion" else 0.25)
+        alpha = 0.1
+    return d0.astype(np.float32), d1.astype(np.float32), float(alpha)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,seed,kind", [
+    (37, 23, 1, "uniform"), (64, 48, 2, "uniform"), (131, 77, 3, "occlusion"), (200, 150, 4, "occlusion"),
+    (97, 61, 5, "ties"), (1, 40, 6, "uniform"), (40, 1, 7, "uniform"), (160, 120, 8, "blobs"), (90, 70, 9, "no_pairwise"),
+    (120, 80, 10, "all_sink"), (400, 96, 11, "wide_band"), (1280, 1024, 12, "occlusion"), (1280, 1024, 13, "blobs"),
+    (2560, 1440, 14, "blobs"),
+])
+def test_device_mincut_labels_equal_host_solver(ctx, w, h, seed, kind):
+    """The cooperative-kernel solver the multi-frame path runs (no D2H of capacities, no host cut) labels every pixel
+    like the host SinkForestCut -- which test_mincut_matches_oracle_labels pins to the oracle's Boykov-Kolmogorov."""
+    d0, d1, alpha = _costs(w, h, seed, kind)
+    host = product_cut(w, h, d0, d1, alpha)
+    dev, (phases, passes) = device_cut(ctx, w, h, d0, d1, alpha)
+    print("%dx%d %s: %d phases, %d grid-wide passes, %d pixels labelled 1" % (w, h, kind, phases, passes, int(dev.sum())))
+    assert np.array_equal(host, dev), "labels differ at %d of %d pixels" % (int((host != dev).sum()), w * h)
+
+
+@pytest.mark.gpu
+def test_device_mincut_brute_force_and_int_terms(ctx):
+    r = np.random.RandomState(5)
+    w, h = 4, 3
+    for _ in range(40):
+        d0, d1 = r.rand(w * h).astype(np.float32), r.rand(w * h).astype(np.float32)
+        a = float(np.float32(r.rand() * 0.5))
+        assert np.array_equal(device_cut(ctx, w, h, d0, d1, a)[0], product_cut(w, h, d0, d1, a))
+    assert not device_cut(ctx, w, h, d0, d1, a, int_terms=1)[0].any()
+
+
+@pytest.mark.gpu
+def test_mt_device_cut_equals_host_cut_path(monkeypatch):
+    """The whole multi-frame solve with the occlusion labelling on the device (default) and on the host
+    (SLOWFLOW_GPU_HOST_MINCUT=1): identical labels, identical flow."""
+    import mt_helpers as mh
+    from slowflow_b200 import Context
+    ims, wx, wy = mh.window(320, 200, 3)
+    p = mh.params(3, niter_alter=3, niter_outer=3, robust_color=4, robust_color_eps=0.5)
+    with Context(0) as dev_ctx:
+        a = mh.run_gpu(dev_ctx, ims, wx, wy, p)
+    monkeypatch.setenv("SLOWFLOW_GPU_HOST_MINCUT", "1")
+    with Context(0) as host_ctx:
+        b = mh.run_gpu(host_ctx, ims, wx, wy, p)
+    assert a["stats"].graphcut_calls == 2 and b["stats"].graphcut_calls == 2
+    assert np.array_equal(a["occ"].array, b["occ"].array)
+    assert np.array_equal(a["wx"].array, b["wx"].array) and np.array_equal(a["wy"].array, b["wy"].array)
+    assert (a["occ"].array == 1).any() and (a["occ"].array == -1).any()
