@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=24,
                     help="frame pairs per rank and step (default 24: 10 steps = the 240 pairs of config 5)")
+    ap.add_argument("--total-pairs", type=int, default=0,
+                    help="strong-scaling variant (config 5 as one job): this many consecutive pairs of ONE sequence per step, "
+                         "split over the ranks in contiguous ranges (slowflow_b200.shard.shard_range); overrides --pairs")
     ap.add_argument("--width", type=int, default=W_FULL)
     ap.add_argument("--height", type=int, default=H_FULL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -409,7 +412,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from slowflow_b200 import ColorImage, Context, Image, synth, variational, variational_params_default
-    from slowflow_b200.shard import max_over_ranks, sum_over_ranks
+    from slowflow_b200.shard import max_over_ranks, shard_range, sum_over_ranks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -427,6 +430,14 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     W, H, B = args.width, args.height, args.pairs
+    first_frame, scaling = 0, "weak"
+    if args.total_pairs > 0:
+        # strong scaling: one sequence, rank r refines the contiguous pair range shard_range gives it (a frame shared by
+        # two pairs of the same rank is uploaded once; the frame at a range boundary is uploaded by both neighbours)
+        lo, hi = shard_range(args.total_pairs, rank, world)
+        first_frame, B, scaling = lo, hi - lo, "strong"
+        if B < 1:
+            raise SystemExit("bench.py: --total-pairs must be at least the number of ranks")
     S = ((W + 3) // 4) * 4
     P = S * H
     params = variational_params_default()
@@ -434,7 +445,7 @@ def run_ours(args):
     # ---- synthetic window of B+1 consecutive frames (rank-specific texture seed) + initial flow.  The frames are 8-bit
     # images (the analytic texture rounded to integers, like the camera frames adaptiveFR.cpp:450-464 loads); they exist
     # twice in pinned host memory: packed interleaved u8 (H, W, 3) and as the planar fp32 images mat2colorImg makes of them
-    seed = 20170721 + 1000 * rank
+    seed = 20170721 + (1000 * rank if scaling == "weak" else 0)
     host_frames = [torch.empty(3 * P, dtype=torch.float32).pin_memory() for _ in range(B + 1)]
     host_u8 = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(B + 1)]
     frames = []
@@ -442,7 +453,7 @@ def run_ours(args):
         ci = ColorImage(W, H, buffer=host_frames[t].numpy())
         # the analytic texture of slowflow_b200.synth evaluated with torch on the device (set-up only: 2 s per
         # frame with numpy), then parked in pinned HOST memory -- the timed e2e region uploads it again
-        f = torch.clamp(torch.round(_synth_frame_torch(torch, synth, W, H, t, seed)), 0, 255)
+        f = torch.clamp(torch.round(_synth_frame_torch(torch, synth, W, H, first_frame + t, seed)), 0, 255)
         ci.array[:] = f.cpu().numpy()
         host_u8[t].copy_(f.permute(1, 2, 0).to(torch.uint8).cpu())
         frames.append(ci)
@@ -450,7 +461,7 @@ def run_ours(args):
     if rank == 0:
         yy, xx = np.mgrid[0:8, 0:W].astype(np.float64)
         gu, gv = synth.gt_flow(W, H)
-        chk = synth.texture(xx - gu[:8], yy - gv[:8], seed).astype(np.float32)
+        chk = synth.texture(xx - (first_frame + 1) * gu[:8], yy - (first_frame + 1) * gv[:8], seed).astype(np.float32)
         if not np.allclose(frames[1].array[:, :8, :], np.clip(np.rint(chk), 0, 255), atol=1.001):
             raise SystemExit("bench.py: device-generated synthetic frame differs from slowflow_b200.synth")
     u0, v0 = synth.initial_flow(W, H)
@@ -603,8 +614,8 @@ def run_ours(args):
     line = {
         "metric": "refined_flow_fields_per_sec_2560x1440", "value": value, "unit": "fields/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD % (W, H), "fields_per_step": B * world,
+        "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD % (W, H), "fields_per_step": sum_over_ranks(B),
                    "pairs_per_gpu_per_step": B, "parallelism": "independent consecutive frame pairs per GPU (config 5 sharding), no collective",
                    "host_affinity": affinity,
                    "l2": "per-pair working set %.0f MB > 126 MB L2 (no flush needed)" % (26 * P * 4 / 1e6),

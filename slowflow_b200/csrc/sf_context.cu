@@ -318,6 +318,7 @@ int sfgpu_create(int device, void *stream, sfgpu_ctx **out) {
     if (const char *e = getenv("SLOWFLOW_GPU_DATA_VARIANT")) c->data_variant = atoi(e); // A/B switch for benchmarking
     if (const char *e = getenv("SLOWFLOW_GPU_STAGED_COPIES")) c->staged_host_copies = atoi(e) != 0;
     if (const char *e = getenv("SLOWFLOW_GPU_HOST_MINCUT")) c->host_mincut = atoi(e) != 0;
+    if (const char *e = getenv("SLOWFLOW_GPU_MT_DATA_VARIANT")) c->mt_data_variant = atoi(e);
     c->num_sms = prop.multiProcessorCount;
     if (stream) {
         c->stream = (cudaStream_t)stream;

@@ -335,7 +335,12 @@ __global__ void __launch_bounds__(256) k_data_term(Geom g, DataTermDesc t, DataC
         if (i >= g.S || j >= g.H) continue;
         const size_t o = (size_t)j * g.S + i;
         if (i >= g.W) { // padding columns: defined zeros (the reference leaves garbage there)
-            cm.a11[o] = 0.0f; cm.a12[o] = 0.0f; cm.a22[o] = 0.0f; cm.b1[o] = 0.0f; cm.b2[o] = 0.0f;
+            if (KIND == DK_DERIVS) {
+#pragma unroll
+                for (int k = 0; k < 15; k++) cm.a11[(size_t)k * P + o] = 0.0f;
+            } else {
+                cm.a11[o] = 0.0f; cm.a12[o] = 0.0f; cm.a22[o] = 0.0f; cm.b1[o] = 0.0f; cm.b2[o] = 0.0f;
+            }
             continue;
         }
         Derivs d;
@@ -358,6 +363,17 @@ __global__ void __launch_bounds__(256) k_data_term(Geom g, DataTermDesc t, DataC
                 d.iyy[c] = vconv5(piy[-2 * DT_TW], piy[-DT_TW], piy[0], piy[DT_TW], piy[2 * DT_TW], j, g.H);
                 d.iyz[c] = vconv5(pz[-2 * DT_MW], pz[-DT_MW], pz[0], pz[DT_MW], pz[2 * DT_MW], j, g.H);
             }
+        }
+        if (KIND == DK_DERIVS) { // per-frame derivative planes [Ix Iy Ixx Ixy Iyy][channel] at cm.a11 (A == B: m is the frame)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                cm.a11[(size_t)(0 + c) * P + o] = d.ix[c];
+                cm.a11[(size_t)(3 + c) * P + o] = d.iy[c];
+                cm.a11[(size_t)(6 + c) * P + o] = d.ixx[c];
+                cm.a11[(size_t)(9 + c) * P + o] = d.ixy[c];
+                cm.a11[(size_t)(12 + c) * P + o] = d.iyy[c];
+            }
+            continue;
         }
         const float u = cm.du ? cm.du[o] : 0.0f, v = cm.dv ? cm.dv[o] : 0.0f;
         float m = t.mask[o];
@@ -417,11 +433,92 @@ __global__ void __launch_bounds__(256) k_data_term(Geom g, DataTermDesc t, DataC
     }
 }
 
+// ---- all multi-frame terms of one outer / inner iteration in one pointwise pass (see sf_internal.cuh)
+__global__ void __launch_bounds__(256) k_mt_terms(Geom g, MtTermsArgs ta, DataCommon cm) {
+    pdl_enter();
+    if (g.cancelled()) return;
+    const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
+    if (i >= g.S || j >= g.H) return;
+    const size_t P = g.plane(), o = (size_t)j * g.S + i;
+    if (i >= g.W) {
+        cm.a11[o] = 0.0f; cm.a12[o] = 0.0f; cm.a22[o] = 0.0f; cm.b1[o] = 0.0f; cm.b2[o] = 0.0f;
+        return;
+    }
+    const int W1 = g.W - 1, H1 = g.H - 1;
+    const float u = cm.du ? cm.du[o] : 0.0f, v = cm.dv ? cm.dv[o] : 0.0f;
+    float wc[3] = {1.0f, 1.0f, 1.0f};
+    if (cm.chw) {
+        wc[0] = cm.chw[o]; wc[1] = cm.chw[o + cm.chw_pstride]; wc[2] = cm.chw[o + 2 * cm.chw_pstride];
+    }
+    const float oc = cm.occ ? cm.occ[o] : 0.0f;
+    Acc acc;
+    acc.a11 = acc.a12 = acc.a22 = acc.b1 = acc.b2 = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < ta.nterms; k++) {
+        const MtTerm t = ta.term[k];
+        const float *IA = ta.I[t.fa] + o, *IB = ta.I[t.fb] + o, *DA = ta.D[t.fa] + o, *DB = ta.D[t.fb] + o;
+        Derivs d;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            // the reference forms m = (A + B)/2 and z = A - B first and differentiates those (variational_mt.cpp:118-161);
+            // the filters are linear, so the same values (up to rounding) come from the frames' own derivatives
+            d.iz[c] = __ldg(IA + c * P) - __ldg(IB + c * P);
+            const float xa = __ldg(DA + (0 + c) * P), xb = __ldg(DB + (0 + c) * P);
+            const float ya = __ldg(DA + (3 + c) * P), yb = __ldg(DB + (3 + c) * P);
+            d.ix[c] = 0.5f * (xb + xa);
+            d.iy[c] = 0.5f * (yb + ya);
+            d.ixz[c] = xa - xb;
+            d.iyz[c] = ya - yb;
+            d.ixx[c] = 0.5f * (__ldg(DB + (6 + c) * P) + __ldg(DA + (6 + c) * P));
+            d.ixy[c] = 0.5f * (__ldg(DB + (9 + c) * P) + __ldg(DA + (9 + c) * P));
+            d.iyy[c] = 0.5f * (__ldg(DB + (12 + c) * P) + __ldg(DA + (12 + c) * P));
+        }
+        float m = __ldg(ta.mask[t.mask_frame] + o);
+        if (cm.occ) { // occlusion / window factor of variational_mt.cpp:293-320, applied on the fly to the raw mask
+            const float fac = (1.0f + ((oc == 0.0f) ? 1.0f : 0.0f)) * cm.data_norm;
+            const float sel = (t.dir == 0) ? ((oc >= 0.0f) ? 1.0f : 0.0f) : ((oc <= 0.0f) ? 1.0f : 0.0f);
+            m = (1.0f * (sel / fac)) * m;
+        }
+        if (t.kind == DK_MT_SUCC) term_mt_succ(d, u, v, m, t.wd, t.wg, t.s, wc, cm.dt_norm, cm.pc, cm.pg, acc);
+        else term_mt_ref(d, u, v, m, t.wd, t.wg, t.s, wc, cm.dt_norm, cm.pc, cm.pg, acc);
+    }
+    {
+        // b += div(psi grad w) and the 2x2 block inverse, as in k_data_term's fuse_system (variational_aux.c:158-179,
+        // solver.c:101-106)
+        const float hl = (i > 0) ? cm.ph[o - 1] : 0.0f, hr = cm.ph[o];
+        const float vt = (j > 0) ? cm.pv[o - g.S] : 0.0f, vb = cm.pv[o];
+        const size_t ol = (i > 0) ? o - 1 : o, orr = (i < W1) ? o + 1 : o;
+        const size_t ot = (j > 0) ? o - g.S : o, ob = (j < H1) ? o + g.S : o;
+        {
+            const float wcn = cm.lap_u[o];
+            acc.b1 -= hl * (wcn - cm.lap_u[ol]);
+            acc.b1 += hr * (cm.lap_u[orr] - wcn);
+            acc.b1 -= vt * (wcn - cm.lap_u[ot]);
+            acc.b1 += vb * (cm.lap_u[ob] - wcn);
+        }
+        {
+            const float wcn = cm.lap_v[o];
+            acc.b2 -= hl * (wcn - cm.lap_v[ol]);
+            acc.b2 += hr * (cm.lap_v[orr] - wcn);
+            acc.b2 -= vt * (wcn - cm.lap_v[ot]);
+            acc.b2 += vb * (cm.lap_v[ob] - wcn);
+        }
+        const float sp = ((hl + hr) + vt) + vb;
+        const float D11 = acc.a22 + sp, D22 = acc.a11 + sp;
+        const float det = D11 * D22 - acc.a12 * acc.a12;
+        acc.a11 = D11 / det;
+        acc.a22 = D22 / det;
+        acc.a12 = acc.a12 / -det;
+    }
+    cm.a11[o] = acc.a11; cm.a12[o] = acc.a12; cm.a22[o] = acc.a22; cm.b1[o] = acc.b1; cm.b2[o] = acc.b2;
+}
+
 bool data_term_device_init() { // per device, called by sfgpu_create
     const int smem = (int)(DT_SMEM_FLOATS * sizeof(float));
     return cudaFuncSetAttribute(k_data_term<DK_TWO_FRAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
            cudaFuncSetAttribute(k_data_term<DK_MT_SUCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
-           cudaFuncSetAttribute(k_data_term<DK_MT_REF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+           cudaFuncSetAttribute(k_data_term<DK_MT_REF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+           cudaFuncSetAttribute(k_data_term<DK_DERIVS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
 }
 
 void launch_data_term(cudaStream_t st, Geom g, const DataTermDesc &t, const DataCommon &cm) {
@@ -432,6 +529,19 @@ void launch_data_term(cudaStream_t st, Geom g, const DataTermDesc &t, const Data
     case DK_MT_REF: launch_pdl(k_data_term<DK_MT_REF>, grid, b, smem, st, g, t, cm); break;
     default: launch_pdl(k_data_term<DK_TWO_FRAME>, grid, b, smem, st, g, t, cm); break;
     }
+}
+
+void launch_frame_derivs(cudaStream_t st, Geom g, const float *image3, float *derivs15) {
+    dim3 b(32, 8), grid((g.S + DT_TW - 1) / DT_TW, (g.H + DT_TH - 1) / DT_TH);
+    DataTermDesc t{image3, image3, +1, nullptr, DK_DERIVS, 0.0f, 0.0f, 1.0f, -1};
+    DataCommon cm{};
+    cm.a11 = derivs15;
+    launch_pdl(k_data_term<DK_DERIVS>, grid, b, DT_SMEM_FLOATS * sizeof(float), st, g, t, cm);
+}
+
+void launch_mt_terms(cudaStream_t st, Geom g, const MtTermsArgs &ta, const DataCommon &cm) {
+    dim3 b(32, 8), grid((g.S + 31) / 32, (g.H + 7) / 8);
+    launch_pdl(k_mt_terms, grid, b, 0, st, g, ta, cm);
 }
 
 } // namespace sf

@@ -91,7 +91,7 @@ void launch_update_smoothness(cudaStream_t st, Geom g, const float *wx, const fl
                               float *ph, float *pv);
 // K2: derivatives + robust data term of ONE term, fused (sf_data.cu).  A term pairs two colour images:
 //   m = 0.5*(B + A) (spatial derivatives are taken on it), z = zsign>0 ? B - A : A - B (temporal difference).
-enum DataKind { DK_TWO_FRAME = 0, DK_MT_SUCC = 1, DK_MT_REF = 2 };
+enum DataKind { DK_TWO_FRAME = 0, DK_MT_SUCC = 1, DK_MT_REF = 2, DK_DERIVS = 3 };
 struct DataTermDesc {
     const float *A, *B; // 3-plane images
     int zsign;
@@ -117,6 +117,32 @@ struct DataCommon {
     float *a11, *a12, *a22, *b1, *b2;
 };
 void launch_data_term(cudaStream_t st, Geom g, const DataTermDesc &t, const DataCommon &cm);
+
+// Multi-frame data pass in two kernels (sf_data.cu), replacing one launch_data_term per term:
+//   launch_frame_derivs: the five spatial derivative images Ix Iy Ixx Ixy Iyy of ONE (warped) frame, 15 planes
+//                        [derivative][channel], computed once per frame and outer iteration (the reference frame: once
+//                        per level) with the filters and border rules of get_derivatives (variational_mt.cpp:87-166);
+//   launch_mt_terms:     every term of variational_mt.cpp:343-361 in one pointwise pass.  A term's derivatives are linear
+//                        in its two frames -- m = (A + B)/2, z = A - B -- so they are formed from the per-frame planes:
+//                        Ix = (Ix_A + Ix_B)/2, Ixz = Ix_A - Ix_B, ...; A,b are accumulated in registers and the Laplacian
+//                        and block inverse of fuse_system close the pass.
+constexpr int MT_MAX_FRAMES = 2 * SF_MT_MAX_REF + 1, MT_MAX_TERMS = 4 * SF_MT_MAX_REF;
+struct MtTerm {
+    int fa, fb;        // frame indices of A and B (z = A - B)
+    int mask_frame;    // frame whose warp mask gates the term
+    int kind;          // DK_MT_SUCC / DK_MT_REF
+    int dir;           // occlusion handling: 0 past term, 1 future term
+    float wd, wg, s;
+};
+struct MtTermsArgs {
+    int nterms;
+    MtTerm term[MT_MAX_TERMS];
+    const float *I[MT_MAX_FRAMES];    // warped frames (3 planes); the reference frame unwarped
+    const float *D[MT_MAX_FRAMES];    // their derivative planes (15)
+    const float *mask[MT_MAX_FRAMES]; // warp masks
+};
+void launch_frame_derivs(cudaStream_t st, Geom g, const float *image3, float *derivs15);
+void launch_mt_terms(cudaStream_t st, Geom g, const MtTermsArgs &ta, const DataCommon &cm);
 // K1+K2 fused, marching form (sf_prep.cu): warp + derivatives + two-frame data term + Laplacian + block inverse.
 // Writes the same five planes as launch_warp + launch_data_term(fuse_system) without the warped image in HBM.
 void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im1, const float *im2, const float *wx, const float *wy, const float *du, const float *dv, const float *ph, const float *pv,

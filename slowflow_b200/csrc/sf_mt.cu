@@ -383,6 +383,8 @@ struct LevelCtx {
     std::vector<float *> frames;  // level frames
     std::vector<float *> warped;  // per frame (warped[ref] == frames[ref])
     std::vector<float *> masks;   // per frame (masks[ref] unused)
+    std::vector<float *> derivs;  // per frame: 15 derivative planes (fused_terms)
+    bool fused_terms = false;     // data pass = per-frame derivatives + one pointwise all-terms kernel (sf_data.cu)
     float *wx, *wy, *uu, *vv, *odu, *odv, *dpsis, *occ, *d0, *d1;
     bool cut_pending = false;     // a device min-cut was queued: its status must be read when the stream is next synchronised
     const float *chw;             // channel weights (level-0 planes; Q14: not rescaled per level)
@@ -406,6 +408,13 @@ static void warp_all(LevelCtx &L) { // Variational_MT::get_derivatives, warping 
         if (f == L.ref) continue;
         launch_warp(L.c->stream, L.g, L.frames[f], L.wx, L.wy, f - L.ref, L.warped[f], L.masks[f]);
         L.c->prof_acc.kernel_launches++;
+        if (L.fused_terms) { // the frame's own derivative images; every term that uses the frame combines them linearly
+            cudaEvent_t ev;
+            L.c->prof_begin(1, ev);
+            launch_frame_derivs(L.c->stream, L.g, L.warped[f], L.derivs[f]);
+            L.c->prof_end(1, ev);
+            L.c->prof_acc.kernel_launches++;
+        }
     }
 }
 
@@ -490,7 +499,20 @@ static int compute_one_level(LevelCtx &L, float avg_change[2]) { // variational_
         else if (q < ref) { Aimg = L.warped[q]; Bimg = L.frames[ref]; }
         else { Aimg = L.frames[ref]; Bimg = L.warped[q + 1]; }
     };
+    MtTermsArgs ta;
+    memset(&ta, 0, sizeof(ta));
     auto add_term = [&](int q, int kind, float w, float time, int dir) {
+        if (ta.nterms < MT_MAX_TERMS) {
+            MtTerm &m = ta.term[ta.nterms++];
+            m.fa = (kind == DK_MT_SUCC || q < ref) ? q : ref;
+            m.fb = (kind == DK_MT_SUCC) ? q + 1 : (q < ref ? ref : q + 1);
+            m.mask_frame = q < ref ? q : q + 1;
+            m.kind = kind;
+            m.dir = dir;
+            m.wd = w * L.delta_over3;
+            m.wg = w * L.gamma_over3;
+            m.s = time;
+        }
         DataTermDesc t;
         pair_imgs(q, kind, t.A, t.B);
         t.zsign = -1; // Iz = im1 - im2 (variational_mt.cpp:127,152)
@@ -511,6 +533,28 @@ static int compute_one_level(LevelCtx &L, float avg_change[2]) { // variational_
         if (p->omega[s] > 0) add_term(ref + s, DK_MT_REF, p->omega[s], (float)(s + 1), 1);
     }
 
+    if (L.fused_terms) {
+        for (int f = 0; f < 2 * ref + 1; f++) { ta.I[f] = L.warped[f]; ta.D[f] = L.derivs[f]; ta.mask[f] = L.masks[f]; }
+        launch_frame_derivs(st, g, L.frames[ref], L.derivs[ref]); // the reference frame is never warped: once per level
+        c->prof_acc.kernel_launches++;
+    }
+    auto launch_terms = [&](const Geom &gk, DataCommon &cm) { // all data terms of one linearisation (:343-361)
+        if (L.fused_terms) {
+            launch_mt_terms(st, gk, ta, cm);
+            c->prof_acc.kernel_launches++;
+            c->prof_acc.data_launches++;
+            c->prof_acc.data_pixels += (long long)g.W * g.H;
+            return;
+        }
+        for (size_t k = 0; k < terms.size(); k++) {
+            cm.accumulate = (k > 0);
+            cm.fuse_system = (k + 1 == terms.size());
+            launch_data_term(st, gk, terms[k], cm);
+            c->prof_acc.kernel_launches++;
+            c->prof_acc.data_launches++;
+            c->prof_acc.data_pixels += (long long)g.W * g.H;
+        }
+    };
     const dim3 ugrid((g.W + 31) / 32, std::min((g.H + 7) / 8, 64));
     avg_change[0] = avg_change[1] = 0.f;
     const double inv_n = 1.0 / ((double)g.H * g.W);
@@ -562,14 +606,7 @@ static int compute_one_level(LevelCtx &L, float avg_change[2]) { // variational_
                     launch_invert_blocks(st, gs, cm.a11, cm.a12, cm.a22, cm.ph, cm.pv);
                     c->prof_acc.kernel_launches += 4;
                 }
-                for (size_t k = 0; k < terms.size(); k++) {
-                    cm.accumulate = (k > 0);
-                    cm.fuse_system = (k + 1 == terms.size());
-                    launch_data_term(st, gs, terms[k], cm);
-                    c->prof_acc.kernel_launches++;
-                    c->prof_acc.data_launches++;
-                    c->prof_acc.data_pixels += (long long)g.W * g.H;
-                }
+                if (!terms.empty()) launch_terms(gs, cm);
                 c->prof_end(1, ev);
                 int rc = run_sor(c, p->niter_solver, p->sor_omega, &cur, true); // :368
                 if (rc != SFGPU_OK) { c->sor.g.skip = nullptr; return rc; }
@@ -645,14 +682,7 @@ static int compute_one_level(LevelCtx &L, float avg_change[2]) { // variational_
                     launch_invert_blocks(st, g, cm.a11, cm.a12, cm.a22, cm.ph, cm.pv);
                     c->prof_acc.kernel_launches += 4;
                 }
-                for (size_t k = 0; k < terms.size(); k++) {
-                    cm.accumulate = (k > 0);
-                    cm.fuse_system = (k + 1 == terms.size());
-                    launch_data_term(st, g, terms[k], cm);
-                    c->prof_acc.kernel_launches++;
-                    c->prof_acc.data_launches++;
-                    c->prof_acc.data_pixels += (long long)g.W * g.H;
-                }
+                if (!terms.empty()) launch_terms(g, cm);
                 c->prof_end(1, ev);
                 int rc = run_sor(c, p->niter_solver, p->sor_omega, &cur, first); // :368
                 if (rc != SFGPU_OK) return rc;
@@ -984,7 +1014,8 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
     size_t frame_floats = 0;
     for (int l = 0; l < L; l++) frame_floats += (size_t)F * 3 * geoms[l].plane();
     const size_t work_planes = (size_t)(F - 1) * 3 + (F - 1) + 2 /*wx wy*/ + 2 /*wx,wy of next level*/ + 2 /*uu vv*/ + 2 /*odu odv*/ + 1 /*dpsis*/ +
-                               1 /*occ*/ + 2 /*d0 d1*/ + 3 /*blur tmp*/ + (channel_w ? 3 : 0);
+                               1 /*occ*/ + 2 /*d0 d1*/ + 3 /*blur tmp*/ + (channel_w ? 3 : 0) +
+                               (c->mt_data_variant == 0 ? (size_t)F * 15 /*per-frame derivative planes*/ : 0);
     if (!c->mtw) c->mtw = new MtWork();
     MtWork &work = *c->mtw;
     {
@@ -1005,6 +1036,9 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
     float *uu = take(1), *vv = take(1), *odu = take(1), *odv = take(1), *dpsis = take(1), *occ = take(1), *d0 = take(1), *d1 = take(1);
     float *blur_tmp = take(3);
     float *chw = channel_w ? take(3) : nullptr;
+    std::vector<float *> derivs(F, nullptr);
+    if (c->mt_data_variant == 0)
+        for (int f = 0; f < F; f++) derivs[f] = take(15);
 
     // ---- upload
     {
@@ -1076,6 +1110,8 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
         Lc.warped = warped;
         Lc.warped[ref] = levels[l].frames[ref];
         Lc.masks = masks;
+        Lc.derivs = derivs;
+        Lc.fused_terms = c->mt_data_variant == 0;
         Lc.wx = cur_x; Lc.wy = cur_y; Lc.uu = uu; Lc.vv = vv; Lc.odu = odu; Lc.odv = odv;
         Lc.dpsis = dpsis; Lc.occ = occ; Lc.d0 = d0; Lc.d1 = d1;
         Lc.chw = chw; Lc.chw_pstride = P0;

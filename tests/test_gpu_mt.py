@@ -218,3 +218,21 @@ def test_mt_config4_2560x1440_three_layers_bounded(ctx, mt_checker):
     g = mh.run_gpu(ctx, ims, wx, wy, p)
     assert g["stats"].levels == 3
     check(g, r, "config 4 (bounded)")
+
+
+def test_mt_data_pass_variants_agree(monkeypatch):
+    """The default multi-frame data pass (per-frame derivative planes + one pointwise all-terms kernel) against the
+    one-fused-kernel-per-term variant (SLOWFLOW_GPU_MT_DATA_VARIANT=1): the two differ only in where the linear
+    combination of the two frames of a term is taken (before or after the derivative filters), i.e. in rounding."""
+    from slowflow_b200 import Context
+    ims, wx, wy = mh.window(300, 190, 3)
+    p = mh.params(3, niter_alter=2, niter_outer=3, robust_color=4, robust_color_eps=0.5)
+    with Context(0) as c0:
+        a = mh.run_gpu(c0, ims, wx, wy, p)
+    monkeypatch.setenv("SLOWFLOW_GPU_MT_DATA_VARIANT", "1")
+    with Context(0) as c1:
+        b = mh.run_gpu(c1, ims, wx, wy, p)
+    mean, mx = epe(a["wx"].array, a["wy"].array, b["wx"].array, b["wy"].array, border=0)
+    print("fused vs per-term data pass: mean %.3e max %.3e" % (mean, mx))
+    assert mean <= 1e-4 and mx <= 1e-2
+    assert float((a["occ"].array != b["occ"].array).mean()) <= 0.002
