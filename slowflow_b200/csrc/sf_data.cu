@@ -30,6 +30,14 @@ constexpr int DT_XW = DT_TW + 4;           // Ix columns (x-2 .. x+2)
 constexpr int DT_XH = DT_TH + 4;           // Ix / Iy rows (y-2 .. y+2)
 constexpr size_t DT_SMEM_FLOATS = 3 * (2 * DT_MH * DT_MW + DT_XH * DT_XW + DT_XH * DT_TW);
 
+// 1/x: MUFU.RCP (1 ulp) + one Newton step (~0.5 ulp); the reference divides (divps).  4 instructions instead of the ~10 of
+// an IEEE-rounded reciprocal -- the term arithmetic, not the stencils, is the bulk of the multi-frame data pass.
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+
 struct Derivs {
     float ix[3], iy[3], iz[3], ixx[3], ixy[3], iyy[3], ixz[3], iyz[3];
 };
@@ -46,7 +54,7 @@ __device__ __forceinline__ void term_two_frame(const Derivs &d, float u, float v
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             r[c] = d.iz[c] + d.ix[c] * u + d.iy[c] * v;
-            inv[c] = __frcp_rn(d.ix[c] * d.ix[c] + d.iy[c] * d.iy[c] + dnorm);
+            inv[c] = fast_rcp(d.ix[c] * d.ix[c] + d.iy[c] * d.iy[c] + dnorm);
         }
         const float t = m * hd * rsqrtf(r[0] * r[0] * inv[0] + r[1] * r[1] * inv[1] + r[2] * r[2] * inv[2] + eps_color);
 #pragma unroll
@@ -62,8 +70,8 @@ __device__ __forceinline__ void term_two_frame(const Derivs &d, float u, float v
     float rx[3], ry[3], ivx[3], ivy[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        ivx[c] = __frcp_rn(d.ixx[c] * d.ixx[c] + d.ixy[c] * d.ixy[c] + dnorm);
-        ivy[c] = __frcp_rn(d.iyy[c] * d.iyy[c] + d.ixy[c] * d.ixy[c] + dnorm);
+        ivx[c] = fast_rcp(d.ixx[c] * d.ixx[c] + d.ixy[c] * d.ixy[c] + dnorm);
+        ivy[c] = fast_rcp(d.iyy[c] * d.iyy[c] + d.ixy[c] * d.ixy[c] + dnorm);
         rx[c] = d.ixz[c] + d.ixx[c] * u + d.ixy[c] * v;
         ry[c] = d.iyz[c] + d.ixy[c] * u + d.iyy[c] * v;
     }
@@ -108,7 +116,7 @@ __device__ __forceinline__ void term_mt_succ(const Derivs &d, float u, float v, 
         } else {
             float inv[3];
 #pragma unroll
-            for (int c = 0; c < 3; c++) inv[c] = __frcp_rn(gx[c] * gx[c] + gy[c] * gy[c] + dnorm);
+            for (int c = 0; c < 3; c++) inv[c] = fast_rcp(gx[c] * gx[c] + gy[c] * gy[c] + dnorm);
             const float t = m * wd * penalty_deriv_v(pc, r[0] * r[0] * inv[0] + r[1] * r[1] * inv[1] + r[2] * r[2] * inv[2]);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
@@ -146,8 +154,8 @@ __device__ __forceinline__ void term_mt_succ(const Derivs &d, float u, float v, 
         float ivx[3], ivy[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            ivx[c] = __frcp_rn(gxx[c] * gxx[c] + gxy[c] * gxy[c] + dnorm);
-            ivy[c] = __frcp_rn(gyy[c] * gyy[c] + gxy[c] * gxy[c] + dnorm);
+            ivx[c] = fast_rcp(gxx[c] * gxx[c] + gxy[c] * gxy[c] + dnorm);
+            ivy[c] = fast_rcp(gyy[c] * gyy[c] + gxy[c] * gxy[c] + dnorm);
         }
         const float t = m * wg * penalty_deriv_v(pg, rx[0] * rx[0] * ivx[0] + ry[0] * ry[0] * ivy[0] + rx[1] * rx[1] * ivx[1] +
                                                          ry[1] * ry[1] * ivy[1] + rx[2] * rx[2] * ivx[2] + ry[2] * ry[2] * ivy[2]);
@@ -191,7 +199,7 @@ __device__ __forceinline__ void term_mt_ref(const Derivs &d, float u, float v, f
         } else {
             float inv[3];
 #pragma unroll
-            for (int c = 0; c < 3; c++) inv[c] = __frcp_rn(fsq * d.ix[c] * d.ix[c] + fsq * d.iy[c] * d.iy[c] + dnorm);
+            for (int c = 0; c < 3; c++) inv[c] = fast_rcp(fsq * d.ix[c] * d.ix[c] + fsq * d.iy[c] * d.iy[c] + dnorm);
             const float t = m * wd * penalty_deriv_v(pc, r[0] * r[0] * inv[0] + r[1] * r[1] * inv[1] + r[2] * r[2] * inv[2]);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
@@ -230,8 +238,8 @@ __device__ __forceinline__ void term_mt_ref(const Derivs &d, float u, float v, f
         float ivx[3], ivy[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            ivx[c] = __frcp_rn(fsq * d.ixx[c] * d.ixx[c] + fsq * d.ixy[c] * d.ixy[c] + dnorm);
-            ivy[c] = __frcp_rn(fsq * d.iyy[c] * d.iyy[c] + fsq * d.ixy[c] * d.ixy[c] + dnorm);
+            ivx[c] = fast_rcp(fsq * d.ixx[c] * d.ixx[c] + fsq * d.ixy[c] * d.ixy[c] + dnorm);
+            ivy[c] = fast_rcp(fsq * d.iyy[c] * d.iyy[c] + fsq * d.ixy[c] * d.ixy[c] + dnorm);
         }
         const float t = m * wg * penalty_deriv_v(pg, rx[0] * rx[0] * ivx[0] + ry[0] * ry[0] * ivy[0] + rx[1] * rx[1] * ivx[1] +
                                                          ry[1] * ry[1] * ivy[1] + rx[2] * rx[2] * ivx[2] + ry[2] * ry[2] * ivy[2]);

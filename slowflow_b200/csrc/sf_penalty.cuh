@@ -11,21 +11,32 @@
 
 namespace sf {
 
-// psi'(s^2), v4sf overloads (fp32)
+// psi'(s^2), v4sf overloads (fp32).  Quotients go through MUFU.RCP / MUFU.RSQ plus one Newton step (within 1 ulp of the
+// reference's divps / sqrtps chain) instead of IEEE division sequences: this sits in the innermost per-term arithmetic.
+__device__ __forceinline__ float penalty_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+__device__ __forceinline__ float penalty_half_rsqrt(float x) { // 1 / (2 sqrt(x)), x > 0
+    const float r = rsqrtf(x);
+    const float h = 0.5f * r;
+    return fmaf(0.5f * h, fmaf(-x * r, r, 1.0f), h); // one Newton step on rsqrt, r' = r + r/2 (1 - x r^2), halved
+}
 __device__ __forceinline__ float penalty_deriv_v(const Penalty &p, float xsq) {
     switch (p.type) {
     case SF_ROBUST_QUADRATIC: return 1.0f;
-    case SF_ROBUST_LORENTZIAN: return 1.0f / (2.0f * p.eps_sq_f + xsq);
+    case SF_ROBUST_LORENTZIAN: return penalty_rcp(2.0f * p.eps_sq_f + xsq);
     case SF_ROBUST_GEMAN_MCCLURE: {
         float t = p.eps_sq_f + xsq;
         t = t * t;
-        return (p.eps_sq_f + 2.0f * xsq) / t;
+        return (p.eps_sq_f + 2.0f * xsq) * penalty_rcp(t);
     }
     case SF_ROBUST_TRUNC_MODL1: {
         if (sqrtf(xsq) > p.trunc) return 0.0f;
-        return 1.0f / (2.0f * sqrtf(xsq + p.eps_sq_f));
+        return penalty_half_rsqrt(xsq + p.eps_sq_f);
     }
-    default: return 1.0f / (2.0f * sqrtf(xsq + p.eps_sq_f)); // ModifiedL1Norm
+    default: return penalty_half_rsqrt(xsq + p.eps_sq_f); // ModifiedL1Norm
     }
 }
 
