@@ -281,6 +281,42 @@ int sfgpu_get_derivatives(sfgpu_ctx *ctx, const color_image_t *im1, const color_
                           color_image_t *dy, color_image_t *dt, color_image_t *dxx, color_image_t *dxy, color_image_t *dyy,
                           color_image_t *dxt, color_image_t *dyt);
 
+/* ---- EPIC sparse-to-dense interpolation: the step that produces the flow variational() refines.
+ * Types are those of epic_flow_extended/epic.h:5-14 and array_types.h:70-77; if the reference headers were included first
+ * (array_types.h defines ___ARRAY_TYPES_H___; define SLOWFLOW_GPU_HAVE_EPIC_H after including the guard-less epic.h) their
+ * definitions are used. */
+#ifndef ___ARRAY_TYPES_H___
+typedef struct { float *pixels; int tx, ty; } float_image; /* row-major tx columns x ty rows */
+#endif
+#ifndef SLOWFLOW_GPU_HAVE_EPIC_H
+typedef struct epic_params_s {
+    char method[20];     /* "LA" locally-weighted affine or "NW" Nadaraya-Watson */
+    float saliency_th;   /* matches from pixels with a saliency below this are removed (0: off) */
+    int pref_nn;         /* neighbours of the consistency filter (0: off) */
+    float pref_th;       /* its threshold, pixels */
+    int nn;              /* neighbours of the interpolation */
+    float coef_kernel;   /* kernel exp(-coef * geodesic distance) */
+    float euc;           /* constant added to the edge cost */
+    int verbose;
+} epic_params_t;
+/* replaces epic.cpp:131-140 */
+void epic_params_default(epic_params_t *params);
+#endif
+typedef struct sfgpu_epic_stats_s {
+    int matches_in, matches_after_saliency, matches_after_consistency;
+    int sweeps_prefilter, sweeps_interpolation; /* distance-transform sweeps executed (epic_aux.cpp:170-178) */
+} sfgpu_epic_stats_t;
+/* replaces epic() (epic.cpp:147-234; callers epicflow.cpp:125, adaptiveFR.cpp:568, slow_flow.cpp:819,979,
+ * dense_tracking.cpp:1294).  flowx, flowy: output planes (host); im: first image in Lab (only the saliency filter reads
+ * it); input_matches: ty rows of tx >= 4 floats x1 y1 x2 y2; edges: width x height costs, and like in the reference
+ * params->euc is ADDED TO THE CALLER'S ARRAY.  stats may be NULL.  The reference's n_thread argument has no meaning here. */
+int sfgpu_epic(sfgpu_ctx *ctx, image_t *flowx, image_t *flowy, const color_image_t *im, const float_image *input_matches,
+               float_image *edges, const epic_params_t *params, sfgpu_epic_stats_t *stats);
+/* operator twin of dist_trf_nnfield_subset (epic_aux.cpp:350-401) with the seeds as the query points: the label map
+ * (w*h), and per seed the nn nearest seeds over the geodesic neighbourhood graph with their distances */
+int sfgpu_epic_nnfield(sfgpu_ctx *ctx, int *best, float *dist, int *labels, const int *seeds, int ns, int nn,
+                       const float *cost, int w, int h, int *sweeps);
+
 /* library / build identification, e.g. "slowflow_gpu 0.1 sm_100a" */
 const char *sfgpu_version(void);
 

@@ -33,6 +33,22 @@ class FrameInt(C.Structure):
                 ("data", C.c_void_p)]
 
 
+class EpicParams(C.Structure):
+    """epic_params_t (epic_flow_extended/epic.h:5-14)."""
+    _fields_ = [("method", C.c_char * 20), ("saliency_th", C.c_float), ("pref_nn", C.c_int), ("pref_th", C.c_float),
+                ("nn", C.c_int), ("coef_kernel", C.c_float), ("euc", C.c_float), ("verbose", C.c_int)]
+
+
+class FloatImage(C.Structure):
+    """float_image (array_types.h:70-77): row-major tx columns x ty rows."""
+    _fields_ = [("pixels", C.POINTER(C.c_float)), ("tx", C.c_int), ("ty", C.c_int)]
+
+
+class EpicStats(C.Structure):
+    _fields_ = [("matches_in", C.c_int), ("matches_after_saliency", C.c_int), ("matches_after_consistency", C.c_int),
+                ("sweeps_prefilter", C.c_int), ("sweeps_interpolation", C.c_int)]
+
+
 class MTStats(C.Structure):
     _fields_ = [("levels", C.c_int), ("outer_iterations", C.c_int), ("sor_calls", C.c_int),
                 ("graphcut_calls", C.c_int), ("setup_ms", C.c_double), ("graphcut_ms", C.c_double),
@@ -48,7 +64,7 @@ ABI_SYMBOLS = [
     "sfgpu_host_unregister", "sfgpu_variational_mt", "sfgpu_normalize", "sfgpu_get_mt_stats", "sfgpu_profile_enable",
     "sfgpu_profile_reset", "sfgpu_profile_get", "sfgpu_image_warp", "sfgpu_compute_dpsis_weight",
     "sfgpu_compute_smoothness", "sfgpu_compute_data_and_match", "sfgpu_prep_two_frame", "sfgpu_sub_laplacian", "sfgpu_sor_coupled",
-    "sfgpu_version", "sfgpu_grid_mincut", "sfgpu_grid_mincut_dev", "sfgpu_prescale_size", "sfgpu_prescale", "sfgpu_raw_weighting",
+    "sfgpu_epic", "sfgpu_epic_nnfield", "epic_params_default", "sfgpu_version", "sfgpu_grid_mincut", "sfgpu_grid_mincut_dev", "sfgpu_prescale_size", "sfgpu_prescale", "sfgpu_raw_weighting",
     "sfgpu_write_flo", "sfgpu_read_flo_size", "sfgpu_read_flo", "sfgpu_write_occlusion_pbm", "sfgpu_set_device", "sfgpu_get_device",
     "sfgpu_convolve_horiz", "sfgpu_convolve_vert", "sfgpu_color_image_convolve_hv", "sfgpu_get_derivatives",
 ]
@@ -116,11 +132,23 @@ def load_library(path=None):
     lib.sfgpu_convolve_vert.argtypes = [C.c_void_p, IP, IP, C.c_int, FP]
     lib.sfgpu_color_image_convolve_hv.argtypes = [C.c_void_p, CP, CP, C.c_int, FP, C.c_int, FP]
     lib.sfgpu_get_derivatives.argtypes = [C.c_void_p] + [CP] * 10
+    lib.epic_params_default.argtypes = [C.POINTER(EpicParams)]
+    lib.epic_params_default.restype = None
+    lib.sfgpu_epic.argtypes = [C.c_void_p, IP, IP, CP, C.POINTER(FloatImage), C.POINTER(FloatImage), C.POINTER(EpicParams),
+                               C.POINTER(EpicStats)]
+    lib.sfgpu_epic_nnfield.argtypes = [C.c_void_p, C.POINTER(C.c_int), FP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, FP,
+                                       C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.sfgpu_grid_mincut.argtypes = [C.c_int, C.c_int, FP, FP, C.c_float, C.c_int, C.POINTER(C.c_int)]
     lib.sfgpu_grid_mincut_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, FP, FP, C.c_float, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     if path is None:
         _LIB = lib
     return lib
+
+
+def epic_params_default():
+    p = EpicParams()
+    load_library().epic_params_default(C.byref(p))
+    return p
 
 
 def _check(lib, rc, what):
@@ -223,6 +251,37 @@ class Context:
         fn = self.lib.sfgpu_variational_sequence_u8 if depth == 8 else self.lib.sfgpu_variational_sequence_u16
         _check(self.lib, fn(self.h, n, fa, xa, ya, C.byref(params) if params is not None else None,
                             1 if continue_from_previous else 0), "sfgpu_variational_sequence_u%d" % depth)
+
+    # --- EPIC interpolation (epic.cpp:147)
+    def epic(self, flowx, flowy, im, matches, edges, params=None):
+        """matches: float32 array (n, >= 4) of x1 y1 x2 y2; edges: float32 (H, W) cost map, params.euc is added to it IN
+        PLACE like in the reference.  Returns the EpicStats of the call."""
+        import numpy as np
+        assert matches.dtype == np.float32 and matches.flags.c_contiguous and matches.ndim == 2
+        assert edges.dtype == np.float32 and edges.flags.c_contiguous and edges.shape == (im.height, im.width)
+        if params is None:
+            params = epic_params_default()
+        FP = C.POINTER(C.c_float)
+        m = FloatImage(matches.ctypes.data_as(FP), matches.shape[1], matches.shape[0])
+        e = FloatImage(edges.ctypes.data_as(FP), edges.shape[1], edges.shape[0])
+        st = EpicStats()
+        _check(self.lib, self.lib.sfgpu_epic(self.h, flowx.ptr(), flowy.ptr(), im.ptr(), C.byref(m), C.byref(e), C.byref(params),
+                                             C.byref(st)), "sfgpu_epic")
+        return st
+
+    def epic_nnfield(self, seeds, nn, cost):
+        """seeds: int32 (ns, 2) x y; cost: float32 (H, W).  -> (labels (H, W), best (ns, nn), dist (ns, nn), sweeps)."""
+        import numpy as np
+        h, w = cost.shape
+        ns = seeds.shape[0]
+        labels, best, dist = np.zeros((h, w), np.int32), np.zeros((ns, nn), np.int32), np.zeros((ns, nn), np.float32)
+        sweeps = C.c_int()
+        IPi, FP = C.POINTER(C.c_int), C.POINTER(C.c_float)
+        _check(self.lib, self.lib.sfgpu_epic_nnfield(self.h, best.ctypes.data_as(IPi), dist.ctypes.data_as(FP), labels.ctypes.data_as(IPi),
+                                                     np.ascontiguousarray(seeds, np.int32).ctypes.data_as(IPi), ns, nn,
+                                                     np.ascontiguousarray(cost, np.float32).ctypes.data_as(FP), w, h, C.byref(sweeps)),
+               "sfgpu_epic_nnfield")
+        return labels, best, dist, sweeps.value
 
     # --- multi-frame
     def normalize(self, seq, params):

@@ -1,0 +1,881 @@
+// sf_epic.cu -- EPIC sparse-to-dense interpolation on the device: the step that produces the initial
+// flow variational() refines (epicflow.cpp:125, adaptiveFR.cpp:568, slow_flow.cpp:819,979).  Replaces
+//   epic()                          epic_flow_extended/epic.cpp:147-234  (+ rectify / saliency / consistency filters :13-127)
+//   dist_trf_nnfield_subset()       epic_aux.cpp:350-401: geodesic distance transform with label propagation (:91-182),
+//                                   neighbourhood graph of the seeds (:186-288), k nearest seeds on that graph (:47-85)
+//   fit_nadarayawatson / fit_localaffine / apply_*   epic_aux.cpp:404-492
+//   saliency()                      image.c:728-790
+//
+// What runs where.  Everything image-sized or per-seed runs on the GPU; the host only compacts the (small) match list
+// after the two filters, in the reference's order.
+//   * Distance transform: the reference sweeps the image in raster order in four directions (Gauss-Seidel: a pixel uses
+//     the already updated left / upper neighbour of the SAME sweep).  The sweeps are reproduced exactly -- same operations,
+//     same order per pixel, no FMA contraction -- as a wavefront: 32 x 32 tiles in anti-diagonal order (tickets taken in
+//     wave-major order from an atomic counter, a tile spins on the done-flags of its two predecessors), and inside a tile
+//     one warp walks the 63 local anti-diagonals with the row state in registers and the upper neighbour by shuffle.
+//     The data-dependent number of sweeps (epic_aux.cpp:170-178) is decided on the device: all 40 sweep kernels are queued,
+//     the ones beyond end_iter return at once.
+//   * Neighbourhood graph: every label border emits (row, col, d) in both directions; radix sort by (row, col) and a
+//     segmented minimum (CUB) give the CSR matrix in the reference's order (sorted by row, then column).
+//   * k nearest seeds: one warp per seed runs the reference's Dijkstra with ITS heap discipline (libstdc++'s push_heap /
+//     pop_heap, so ties pop in the same order); heap in shared memory, tentative distances in a per-warp global array.
+//   * Locally-weighted affine fit: the reference hands a 2(nn+4) x 6 system to LAPACK's sgels; the system decouples into
+//     two weighted 3-parameter fits with one design matrix, solved here per seed by normal equations in DOUBLE with
+//     coordinates centred on the seed (parity unpinned at this call anyway: LAPACK is not part of the reference tree).
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include <string.h>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
+
+#include "sf_context.cuh"
+#include "sf_stencil.cuh"
+
+namespace sf {
+
+constexpr int DT_TILE = 32;
+constexpr int DT_PITCH = 34; // shared-memory row pitch: lane l at step s reads (l, s - l) -> bank (l + s) % 32
+constexpr int DT_MAX_SWEEPS = 40;
+constexpr unsigned EPIC_UNSEEN = 0x7F7F7F7Fu; // memset(…, 0x7F, …) pattern of the reference: 3.39e38f
+
+// ------------------------------------------------------------------------------------------ saliency (image.c:728-790)
+struct ConvTaps { int order; float c[17]; }; // c[order + k] = weight of src[i + k]
+__global__ void __launch_bounds__(256) k_conv_any(Geom g, const float *__restrict__ src, float *__restrict__ dst, ConvTaps t, int vertical,
+                                                  int planes) {
+    const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
+    if (i >= g.W || j >= g.H) return;
+    const size_t P = g.plane();
+    for (int c = 0; c < planes; c++) {
+        const float *s = src + c * P;
+        float sum = 0.0f;
+        for (int k = -t.order; k <= t.order; k++) {
+            const float v = vertical ? s[(size_t)clampi(j + k, 0, g.H - 1) * g.S + i] : s[(size_t)j * g.S + clampi(i + k, 0, g.W - 1)];
+            sum += t.c[t.order + k] * v;
+        }
+        dst[c * P + (size_t)j * g.S + i] = sum;
+    }
+}
+__global__ void __launch_bounds__(256) k_autocorr(Geom g, const float *__restrict__ ix, const float *__restrict__ iy, float *__restrict__ xx,
+                                                  float *__restrict__ xy, float *__restrict__ yy) {
+    const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
+    if (i >= g.W || j >= g.H) return;
+    const size_t P = g.plane(), o = (size_t)j * g.S + i;
+    const float a0 = ix[o], a1 = ix[o + P], a2 = ix[o + 2 * P], b0 = iy[o], b1 = iy[o + P], b2 = iy[o + 2 * P];
+    xx[o] = a0 * a0 + a1 * a1 + a2 * a2;
+    xy[o] = a0 * b0 + a1 * b1 + a2 * b2;
+    yy[o] = b0 * b0 + b1 * b1 + b2 * b2;
+}
+__global__ void __launch_bounds__(256) k_min_eig(Geom g, const float *__restrict__ xx, const float *__restrict__ xy, const float *__restrict__ yy,
+                                                 float *__restrict__ out) {
+    const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
+    if (i >= g.W || j >= g.H) return;
+    const size_t o = (size_t)j * g.S + i;
+    const float t = 0.5f * (xx[o] + yy[o]);
+    out[o] = sqrtf(fmaxf(0.0f, t - sqrtf(fmaxf(0.0f, t * t + xy[o] * xy[o] - xx[o] * yy[o]))));
+}
+static ConvTaps gaussian_taps(float sigma) { // gaussian_filter + convolution_new(even) (image.c:310-398)
+    ConvTaps t;
+    memset(&t, 0, sizeof(t));
+    int order = (int)floor(3 * sigma) + 1;
+    if (order == 0) order = 1;
+    if (order > 8) order = 8;
+    t.order = order;
+    const float alpha = 1.0f / (2.0f * sigma * sigma);
+    float sum = 0.0f;
+    for (int i = -order; i <= order; i++) {
+        t.c[order + i] = (float)exp(-i * i * alpha);
+        sum += t.c[order + i];
+    }
+    for (int i = -order; i <= order; i++) t.c[order + i] /= sum;
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------ small per-match kernels
+__global__ void k_gather_plane(int n, const int *__restrict__ seeds, Geom g, const float *__restrict__ plane, float *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = plane[(size_t)seeds[2 * k + 1] * g.S + seeds[2 * k]];
+}
+__global__ void k_fill_u32(size_t n, unsigned *__restrict__ dst, unsigned v) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) dst[k] = v;
+}
+// seeds onto the distance / label maps: dmap[p] = cost[p]; of several seeds on one pixel the LAST one wins (the reference
+// writes them in order, epic_aux.cpp:319-323)
+__global__ void k_dt_seed_labels(int ns, const int *__restrict__ seeds, int W, int *__restrict__ labels) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < ns) atomicMax(labels + (size_t)seeds[2 * k + 1] * W + seeds[2 * k], k);
+}
+__global__ void k_dt_seed_dist(int ns, const int *__restrict__ seeds, int W, const float *__restrict__ cost, float *__restrict__ dmap) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < ns) {
+        const size_t p = (size_t)seeds[2 * k + 1] * W + seeds[2 * k];
+        dmap[p] = cost[p];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ distance transform sweeps
+struct DtCtrl {
+    int end_iter;                   // sweeps with index > end_iter are skipped (epic_aux.cpp:170-178)
+    int sweeps_run;
+    unsigned maxdiff[DT_MAX_SWEEPS + 1]; // float bits of the largest decrease of sweep k (non-negative: ordered like ints)
+    int ticket[DT_MAX_SWEEPS + 1];
+};
+struct DtSweepArgs {
+    int W, H, TX, TY;
+    const float *cost;
+    float *A;
+    int *L;
+    int sx, sy;       // sweep direction (+1 / -1)
+    int k;            // sweep index, 1-based
+    DtCtrl *ctrl;
+    int *done;        // per tile: index of the last sweep that finished it
+    const int *wave_start; // TX + TY entries: first ticket of every anti-diagonal of tiles
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// one arg_sweep update (epic_aux.cpp:118-148), operation for operation, without FMA contraction
+__device__ __forceinline__ void dt_update(float t1, int l1, float t2, int l2, float C, float &a, int &l, float &maxdiff) {
+    const float dt12 = fabsf(__fsub_rn(t1, t2));
+    float t0;
+    int l0;
+    if (dt12 > C) {
+        if (t1 < t2) { t0 = __fadd_rn(t1, C); l0 = l1; }
+        else { t0 = __fadd_rn(t2, C); l0 = l2; }
+    } else {
+        const float r = sqrtf(__fsub_rn(__fmul_rn(__fmul_rn(2.0f, C), C), __fmul_rn(dt12, dt12)));
+        t0 = 0.5f * __fadd_rn(__fadd_rn(t1, t2), r);
+        l0 = (t1 < t2) ? l1 : l2;
+    }
+    if (t0 < a) {
+        maxdiff = fmaxf(maxdiff, __fsub_rn(a, t0));
+        a = t0;
+        l = l0;
+    }
+}
+
+constexpr int DT_WARPS = 2; // warps (= tiles in flight) per block: 3 x 4.25 KB of staging each
+// bounded spin on a predecessor tile's done-flag: a protocol error traps instead of hanging the GPU
+__device__ __forceinline__ void dt_wait(const int *flag, int k) {
+    unsigned spins = 0;
+    while (ld_acquire_gpu(flag) != k)
+        if (++spins > (1u << 26)) __trap();
+}
+__global__ void __launch_bounds__(DT_WARPS * 32) k_dt_sweep(DtSweepArgs a) {
+    if (a.k > *reinterpret_cast<volatile int *>(&a.ctrl->end_iter)) return;
+    __shared__ float sA[DT_WARPS][DT_TILE * DT_PITCH], sC[DT_WARPS][DT_TILE * DT_PITCH];
+    __shared__ int sL[DT_WARPS][DT_TILE * DT_PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *tA = sA[warp], *tC = sC[warp];
+    int *tL = sL[warp];
+    const int ntiles = a.TX * a.TY, nwaves = a.TX + a.TY - 1;
+    const float INF = __int_as_float(0x7f800000);
+    float maxdiff = 0.0f;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&a.ctrl->ticket[a.k], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= ntiles) break;
+        // ticket -> (wave, position) -> tile in sweep coordinates (ta, tb) -> actual tile (cx, cy)
+        int lo = 0, hi = nwaves - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (a.wave_start[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        const int wave = lo, pos = t - a.wave_start[wave];
+        const int ta = max(0, wave - a.TY + 1) + pos, tb = wave - ta;
+        const int cx = a.sx > 0 ? ta : a.TX - 1 - ta, cy = a.sy > 0 ? tb : a.TY - 1 - tb;
+        const int x0 = cx * DT_TILE, y0 = cy * DT_TILE;
+        const int tw = min(DT_TILE, a.W - x0), th = min(DT_TILE, a.H - y0);
+        // wait for the two predecessor tiles of this sweep
+        if (lane == 0) {
+            if (ta > 0) dt_wait(a.done + cy * a.TX + (cx - a.sx), a.k);
+            if (tb > 0) dt_wait(a.done + (cy - a.sy) * a.TX + cx, a.k);
+        }
+        __syncwarp();
+        // stage the tile (coalesced rows) in sweep coordinates: local (p, q) <-> pixel (x0 + (sx>0 ? p : tw-1-p), y0 + ...)
+        for (int q = 0; q < th; q++) {
+            const int j = y0 + (a.sy > 0 ? q : th - 1 - q);
+            if (lane < tw) {
+                const int i = x0 + (a.sx > 0 ? lane : tw - 1 - lane);
+                const size_t o = (size_t)j * a.W + i;
+                tA[q * DT_PITCH + lane] = __ldcg(a.A + o);
+                tL[q * DT_PITCH + lane] = __ldcg(a.L + o);
+                tC[q * DT_PITCH + lane] = __ldg(a.cost + o);
+            }
+        }
+        __syncwarp();
+        // lane = row q of the tile (sweep order); left neighbour of column 0 from the tile before in x
+        const int q = lane;
+        float left_t = INF;
+        int left_l = -1;
+        if (q < th && ta > 0) {
+            const int j = y0 + (a.sy > 0 ? q : th - 1 - q), i = (a.sx > 0) ? x0 - 1 : x0 + tw;
+            left_t = __ldcg(a.A + (size_t)j * a.W + i);
+            left_l = __ldcg(a.L + (size_t)j * a.W + i);
+        }
+        float cur_t = 0.0f;   // value this lane produced in the previous step (its column p - 1)
+        int cur_l = 0;
+        // row above the tile in sweep order (the upper neighbours of local row 0): lane p holds column p
+        float top_t = INF;
+        int top_l = -1;
+        if (tb > 0 && lane < tw) {
+            const int jup = (a.sy > 0) ? y0 - 1 : y0 + th, i = x0 + (a.sx > 0 ? lane : tw - 1 - lane);
+            top_t = __ldcg(a.A + (size_t)jup * a.W + i);
+            top_l = __ldcg(a.L + (size_t)jup * a.W + i);
+        }
+        for (int s = 0; s < tw + th - 1; s++) {
+            // the upper neighbour of (p, q) is what lane q - 1 produced in the previous step
+            float up_t = __shfl_up_sync(0xffffffffu, cur_t, 1);
+            int up_l = __shfl_up_sync(0xffffffffu, cur_l, 1);
+            const int p = s - q;
+            const float halo_t = __shfl_sync(0xffffffffu, top_t, s & 31); // local row 0 is at column p = s in this step
+            const int halo_l = __shfl_sync(0xffffffffu, top_l, s & 31);
+            if (q < th && p >= 0 && p < tw) {
+                if (q == 0) { up_t = halo_t; up_l = halo_l; }
+                const float t2 = (p == 0) ? left_t : cur_t;
+                const int l2 = (p == 0) ? left_l : cur_l;
+                float av = tA[q * DT_PITCH + p];
+                int lv = tL[q * DT_PITCH + p];
+                dt_update(up_t, up_l, t2, l2, tC[q * DT_PITCH + p], av, lv, maxdiff);
+                tA[q * DT_PITCH + p] = av;
+                tL[q * DT_PITCH + p] = lv;
+                cur_t = av;
+                cur_l = lv;
+            }
+        }
+        __syncwarp();
+        for (int qq = 0; qq < th; qq++) {
+            const int j = y0 + (a.sy > 0 ? qq : th - 1 - qq);
+            if (lane < tw) {
+                const int i = x0 + (a.sx > 0 ? lane : tw - 1 - lane);
+                const size_t o = (size_t)j * a.W + i;
+                a.A[o] = tA[qq * DT_PITCH + lane];
+                a.L[o] = tL[qq * DT_PITCH + lane];
+            }
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(a.done + cy * a.TX + cx, a.k);
+    }
+    for (int off = 16; off > 0; off >>= 1) maxdiff = fmaxf(maxdiff, __shfl_xor_sync(0xffffffffu, maxdiff, off));
+    if (lane == 0 && maxdiff > 0.0f) atomicMax(&a.ctrl->maxdiff[a.k], __float_as_uint(maxdiff));
+}
+// the loop control of weighted_distance_transform (epic_aux.cpp:170-178) after sweep k
+__global__ void k_dt_control(DtCtrl *c, int k, float min_change, int max_iter) {
+    if (k > c->end_iter) return;
+    c->sweeps_run = k;
+    if (__uint_as_float(c->maxdiff[k]) > min_change) c->end_iter = min(max_iter, k + 3);
+}
+
+// ------------------------------------------------------------------------------------------ neighbourhood graph of the seeds
+// (ngh_labels_to_spmat, epic_aux.cpp:226-288): for every pixel with i >= 1 and j >= 1 whose left / upper neighbour carries
+// another label, the edge (l0, l1) with cost dis[p] + dis[q]; emitted in both directions with key = (row << 32) | col
+__global__ void __launch_bounds__(256) k_border_emit(int W, int H, const int *__restrict__ lab, const float *__restrict__ dis,
+                                                     unsigned long long *__restrict__ keys, float *__restrict__ vals, int *__restrict__ count, int cap) {
+    const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
+    int n = 0;
+    unsigned long long k0 = 0, k1 = 0;
+    float d0 = 0.f, d1 = 0.f;
+    if (i >= 1 && j >= 1 && i < W && j < H) {
+        const size_t o = (size_t)j * W + i;
+        const int l0 = lab[o], l1 = lab[o - 1], l2 = lab[o - W];
+        if (l0 != l1 && l0 >= 0 && l1 >= 0) { k0 = ((unsigned long long)(unsigned)l0 << 32) | (unsigned)l1; d0 = dis[o] + dis[o - 1]; n = 1; }
+        if (l0 != l2 && l0 >= 0 && l2 >= 0) { k1 = ((unsigned long long)(unsigned)l0 << 32) | (unsigned)l2; d1 = dis[o] + dis[o - W]; n |= 2; }
+    }
+    const int mine = 2 * ((n & 1) + ((n >> 1) & 1));
+    // warp-aggregated append
+    int pre = mine;
+    const int lane = (threadIdx.y * 32 + threadIdx.x) & 31;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, off);
+        if (lane >= off) pre += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(count, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int at = base + pre - mine;
+    auto put = [&](unsigned long long k, float d) {
+        if (at + 1 < cap) {
+            keys[at] = k; vals[at] = d;
+            keys[at + 1] = (k << 32) | (k >> 32); vals[at + 1] = d;
+        }
+        at += 2;
+    };
+    if (n & 1) put(k0, d0);
+    if (n & 2) put(k1, d1);
+}
+__global__ void k_csr_rows(int ns, int nedges, const unsigned long long *__restrict__ keys, int *__restrict__ indptr, int *__restrict__ indices) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= ns) { // indptr[r] = first edge whose row is >= r
+        int lo = 0, hi = nedges;
+        const unsigned long long key = (unsigned long long)(unsigned)r << 32;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (keys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        indptr[r] = lo;
+    }
+    for (int e = r; e < nedges; e += ns + 1) indices[e] = (int)(keys[e] & 0xffffffffu);
+}
+
+// ------------------------------------------------------------------------------------------ k nearest seeds on the graph
+// find_nn_graph_arr (epic_aux.cpp:47-85): Dijkstra with std::priority_queue<current_t, vector, smallest_on_top>.  The heap
+// below performs exactly libstdc++'s push_heap / pop_heap moves, so entries with equal distance leave it in the same order.
+constexpr int KNN_HEAP = 2048;
+struct HeapItem { int node; float dis; };
+__device__ __forceinline__ bool heap_less(const HeapItem &x, const HeapItem &y) { return x.dis > y.dis; } // comp(a, b): a.dis > b.dis
+__device__ void heap_push(HeapItem *h, int &len, HeapItem v) {
+    int hole = len++;
+    int parent = (hole - 1) / 2;
+    while (hole > 0 && heap_less(h[parent], v)) {
+        h[hole] = h[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    h[hole] = v;
+}
+__device__ HeapItem heap_pop(HeapItem *h, int &len) { // pop_heap + pop_back
+    const HeapItem top = h[0];
+    const HeapItem v = h[len - 1];
+    len--;
+    if (len == 0) return top;
+    int hole = 0, child = 0;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (heap_less(h[child], h[child - 1])) child--;
+        h[hole] = h[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        h[hole] = h[child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > 0 && heap_less(h[parent], v)) {
+        h[hole] = h[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    h[hole] = v;
+    return top;
+}
+// one warp per seed (lane 0 runs the search, the warp restores the tentative-distance array afterwards)
+__global__ void __launch_bounds__(256) k_knn_graph(int ns, int nn, const int *__restrict__ indptr, const int *__restrict__ indices,
+                                                   const float *__restrict__ data, unsigned *__restrict__ done_all, int *__restrict__ touched_all,
+                                                   int *__restrict__ nnf, float *__restrict__ dis, int *__restrict__ overflow) {
+    extern __shared__ HeapItem heaps[];
+    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_block, nwarps = gridDim.x * (blockDim.x >> 5);
+    HeapItem *h = heaps + warp_in_block * KNN_HEAP;
+    unsigned *done = done_all + (size_t)gwarp * ns; // float bits; EPIC_UNSEEN = not reached (memset 0x7F in the reference)
+    int *touched = touched_all + (size_t)gwarp * KNN_HEAP * 2;
+    for (int seed = gwarp; seed < ns; seed += nwarps) {
+        int ntouched = 0, n = 0;
+        if (lane == 0) {
+            int len = 0;
+            heap_push(h, len, HeapItem{seed, 0.0f});
+            done[seed] = __float_as_uint(0.0f);
+            touched[ntouched++] = seed;
+            while (len > 0) {
+                const HeapItem cur = heap_pop(h, len);
+                if (cur.dis > __uint_as_float(done[cur.node])) continue;
+                nnf[(size_t)seed * nn + n] = cur.node;
+                dis[(size_t)seed * nn + n] = cur.dis;
+                n++;
+                if (n >= nn) break;
+                for (int e = indptr[cur.node]; e < indptr[cur.node + 1]; e++) {
+                    const int ngh = indices[e];
+                    const float nd = cur.dis + data[e];
+                    if (nd >= __uint_as_float(done[ngh])) continue;
+                    if (len >= KNN_HEAP || ntouched >= 2 * KNN_HEAP) { atomicExch(overflow, 1); continue; }
+                    heap_push(h, len, HeapItem{ngh, nd});
+                    if (done[ngh] == EPIC_UNSEEN) touched[ntouched++] = ngh;
+                    done[ngh] = __float_as_uint(nd);
+                }
+            }
+            for (int k = n; k < nn; k++) { // not enough results: 0xFF / 0x7F patterns like the reference's memsets
+                nnf[(size_t)seed * nn + k] = -1;
+                dis[(size_t)seed * nn + k] = __uint_as_float(EPIC_UNSEEN);
+            }
+        }
+        ntouched = __shfl_sync(0xffffffffu, ntouched, 0);
+        __syncwarp();
+        for (int k = lane; k < ntouched; k += 32) done[touched[k]] = EPIC_UNSEEN;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ per-seed fits, per-pixel apply
+// query point = seed i: neighbours of the seed that owns its pixel, distances + the pixel's own distance, then the kernel
+// exp(-coef d) + 1e-08 (dist_trf_nnfield_subset :385-394, epic.cpp:96-98, 203-205)
+__global__ void k_query_weights(int ns, int nn, const int *__restrict__ seeds, int W, const int *__restrict__ labels, const float *__restrict__ dmap,
+                                const int *__restrict__ nnf, const float *__restrict__ dis, float coef, int *__restrict__ qnn, float *__restrict__ qw) {
+    const int i = blockIdx.x, j = threadIdx.x;
+    if (i >= ns) return;
+    const size_t p = (size_t)seeds[2 * i + 1] * W + seeds[2 * i];
+    const int s = labels[p];
+    const float d = dmap[p];
+    for (int k = j; k < nn; k += blockDim.x) {
+        qnn[(size_t)i * nn + k] = nnf[(size_t)s * nn + k];
+        const float dist = d + dis[(size_t)s * nn + k];
+        qw[(size_t)i * nn + k] = (coef < 0.0f) ? dist : (float)((double)expf(-coef * dist) + 1e-08); // coef < 0: raw distances (operator twin)
+    }
+}
+// fit_nadarayawatson (epic_aux.cpp:410-428): sequential float sums in neighbour order
+__global__ void k_fit_nw(int ns, int nn, const int *__restrict__ qnn, const float *__restrict__ qw, const float *__restrict__ vects, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    float u = 0.0f, v = 0.0f, s = 0.0f;
+    for (int j = 0; j < nn; j++) {
+        const float d = qw[(size_t)i * nn + j];
+        const int jj = qnn[(size_t)i * nn + j];
+        if (jj < 0) continue;
+        u = __fadd_rn(u, __fmul_rn(d, vects[2 * jj]));
+        v = __fadd_rn(v, __fmul_rn(d, vects[2 * jj + 1]));
+        s = __fadd_rn(s, d);
+    }
+    out[2 * i] = u / s;
+    out[2 * i + 1] = v / s;
+}
+__global__ void k_prefilter_flags(int ns, const float *__restrict__ est, const float *__restrict__ vects, float th2, unsigned char *__restrict__ keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const float a = est[2 * i] - vects[2 * i], b = est[2 * i + 1] - vects[2 * i + 1];
+    keep[i] = (__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)) < th2) ? 1 : 0;
+}
+// fit_localaffine (epic_aux.cpp:438-481).  Rows of the reference's system are (x c, y c, c | (x + wx) c) and the same for y:
+// two weighted least-squares fits (weights c^2) of x' and y' over [x y 1].  Normal equations in double, centred on the seed.
+__global__ void k_fit_la(int ns, int nn, const int *__restrict__ qnn, const float *__restrict__ qw, const int *__restrict__ seeds,
+                         const float *__restrict__ vects, float *__restrict__ aff) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const double xi = seeds[2 * i], yi = seeds[2 * i + 1];
+    double sxx = 0, sxy = 0, sx = 0, syy = 0, sy = 0, s1 = 0, bx0 = 0, bx1 = 0, bx2 = 0, by0 = 0, by1 = 0, by2 = 0;
+    auto add = [&](double x, double y, double wx, double wy, float cf) {
+        // the reference forms the row entries in float: (x)*(c), (y)*(c), ((x)+(wx))*(c)
+        const double c2 = (double)cf * (double)cf;
+        const double dx = x - xi, dy = y - yi;          // centred design
+        const double tx = (x + wx) - xi, ty = (y + wy) - yi; // centred targets
+        sxx += c2 * dx * dx; sxy += c2 * dx * dy; sx += c2 * dx; syy += c2 * dy * dy; sy += c2 * dy; s1 += c2;
+        bx0 += c2 * dx * tx; bx1 += c2 * dy * tx; bx2 += c2 * tx;
+        by0 += c2 * dx * ty; by1 += c2 * dy * ty; by2 += c2 * ty;
+    };
+    float coefi = 0.0f;
+    for (int j = 0; j < nn; j++) {
+        const int s = qnn[(size_t)i * nn + j];
+        if (s < 0) continue;
+        float coef = qw[(size_t)i * nn + j];
+        if (s == i) { coefi = 0.01f * coef; coef *= 0.96f; }
+        add((double)seeds[2 * s], (double)seeds[2 * s + 1], (double)vects[2 * s], (double)vects[2 * s + 1], coef);
+    }
+    const double ui = vects[2 * i], vi = vects[2 * i + 1];
+    add((double)((float)xi + 0.1f), yi, ui, vi, coefi);
+    add(xi, (double)((float)yi + 0.1f), ui, vi, coefi);
+    add((double)((float)xi - 0.1f), yi, ui, vi, coefi);
+    add(xi, (double)((float)yi - 0.1f), ui, vi, coefi);
+    // solve the symmetric 3x3 system [sxx sxy sx; sxy syy sy; sx sy s1] p = b (cofactors)
+    const double c00 = syy * s1 - sy * sy, c01 = sx * sy - sxy * s1, c02 = sxy * sy - syy * sx;
+    const double c11 = sxx * s1 - sx * sx, c12 = sxy * sx - sxx * sy, c22 = sxx * syy - sxy * sxy;
+    const double det = sxx * c00 + sxy * c01 + sx * c02;
+    const double inv = 1.0 / det;
+    const double a0 = (c00 * bx0 + c01 * bx1 + c02 * bx2) * inv, a1 = (c01 * bx0 + c11 * bx1 + c12 * bx2) * inv,
+                 a2 = (c02 * bx0 + c12 * bx1 + c22 * bx2) * inv;
+    const double a3 = (c00 * by0 + c01 * by1 + c02 * by2) * inv, a4 = (c01 * by0 + c11 * by1 + c12 * by2) * inv,
+                 a5 = (c02 * by0 + c12 * by1 + c22 * by2) * inv;
+    // back to absolute coordinates: x' = a0 (x - xi) + a1 (y - yi) + a2 + xi
+    float *m = aff + (size_t)6 * i;
+    m[0] = (float)a0; m[1] = (float)a1; m[2] = (float)(a2 + xi - a0 * xi - a1 * yi);
+    m[3] = (float)a3; m[4] = (float)a4; m[5] = (float)(a5 + yi - a3 * xi - a4 * yi);
+}
+// apply_localaffine / apply_nadarayawatson (epic_aux.cpp:430-436, 483-492) straight into the flow planes (stride S)
+__global__ void __launch_bounds__(256) k_apply(Geom g, const int *__restrict__ labels, const float *__restrict__ model, int affine, float *__restrict__ fx,
+                                               float *__restrict__ fy) {
+    const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
+    if (i >= g.W || j >= g.H) return;
+    const int s = labels[(size_t)j * g.W + i];
+    const size_t o = (size_t)j * g.S + i;
+    if (s < 0) { fx[o] = 0.0f; fy[o] = 0.0f; return; }
+    if (affine) {
+        const float *m = model + (size_t)6 * s;
+        fx[o] = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], (float)i), __fmul_rn(m[1], (float)j)), m[2]), (float)i);
+        fy[o] = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[3], (float)i), __fmul_rn(m[4], (float)j)), m[5]), (float)j);
+    } else {
+        fx[o] = model[2 * s];
+        fy[o] = model[2 * s + 1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct DevBuf { // RAII device allocation
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+    bool alloc(size_t bytes) { return cuda_ok(cudaMalloc(&p, bytes ? bytes : 4), "cudaMalloc(epic)"); }
+};
+static dim3 grid2(int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); }
+
+struct EpicGeo {
+    int W, H, TX, TY;
+    std::vector<int> wave_start;
+};
+
+// dist_trf_nnfield_subset with the seeds as query points, followed by the kernel weights: fills qnn / qw (ns x nn) and
+// leaves the label map of the seeds in `labels`.  Everything is queued on the context's stream; returns after one sync.
+static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns, int nn, const int *d_seeds, float coef, int *d_labels,
+                    float *d_dmap, int *d_qnn, float *d_qw, int *sweeps_out) {
+    cudaStream_t st = c->stream;
+    const int W = eg.W, H = eg.H;
+    const size_t N = (size_t)W * H;
+    const int ntiles = eg.TX * eg.TY;
+    DevBuf ctrl, done, waves;
+    if (!ctrl.alloc(sizeof(DtCtrl)) || !done.alloc(ntiles * sizeof(int)) || !waves.alloc(eg.wave_start.size() * sizeof(int))) return SFGPU_ERR_CUDA;
+    SF_CUDA(cudaMemsetAsync(ctrl.p, 0, sizeof(DtCtrl), st));
+    SF_CUDA(cudaMemsetAsync(done.p, 0, ntiles * sizeof(int), st));
+    SF_CUDA(cudaMemcpyAsync(waves.p, eg.wave_start.data(), eg.wave_start.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    {
+        const int four = 4;
+        SF_CUDA(cudaMemcpyAsync(&ctrl.as<DtCtrl>()->end_iter, &four, sizeof(int), cudaMemcpyHostToDevice, st)); // end_iter = 4 (:168)
+    }
+    k_fill_u32<<<592, 256, 0, st>>>(N, reinterpret_cast<unsigned *>(d_dmap), EPIC_UNSEEN);
+    k_fill_u32<<<592, 256, 0, st>>>(N, reinterpret_cast<unsigned *>(d_labels), 0xFFFFFFFFu);
+    k_dt_seed_labels<<<(ns + 255) / 256, 256, 0, st>>>(ns, d_seeds, W, d_labels);
+    k_dt_seed_dist<<<(ns + 255) / 256, 256, 0, st>>>(ns, d_seeds, W, d_cost, d_dmap);
+    // sweeps i = 1 .. : direction (x[i % 4], y[i % 4]) with x = {-1, 1, 1, -1}, y = {1, 1, -1, -1} (:165-172)
+    static const int dx[4] = {-1, 1, 1, -1}, dy[4] = {1, 1, -1, -1};
+    int sm_blocks = 0;
+    SF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sm_blocks, k_dt_sweep, DT_WARPS * 32, 0));
+    const int grid = std::max(1, std::min((ntiles + DT_WARPS - 1) / DT_WARPS, c->num_sms * std::max(1, sm_blocks)));
+    for (int k = 1; k <= DT_MAX_SWEEPS; k++) {
+        DtSweepArgs a;
+        a.W = W; a.H = H; a.TX = eg.TX; a.TY = eg.TY;
+        a.cost = d_cost; a.A = d_dmap; a.L = d_labels;
+        a.sx = dx[k % 4]; a.sy = dy[k % 4];
+        a.k = k;
+        a.ctrl = ctrl.as<DtCtrl>();
+        a.done = done.as<int>();
+        a.wave_start = waves.as<int>();
+        k_dt_sweep<<<grid, DT_WARPS * 32, 0, st>>>(a);
+        k_dt_control<<<1, 1, 0, st>>>(ctrl.as<DtCtrl>(), k, 1.0f, DT_MAX_SWEEPS); // default dt_params: max_iter 40, min_change 1 (:151-154)
+    }
+    c->prof_acc.kernel_launches += 4 + 2 * DT_MAX_SWEEPS;
+
+    // ---- neighbourhood graph
+    const int cap = (int)std::min<size_t>(4 * N, (size_t)1 << 30);
+    DevBuf keys, vals, keys2, vals2, count, ukeys, uvals, nruns, tmp;
+    if (!keys.alloc((size_t)cap * 8) || !vals.alloc((size_t)cap * 4) || !keys2.alloc((size_t)cap * 8) || !vals2.alloc((size_t)cap * 4) ||
+        !count.alloc(8) || !nruns.alloc(8))
+        return SFGPU_ERR_CUDA;
+    SF_CUDA(cudaMemsetAsync(count.p, 0, 8, st));
+    k_border_emit<<<grid2(W, H), dim3(32, 8), 0, st>>>(W, H, d_labels, d_dmap, keys.as<unsigned long long>(), vals.as<float>(), count.as<int>(), cap);
+    int h_count = 0;
+    DtCtrl h_ctrl;
+    SF_CUDA(cudaMemcpyAsync(&h_count, count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaMemcpyAsync(&h_ctrl, ctrl.p, sizeof(DtCtrl), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaStreamSynchronize(st));
+    if (sweeps_out) *sweeps_out = h_ctrl.sweeps_run;
+    if (h_count + 1 >= cap) {
+        set_error("sfgpu_epic: label border list overflow");
+        return SFGPU_ERR_NOMEM;
+    }
+    int nedges = 0;
+    DevBuf indptr, indices;
+    if (!indptr.alloc((size_t)(ns + 1) * sizeof(int))) return SFGPU_ERR_CUDA;
+    if (h_count > 0) {
+        size_t tb1 = 0, tb2 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb1, keys.as<unsigned long long>(), keys2.as<unsigned long long>(), vals.as<float>(), vals2.as<float>(), h_count, 0, 64, st);
+        if (!ukeys.alloc((size_t)h_count * 8) || !uvals.alloc((size_t)h_count * 4)) return SFGPU_ERR_CUDA;
+        cub::DeviceReduce::ReduceByKey(nullptr, tb2, keys2.as<unsigned long long>(), ukeys.as<unsigned long long>(), vals2.as<float>(), uvals.as<float>(),
+                                       nruns.as<int>(), cub::Min(), h_count, st);
+        if (!tmp.alloc(std::max(tb1, tb2))) return SFGPU_ERR_CUDA;
+        size_t tb = std::max(tb1, tb2);
+        SF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.as<unsigned long long>(), keys2.as<unsigned long long>(), vals.as<float>(), vals2.as<float>(),
+                                                h_count, 0, 64, st));
+        tb = std::max(tb1, tb2);
+        SF_CUDA(cub::DeviceReduce::ReduceByKey(tmp.p, tb, keys2.as<unsigned long long>(), ukeys.as<unsigned long long>(), vals2.as<float>(), uvals.as<float>(),
+                                               nruns.as<int>(), cub::Min(), h_count, st));
+        SF_CUDA(cudaMemcpyAsync(&nedges, nruns.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SF_CUDA(cudaStreamSynchronize(st));
+    }
+    if (!indices.alloc((size_t)std::max(nedges, 1) * sizeof(int))) return SFGPU_ERR_CUDA;
+    k_csr_rows<<<(ns + 1 + 255) / 256, 256, 0, st>>>(ns, nedges, ukeys.as<unsigned long long>(), indptr.as<int>(), indices.as<int>());
+
+    // ---- k nearest seeds of every seed, then the query step
+    const int warps_per_block = 8;
+    int blocks = std::min((ns + warps_per_block - 1) / warps_per_block, c->num_sms);
+    // the per-warp tentative-distance arrays: ns floats per resident warp (bounded to 1 GB)
+    while (blocks > 1 && (size_t)blocks * warps_per_block * ns * 4 > ((size_t)1 << 30)) blocks /= 2;
+    DevBuf done_all, touched, nnf, dis, overflow;
+    const size_t nwarps = (size_t)blocks * warps_per_block;
+    if (!done_all.alloc(nwarps * ns * 4) || !touched.alloc(nwarps * KNN_HEAP * 2 * 4) || !nnf.alloc((size_t)ns * nn * 4) || !dis.alloc((size_t)ns * nn * 4) ||
+        !overflow.alloc(4))
+        return SFGPU_ERR_CUDA;
+    k_fill_u32<<<592, 256, 0, st>>>(nwarps * ns, done_all.as<unsigned>(), EPIC_UNSEEN);
+    SF_CUDA(cudaMemsetAsync(overflow.p, 0, 4, st));
+    const size_t smem = (size_t)warps_per_block * KNN_HEAP * sizeof(HeapItem);
+    SF_CUDA(cudaFuncSetAttribute(k_knn_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_graph<<<blocks, warps_per_block * 32, smem, st>>>(ns, nn, indptr.as<int>(), indices.as<int>(), uvals.as<float>(), done_all.as<unsigned>(),
+                                                            touched.as<int>(), nnf.as<int>(), dis.as<float>(), overflow.as<int>());
+    k_query_weights<<<ns, 128, 0, st>>>(ns, nn, d_seeds, W, d_labels, d_dmap, nnf.as<int>(), dis.as<float>(), coef, d_qnn, d_qw);
+    int h_over = 0;
+    SF_CUDA(cudaMemcpyAsync(&h_over, overflow.p, 4, cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaStreamSynchronize(st));
+    SF_CUDA(cudaGetLastError());
+    c->prof_acc.kernel_launches += 6;
+    if (h_over) {
+        set_error("sfgpu_epic: neighbour search heap overflow (a seed with more than 2048 open graph nodes)");
+        return SFGPU_ERR_NOMEM;
+    }
+    return SFGPU_OK;
+}
+
+} // namespace sf
+
+using namespace sf;
+
+extern "C" {
+
+void epic_params_default(epic_params_t *params) { // epic.cpp:131-140
+    if (!params) return;
+    strcpy(params->method, "LA");
+    params->saliency_th = 0.045f;
+    params->pref_nn = 25;
+    params->pref_th = 5.0f;
+    params->nn = 100;
+    params->coef_kernel = 0.8f;
+    params->euc = 0.001f;
+    params->verbose = 0;
+}
+
+int sfgpu_epic(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_image_t *im, const float_image *input_matches, float_image *edges,
+               const epic_params_t *params, sfgpu_epic_stats_t *stats) {
+    if (!c || !flowx || !flowy || !im || !input_matches || !edges || !params || !flowx->data || !flowy->data || !im->c1 ||
+        !input_matches->pixels || !edges->pixels) {
+        set_error("sfgpu_epic: null argument");
+        return SFGPU_ERR_ARG;
+    }
+    const int W = im->width, H = im->height;
+    if (edges->tx != W || edges->ty != H || flowx->width != W || flowx->height != H || flowy->width != W || flowy->height != H ||
+        flowx->stride != ((W + 3) / 4) * 4 || flowy->stride != flowx->stride || im->stride != flowx->stride || input_matches->tx < 4) {
+        set_error("sfgpu_epic: geometry mismatch (edges and flow planes must have the image's size; matches need >= 4 columns)");
+        return SFGPU_ERR_ARG;
+    }
+    const bool la = strcmp(params->method, "LA") == 0, nw = strcmp(params->method, "NW") == 0;
+    if (!la && !nw) {
+        set_error(std::string("sfgpu_epic: method ") + params->method + " not recognized");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const Geom g{W, H, flowx->stride};
+    const size_t N = (size_t)W * H, P = g.plane();
+    sfgpu_epic_stats_t sstat;
+    memset(&sstat, 0, sizeof(sstat));
+
+    // ---- rectify_corres (epic.cpp:13-27)
+    std::vector<float> m4((size_t)input_matches->ty * 4);
+    int nm = input_matches->ty;
+    for (int i = 0; i < nm; i++) {
+        const float *r = input_matches->pixels + (size_t)i * input_matches->tx;
+        m4[4 * i + 0] = std::max(0.0f, std::min(r[0], (float)(W - 1)));
+        m4[4 * i + 1] = std::max(0.0f, std::min(r[1], (float)(H - 1)));
+        m4[4 * i + 2] = std::max(0.0f, std::min(r[2], (float)(W - 1)));
+        m4[4 * i + 3] = std::max(0.0f, std::min(r[3], (float)(H - 1)));
+    }
+    sstat.matches_in = nm;
+    // ---- edges += euc, in the caller's array like the reference (:155-163), then to the device
+    if (params->euc)
+        for (size_t i = 0; i < N; i++) edges->pixels[i] += params->euc;
+    DevBuf d_cost, d_labels, d_dmap;
+    if (!d_cost.alloc(N * 4) || !d_labels.alloc(N * 4) || !d_dmap.alloc(N * 4)) return SFGPU_ERR_CUDA;
+    SF_CUDA(cudaMemcpyAsync(d_cost.p, edges->pixels, N * 4, cudaMemcpyHostToDevice, st));
+
+    EpicGeo eg;
+    eg.W = W; eg.H = H;
+    eg.TX = (W + DT_TILE - 1) / DT_TILE;
+    eg.TY = (H + DT_TILE - 1) / DT_TILE;
+    {
+        int acc = 0;
+        for (int w = 0; w < eg.TX + eg.TY - 1; w++) {
+            eg.wave_start.push_back(acc);
+            const int lo = std::max(0, w - eg.TY + 1), hi = std::min(w, eg.TX - 1);
+            acc += hi - lo + 1;
+        }
+        eg.wave_start.push_back(acc);
+    }
+
+    auto seeds_of = [&](std::vector<int> &seeds, std::vector<float> &vects) { // matches_to_seeds / matches_to_vects (:30-57)
+        seeds.resize((size_t)nm * 2);
+        vects.resize((size_t)nm * 2);
+        for (int i = 0; i < nm; i++) {
+            seeds[2 * i] = (int)m4[4 * i];
+            seeds[2 * i + 1] = (int)m4[4 * i + 1];
+            vects[2 * i] = m4[4 * i + 2] - m4[4 * i];
+            vects[2 * i + 1] = m4[4 * i + 3] - m4[4 * i + 1];
+        }
+    };
+    auto compact = [&](const std::vector<unsigned char> &keep) {
+        int ii = 0;
+        for (int i = 0; i < nm; i++)
+            if (keep[i]) {
+                if (ii != i) memcpy(&m4[4 * (size_t)ii], &m4[4 * (size_t)i], 4 * sizeof(float));
+                ii++;
+            }
+        nm = ii;
+    };
+
+    // ---- saliency filter (epic.cpp:60-77)
+    if (params->saliency_th) {
+        DevBuf work;
+        if (!work.alloc(16 * P * 4)) return SFGPU_ERR_CUDA;
+        float *d_im = work.as<float>(), *d_tmp = d_im + 3 * P, *d_sm = d_im + 6 * P, *d_ix = d_im + 9 * P, *d_iy = d_im + 12 * P;
+        float *d_xx = d_im + 15 * P; // xy, yy reuse d_tmp / d_sm planes below
+        SF_CUDA(cudaMemcpyAsync(d_im, im->c1, 3 * P * 4, cudaMemcpyHostToDevice, st));
+        const ConvTaps pre = gaussian_taps(0.8f), post = gaussian_taps(1.0f);
+        ConvTaps der;
+        memset(&der, 0, sizeof(der));
+        der.order = 1; der.c[0] = -0.5f; der.c[1] = 0.0f; der.c[2] = 0.5f; // convolution_new(1, {0, -0.5}, odd)
+        k_conv_any<<<grid2(W, H), dim3(32, 8), 0, st>>>(g, d_im, d_tmp, pre, 0, 3);
+        k_conv_any<<<grid2(W, H), dim3(32, 8), 0, st>>>(g, d_tmp, d_sm, pre, 1, 3);
+        k_conv_any<<<grid2(W, H), dim3(32, 8), 0, st>>>(g, d_sm, d_ix, der, 0, 3);
+        k_conv_any<<<grid2(W, H), dim3(32, 8), 0, st>>>(g, d_sm, d_iy, der, 1, 3);
+        float *d_xy = d_tmp, *d_yy = d_tmp + P, *d_t = d_tmp + 2 * P, *d_sal = d_sm;
+        k_autocorr<<<grid2(W, H), dim3(32, 8), 0, st>>>(g, d_ix, d_iy, d_xx, d_xy, d_yy);
+        float *planes[3] = {d_xx, d_xy, d_yy};
+        for (int k = 0; k < 3; k++) {
+            k_conv_any<<<grid2(W, H), dim3(32, 8), 0, st>>>(g, planes[k], d_t, post, 0, 1);
+            k_conv_any<<<grid2(W, H), dim3(32, 8), 0, st>>>(g, d_t, planes[k], post, 1, 1);
+        }
+        k_min_eig<<<grid2(W, H), dim3(32, 8), 0, st>>>(g, d_xx, d_xy, d_yy, d_sal);
+        c->prof_acc.kernel_launches += 12;
+        std::vector<int> pos((size_t)nm * 2);
+        for (int i = 0; i < nm; i++) { // the reference indexes with (int)(y * stride + x) on the float coordinates
+            const int idx = (int)(m4[4 * i + 1] * (float)g.S + m4[4 * i]);
+            pos[2 * i] = idx % g.S;
+            pos[2 * i + 1] = idx / g.S;
+        }
+        DevBuf d_pos, d_val;
+        if (!d_pos.alloc(pos.size() * 4 + 4) || !d_val.alloc((size_t)nm * 4 + 4)) return SFGPU_ERR_CUDA;
+        std::vector<float> sal((size_t)nm);
+        if (nm > 0) {
+            SF_CUDA(cudaMemcpyAsync(d_pos.p, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, st));
+            k_gather_plane<<<(nm + 255) / 256, 256, 0, st>>>(nm, d_pos.as<int>(), g, d_sal, d_val.as<float>());
+            SF_CUDA(cudaMemcpyAsync(sal.data(), d_val.p, (size_t)nm * 4, cudaMemcpyDeviceToHost, st));
+        }
+        SF_CUDA(cudaStreamSynchronize(st));
+        std::vector<unsigned char> keep((size_t)nm);
+        for (int i = 0; i < nm; i++) keep[i] = sal[i] >= params->saliency_th;
+        compact(keep);
+    }
+    sstat.matches_after_saliency = nm;
+
+    std::vector<int> seeds;
+    std::vector<float> vects;
+    DevBuf d_seeds, d_vects, d_qnn, d_qw, d_est, d_keep;
+    auto upload_matches = [&](int nn) -> int {
+        seeds_of(seeds, vects);
+        DevBuf *bufs[] = {&d_seeds, &d_vects, &d_qnn, &d_qw, &d_est, &d_keep};
+        for (DevBuf *b : bufs)
+            if (b->p) { cudaFree(b->p); b->p = nullptr; }
+        if (!d_seeds.alloc((size_t)nm * 8) || !d_vects.alloc((size_t)nm * 8) || !d_qnn.alloc((size_t)nm * nn * 4) || !d_qw.alloc((size_t)nm * nn * 4) ||
+            !d_est.alloc((size_t)nm * 6 * 4) || !d_keep.alloc((size_t)nm + 4))
+            return SFGPU_ERR_CUDA;
+        if (nm > 0) {
+            SF_CUDA(cudaMemcpyAsync(d_seeds.p, seeds.data(), (size_t)nm * 8, cudaMemcpyHostToDevice, st));
+            SF_CUDA(cudaMemcpyAsync(d_vects.p, vects.data(), (size_t)nm * 8, cudaMemcpyHostToDevice, st));
+        }
+        return SFGPU_OK;
+    };
+
+    // ---- consistency filter (prefiltering, epic.cpp:80-127)
+    if (params->pref_nn && nm > 0) {
+        const int nns = std::min(params->pref_nn + 1, nm);
+        int rc = upload_matches(nns);
+        if (rc != SFGPU_OK) return rc;
+        rc = nn_field(c, eg, d_cost.as<float>(), nm, nns, d_seeds.as<int>(), params->coef_kernel, d_labels.as<int>(), d_dmap.as<float>(), d_qnn.as<int>(),
+                      d_qw.as<float>(), &sstat.sweeps_prefilter);
+        if (rc != SFGPU_OK) return rc;
+        k_fit_nw<<<(nm + 127) / 128, 128, 0, st>>>(nm, nns, d_qnn.as<int>(), d_qw.as<float>(), d_vects.as<float>(), d_est.as<float>());
+        k_prefilter_flags<<<(nm + 127) / 128, 128, 0, st>>>(nm, d_est.as<float>(), d_vects.as<float>(), params->pref_th * params->pref_th,
+                                                          d_keep.as<unsigned char>());
+        c->prof_acc.kernel_launches += 2;
+        std::vector<unsigned char> keep((size_t)nm);
+        SF_CUDA(cudaMemcpyAsync(keep.data(), d_keep.p, (size_t)nm, cudaMemcpyDeviceToHost, st));
+        SF_CUDA(cudaStreamSynchronize(st));
+        compact(keep);
+    }
+    sstat.matches_after_consistency = nm;
+    if (nm <= 0) {
+        set_error("sfgpu_epic: no match survived the filters");
+        return SFGPU_ERR_ARG;
+    }
+
+    // ---- interpolation (epic.cpp:184-219)
+    const int nns = std::min(params->nn, nm);
+    int rc = upload_matches(nns);
+    if (rc != SFGPU_OK) return rc;
+    rc = nn_field(c, eg, d_cost.as<float>(), nm, nns, d_seeds.as<int>(), params->coef_kernel, d_labels.as<int>(), d_dmap.as<float>(), d_qnn.as<int>(),
+                  d_qw.as<float>(), &sstat.sweeps_interpolation);
+    if (rc != SFGPU_OK) return rc;
+    DevBuf d_flow;
+    if (!d_flow.alloc(2 * P * 4)) return SFGPU_ERR_CUDA;
+    SF_CUDA(cudaMemsetAsync(d_flow.p, 0, 2 * P * 4, st));
+    if (la) k_fit_la<<<(nm + 127) / 128, 128, 0, st>>>(nm, nns, d_qnn.as<int>(), d_qw.as<float>(), d_seeds.as<int>(), d_vects.as<float>(), d_est.as<float>());
+    else k_fit_nw<<<(nm + 127) / 128, 128, 0, st>>>(nm, nns, d_qnn.as<int>(), d_qw.as<float>(), d_vects.as<float>(), d_est.as<float>());
+    k_apply<<<grid2(W, H), dim3(32, 8), 0, st>>>(g, d_labels.as<int>(), d_est.as<float>(), la ? 1 : 0, d_flow.as<float>(), d_flow.as<float>() + P);
+    c->prof_acc.kernel_launches += 2;
+    rc = host_copies(c, {{d_flow.p, flowx->data, P * 4}, {d_flow.as<float>() + P, flowy->data, P * 4}}, false);
+    if (rc != SFGPU_OK) return rc;
+    SF_CUDA(cudaStreamSynchronize(st));
+    SF_CUDA(cudaGetLastError());
+    if (stats) *stats = sstat;
+    return SFGPU_OK;
+}
+
+// operator twin of dist_trf_nnfield_subset (epic_aux.cpp:350) with the seeds as query points: labels (W*H), best and dist
+// (ns x nn; dist BEFORE the exp kernel) for operator-level parity tests
+int sfgpu_epic_nnfield(sfgpu_ctx *c, int *best, float *dist, int *labels, const int *seeds, int ns, int nn, const float *cost, int w, int h,
+                       int *sweeps) {
+    if (!c || !best || !dist || !labels || !seeds || !cost || ns < 1 || nn < 1 || nn > ns || w < 1 || h < 1) {
+        set_error("sfgpu_epic_nnfield: bad argument");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t N = (size_t)w * h;
+    EpicGeo eg;
+    eg.W = w; eg.H = h;
+    eg.TX = (w + DT_TILE - 1) / DT_TILE;
+    eg.TY = (h + DT_TILE - 1) / DT_TILE;
+    int acc = 0;
+    for (int k = 0; k < eg.TX + eg.TY - 1; k++) {
+        eg.wave_start.push_back(acc);
+        acc += std::min(k, eg.TX - 1) - std::max(0, k - eg.TY + 1) + 1;
+    }
+    eg.wave_start.push_back(acc);
+    DevBuf d_cost, d_labels, d_dmap, d_seeds, d_qnn, d_qw;
+    if (!d_cost.alloc(N * 4) || !d_labels.alloc(N * 4) || !d_dmap.alloc(N * 4) || !d_seeds.alloc((size_t)ns * 8) || !d_qnn.alloc((size_t)ns * nn * 4) ||
+        !d_qw.alloc((size_t)ns * nn * 4))
+        return SFGPU_ERR_CUDA;
+    SF_CUDA(cudaMemcpyAsync(d_cost.p, cost, N * 4, cudaMemcpyHostToDevice, st));
+    SF_CUDA(cudaMemcpyAsync(d_seeds.p, seeds, (size_t)ns * 8, cudaMemcpyHostToDevice, st));
+    int rc = nn_field(c, eg, d_cost.as<float>(), ns, nn, d_seeds.as<int>(), -1.0f /* raw distances */, d_labels.as<int>(), d_dmap.as<float>(), d_qnn.as<int>(), d_qw.as<float>(),
+                      sweeps);
+    if (rc != SFGPU_OK) return rc;
+    SF_CUDA(cudaMemcpyAsync(labels, d_labels.p, N * 4, cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaMemcpyAsync(best, d_qnn.p, (size_t)ns * nn * 4, cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaMemcpyAsync(dist, d_qw.p, (size_t)ns * nn * 4, cudaMemcpyDeviceToHost, st));
+    SF_CUDA(cudaStreamSynchronize(st));
+    return SFGPU_OK;
+}
+
+} // extern "C"

@@ -179,57 +179,113 @@ __global__ void __launch_bounds__(256) k_occ_labels(Geom g, const unsigned char 
     occ[(size_t)j * g.S + i] = (i < g.W) ? (member[(size_t)j * g.W + i] != none ? 1.0f : -1.0f) : 0.0f;
 }
 
-// separable Gaussian (replicate border), symmetric-sum evaluation like cv::GaussianBlur's float path
+// separable Gaussian (replicate border), symmetric-sum evaluation like cv::GaussianBlur's float path.  Both passes handle
+// 4 consecutive pixels per thread with float4 loads / stores (rows are 16-byte aligned: stride = ceil4(width)).
 struct BlurTaps { int r; float k[17]; }; // k[0] centre, k[i] at distance i
-__global__ void __launch_bounds__(256) k_blur(Geom g, const float *__restrict__ src, float *__restrict__ dst, BlurTaps t,
-                                              int vertical, int planes) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= g.W || j >= g.H) return;
+constexpr int BLUR_SEG = 128 * 4; // columns per block of the horizontal pass (128 threads x 4)
+// horizontal pass: the block stages its row segment + r columns on either side (clamped to the row) in shared memory
+__global__ void __launch_bounds__(128) k_blur_h4(Geom g, const float *__restrict__ src, float *__restrict__ dst, BlurTaps t, int planes) {
+    __shared__ float row[BLUR_SEG + 2 * 16 + 8];
+    const int y = blockIdx.y, x0 = blockIdx.x * BLUR_SEG;
     const size_t P = g.plane();
+    const int lo = x0 - 16; // multiple of 4
     for (int c = 0; c < planes; c++) {
-        const float *s = src + c * P;
-        float acc = t.k[0] * s[(size_t)j * g.S + i];
-        for (int k = 1; k <= t.r; k++) {
-            const float a = vertical ? s[(size_t)clampi(j - k, 0, g.H - 1) * g.S + i] : s[(size_t)j * g.S + clampi(i - k, 0, g.W - 1)];
-            const float b = vertical ? s[(size_t)clampi(j + k, 0, g.H - 1) * g.S + i] : s[(size_t)j * g.S + clampi(i + k, 0, g.W - 1)];
-            acc += t.k[k] * (a + b);
+        const float *s = src + c * P + (size_t)y * g.S;
+        for (int q = threadIdx.x; q < (BLUR_SEG + 32) / 4; q += 128) {
+            const int x = lo + 4 * q;
+            float4 v;
+            if (x >= 0 && x + 3 < g.W) v = *reinterpret_cast<const float4 *>(s + x);
+            else v = make_float4(s[clampi(x, 0, g.W - 1)], s[clampi(x + 1, 0, g.W - 1)], s[clampi(x + 2, 0, g.W - 1)], s[clampi(x + 3, 0, g.W - 1)]);
+            *reinterpret_cast<float4 *>(row + 4 * q) = v;
         }
-        dst[c * P + (size_t)j * g.S + i] = acc;
+        __syncthreads();
+        const int x = x0 + 4 * threadIdx.x;
+        if (x < g.S) {
+            const float *p = row + 16 + 4 * threadIdx.x;
+            float a0 = t.k[0] * p[0], a1 = t.k[0] * p[1], a2 = t.k[0] * p[2], a3 = t.k[0] * p[3];
+            for (int k = 1; k <= t.r; k++) {
+                const float w = t.k[k];
+                a0 += w * (p[-k] + p[k]);
+                a1 += w * (p[1 - k] + p[1 + k]);
+                a2 += w * (p[2 - k] + p[2 + k]);
+                a3 += w * (p[3 - k] + p[3 + k]);
+            }
+            // the stride padding takes the value of the clamped column: it is never read as image data
+            *reinterpret_cast<float4 *>(dst + c * P + (size_t)y * g.S + x) = make_float4(a0, a1, a2, a3);
+        }
+        __syncthreads();
     }
 }
-// bilinear resize with pixel-centre mapping (cv::resize INTER_LINEAR), optional scale of the values
+// vertical pass: float4 per row tap, rows clamped
+__global__ void __launch_bounds__(256) k_blur_v4(Geom g, const float *__restrict__ src, float *__restrict__ dst, BlurTaps t, int planes) {
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= g.S || y >= g.H) return;
+    const size_t P = g.plane();
+    for (int c = 0; c < planes; c++) {
+        const float *s = src + c * P + x;
+        float4 acc = *reinterpret_cast<const float4 *>(s + (size_t)y * g.S);
+        acc.x *= t.k[0]; acc.y *= t.k[0]; acc.z *= t.k[0]; acc.w *= t.k[0];
+        for (int k = 1; k <= t.r; k++) {
+            const float4 a = *reinterpret_cast<const float4 *>(s + (size_t)clampi(y - k, 0, g.H - 1) * g.S);
+            const float4 b = *reinterpret_cast<const float4 *>(s + (size_t)clampi(y + k, 0, g.H - 1) * g.S);
+            const float w = t.k[k];
+            acc.x += w * (a.x + b.x); acc.y += w * (a.y + b.y); acc.z += w * (a.z + b.z); acc.w += w * (a.w + b.w);
+        }
+        *reinterpret_cast<float4 *>(dst + c * P + (size_t)y * g.S + x) = acc;
+    }
+}
+static void launch_blur(cudaStream_t st, Geom g, const float *src, float *tmp, float *dst, const BlurTaps &t, int planes) {
+    k_blur_h4<<<dim3((g.S + BLUR_SEG - 1) / BLUR_SEG, g.H), 128, 0, st>>>(g, src, tmp, t, planes);
+    k_blur_v4<<<dim3((g.S / 4 + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, st>>>(g, tmp, dst, t, planes);
+}
+// bilinear resize with pixel-centre mapping (cv::resize INTER_LINEAR), optional scale of the values; 4 destination pixels
+// per thread, float4 stores (the stride padding is zeroed)
 __global__ void __launch_bounds__(256) k_resize(Geom gs, const float *__restrict__ src, Geom gd, float *__restrict__ dst,
                                                 double scale_x, double scale_y, float mul, int planes) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= gd.S || y >= gd.H) return;
+    if (x4 >= gd.S || y >= gd.H) return;
     const size_t Ps = gs.plane(), Pd = gd.plane();
-    if (x >= gd.W) {
-        for (int c = 0; c < planes; c++) dst[c * Pd + (size_t)y * gd.S + x] = 0.0f;
-        return;
-    }
-    float fx = (float)((x + 0.5) * scale_x - 0.5);
-    int sx = (int)floorf(fx);
-    fx -= sx;
-    if (sx < 0) { sx = 0; fx = 0.f; }
-    if (sx >= gs.W - 1) { sx = gs.W - 1; fx = 0.f; }
     float fy = (float)((y + 0.5) * scale_y - 0.5);
     int sy = (int)floorf(fy);
     fy -= sy;
     if (sy < 0) { sy = 0; fy = 0.f; }
     if (sy >= gs.H - 1) { sy = gs.H - 1; fy = 0.f; }
-    const int x1 = min(sx + 1, gs.W - 1), y1 = min(sy + 1, gs.H - 1);
-    const float a1 = fx, a0 = 1.f - fx, b1 = fy, b0 = 1.f - fy;
+    const int y1 = min(sy + 1, gs.H - 1);
+    const float b1 = fy, b0 = 1.f - fy;
+    int sx[4], x1[4];
+    float a0[4], a1[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float fx = (float)((x4 + k + 0.5) * scale_x - 0.5);
+        int q = (int)floorf(fx);
+        fx -= q;
+        if (q < 0) { q = 0; fx = 0.f; }
+        if (q >= gs.W - 1) { q = gs.W - 1; fx = 0.f; }
+        sx[k] = q;
+        x1[k] = min(q + 1, gs.W - 1);
+        a1[k] = fx;
+        a0[k] = 1.f - fx;
+    }
     for (int c = 0; c < planes; c++) {
-        const float *s = src + c * Ps;
-        const float r0 = s[(size_t)sy * gs.S + sx] * a0 + s[(size_t)sy * gs.S + x1] * a1;
-        const float r1 = s[(size_t)y1 * gs.S + sx] * a0 + s[(size_t)y1 * gs.S + x1] * a1;
-        float v = r0 * b0 + r1 * b1;
-        if (mul != 1.0f) v *= mul; // image_mul_scalar (image.c:49-57)
-        dst[c * Pd + (size_t)y * gd.S + x] = v;
+        const float *s0 = src + c * Ps + (size_t)sy * gs.S, *s1 = src + c * Ps + (size_t)y1 * gs.S;
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (x4 + k < gd.W) {
+                const float r0 = s0[sx[k]] * a0[k] + s0[x1[k]] * a1[k];
+                const float r1 = s1[sx[k]] * a0[k] + s1[x1[k]] * a1[k];
+                float v = r0 * b0 + r1 * b1;
+                if (mul != 1.0f) v *= mul; // image_mul_scalar (image.c:49-57)
+                o[k] = v;
+            } else {
+                o[k] = 0.0f;
+            }
+        }
+        *reinterpret_cast<float4 *>(dst + c * Pd + (size_t)y * gd.S + x4) = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
+static dim3 resize_grid(Geom gd) { return dim3((gd.S / 4 + 31) / 32, (gd.H + 7) / 8); }
 
 // rawWeighting (utils/utils.cpp:1336-1374): per-pixel channel weights of a Bayer mosaic whose red site is at
 // (red_x, red_y) mod 2 -- the measured channel gets `weight`, the two interpolated ones 0.5*(3 - weight)
@@ -925,9 +981,8 @@ int sfgpu_prescale(sfgpu_ctx *c, color_image_t *dst, const color_image_t *src, f
     // (slow_flow.cpp:539-542); the mapping of a resize by factor uses 1/fx, not the ratio of the rounded sizes
     const double sigma = 1.0 / sqrt((double)(2.0f * scale));
     const BlurTaps taps = make_taps(sigma);
-    k_blur<<<grid2d(gs.W, gs.H), dim3(32, 8), 0, st>>>(gs, d_src, d_tmp, taps, 0, 3);
-    k_blur<<<grid2d(gs.W, gs.H), dim3(32, 8), 0, st>>>(gs, d_tmp, d_blur, taps, 1, 3);
-    k_resize<<<grid2d(gd.S, gd.H), dim3(32, 8), 0, st>>>(gs, d_blur, gd, d_dst, 1.0 / (double)scale, 1.0 / (double)scale, 1.0f, 3);
+    launch_blur(st, gs, d_src, d_tmp, d_blur, taps, 3);
+    k_resize<<<resize_grid(gd), dim3(32, 8), 0, st>>>(gs, d_blur, gd, d_dst, 1.0 / (double)scale, 1.0 / (double)scale, 1.0f, 3);
     c->prof_acc.kernel_launches += 3;
     SF_CUDA(cudaMemcpyAsync(dst->c1, d_dst, 3 * Pd * sizeof(float), cudaMemcpyDeviceToHost, st));
     SF_CUDA(cudaStreamSynchronize(st));
@@ -1057,12 +1112,11 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
         for (int l = 1; l < L; l++) {
             const Geom gs = geoms[l - 1], gd = geoms[l];
             for (int f = 0; f < F; f++) {
-                k_blur<<<grid2d(gs.W, gs.H), dim3(32, 8), 0, st>>>(gs, levels[l - 1].frames[f], blur_tmp, taps, 0, 3);
                 // vertical pass writes into the (not yet used) warp scratch of frame slot 0/1
                 float *tmp2 = warped[ref == 0 ? 1 : 0];
-                k_blur<<<grid2d(gs.W, gs.H), dim3(32, 8), 0, st>>>(gs, blur_tmp, tmp2, taps, 1, 3);
-                k_resize<<<grid2d(gd.S, gd.H), dim3(32, 8), 0, st>>>(gs, tmp2, gd, levels[l].frames[f], (double)gs.W / gd.W,
-                                                                     (double)gs.H / gd.H, 1.0f, 3);
+                launch_blur(st, gs, levels[l - 1].frames[f], blur_tmp, tmp2, taps, 3);
+                k_resize<<<resize_grid(gd), dim3(32, 8), 0, st>>>(gs, tmp2, gd, levels[l].frames[f], (double)gs.W / gd.W,
+                                                                  (double)gs.H / gd.H, 1.0f, 3);
                 c->prof_acc.kernel_launches += 3;
             }
         }
@@ -1074,8 +1128,8 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
     if (L > 1) {
         const Geom gd = geoms[L - 1];
         const float fx = (1.0f * gd.W) / g0.W, fy = (1.0f * gd.H) / g0.H;
-        k_resize<<<grid2d(gd.S, gd.H), dim3(32, 8), 0, st>>>(g0, cur_x, gd, oth_x, (double)g0.W / gd.W, (double)g0.H / gd.H, fx, 1);
-        k_resize<<<grid2d(gd.S, gd.H), dim3(32, 8), 0, st>>>(g0, cur_y, gd, oth_y, (double)g0.W / gd.W, (double)g0.H / gd.H, fy, 1);
+        k_resize<<<resize_grid(gd), dim3(32, 8), 0, st>>>(g0, cur_x, gd, oth_x, (double)g0.W / gd.W, (double)g0.H / gd.H, fx, 1);
+        k_resize<<<resize_grid(gd), dim3(32, 8), 0, st>>>(g0, cur_y, gd, oth_y, (double)g0.W / gd.W, (double)g0.H / gd.H, fy, 1);
         std::swap(cur_x, oth_x);
         std::swap(cur_y, oth_y);
         cur_g = gd;
@@ -1088,8 +1142,8 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
         const Geom g = geoms[l];
         if (l < L - 1) { // up-sample the flow of level l+1 and scale the vectors (:687-722)
             const float fx = (1.0f * g.W) / cur_g.W, fy = (1.0f * g.H) / cur_g.H;
-            k_resize<<<grid2d(g.S, g.H), dim3(32, 8), 0, st>>>(cur_g, cur_x, g, oth_x, (double)cur_g.W / g.W, (double)cur_g.H / g.H, fx, 1);
-            k_resize<<<grid2d(g.S, g.H), dim3(32, 8), 0, st>>>(cur_g, cur_y, g, oth_y, (double)cur_g.W / g.W, (double)cur_g.H / g.H, fy, 1);
+            k_resize<<<resize_grid(g), dim3(32, 8), 0, st>>>(cur_g, cur_x, g, oth_x, (double)cur_g.W / g.W, (double)cur_g.H / g.H, fx, 1);
+            k_resize<<<resize_grid(g), dim3(32, 8), 0, st>>>(cur_g, cur_y, g, oth_y, (double)cur_g.W / g.W, (double)cur_g.H / g.H, fy, 1);
             std::swap(cur_x, oth_x);
             std::swap(cur_y, oth_y);
             cur_g = g;

@@ -104,3 +104,29 @@ def window_case(width, height, S=3, seed=20170721, noise=0.25, zero_flow=False):
     frames = [frame(width, height, t, seed) for t in range(-ref, ref + 1)]
     wx, wy = initial_flow(width, height, noise, zero=zero_flow)
     return frames, wx, wy
+
+
+def epic_case(width, height, n_matches=2000, seed=4242, outliers=0.05):
+    """Synthetic inputs of the EPIC interpolation (epic.cpp:147): the first frame (used for the saliency filter), sparse
+    matches x1 y1 x2 y2 scattered over the image that follow the ground-truth flow up to +-0.3 px (plus a few gross
+    outliers for the consistency filter), and an edge-cost map in [0, 1] that is high along the motion discontinuity and
+    along the texture's strongest gradients (the reference takes SED edges here, which are not available offline)."""
+    rng = np.random.RandomState(seed)
+    im = frame(width, height, 0)
+    u, v = gt_flow(width, height)
+    xs = rng.randint(2, width - 2, n_matches)
+    ys = rng.randint(2, height - 2, n_matches)
+    m = np.zeros((n_matches, 4), np.float32)
+    m[:, 0], m[:, 1] = xs, ys
+    m[:, 2] = xs + u[ys, xs] + rng.uniform(-0.3, 0.3, n_matches)
+    m[:, 3] = ys + v[ys, xs] + rng.uniform(-0.3, 0.3, n_matches)
+    bad = rng.rand(n_matches) < outliers
+    m[bad, 2] += rng.uniform(-25, 25, int(bad.sum()))
+    m[bad, 3] += rng.uniform(-25, 25, int(bad.sum()))
+    lum = im.mean(axis=0)
+    gy, gx = np.gradient(lum)
+    mag = np.sqrt(gx * gx + gy * gy)
+    edges = 0.25 * mag / (mag.max() + 1e-9)
+    x = np.arange(width)[None, :]
+    edges = edges + 0.9 * np.exp(-0.5 * ((x - width / 2.0) / 1.5) ** 2)
+    return im, m, np.clip(edges, 0.0, 1.0).astype(np.float32)

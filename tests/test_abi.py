@@ -16,7 +16,7 @@ def declared_functions():
     src = open(os.path.join(ROOT, "include", "slowflow_gpu.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = re.findall(r"\b([a-z_][a-z0-9_]*)\s*\([^;{]*\)\s*;", src)
-    return sorted(set(n for n in names if n.startswith(("sfgpu_", "sf_mt_", "variational"))))
+    return sorted(set(n for n in names if n.startswith(("sfgpu_", "sf_mt_", "variational", "epic"))))
 
 
 def test_header_functions_are_exported(built):
