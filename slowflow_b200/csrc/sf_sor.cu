@@ -61,9 +61,6 @@ __global__ void __launch_bounds__(256) k_sor_half_global(Geom g, const float *__
 #ifndef SF_SOR_PDL
 #define SF_SOR_PDL 1 // chain consecutive launches with programmatic dependent launch
 #endif
-#ifndef SF_SOR_CHAIN
-#define SF_SOR_CHAIN 1 // 1: short dependency chains (pairwise neighbour sums, omega folded into the blocks); 0: one FMA chain
-#endif
 #ifndef SF_SOR_SYNC
 #define SF_SOR_SYNC 0 // 0: one CTA barrier per half sweep; 1: neighbour-to-neighbour publication counters
 #endif
@@ -192,25 +189,12 @@ __device__ __forceinline__ void sor_relax_pair(SorRegs &q, const float2 up, cons
         vb = q.dv[e][P + 1];
     }
     const p64 psb = q.pv[e][P];
-#if SF_SOR_CHAIN
-    // Shorter dependency chains (the kernel is latency-bound: 2 warps per scheduler): the neighbour sum is formed as
-    // (horizontal pair) + (vertical pair + b) instead of one 4-deep FMA chain, and the relaxation
-    //     d += omega*(a1*B1 + a2*B2 - d)  =  (1 - omega)*d + (omega*a1)*B1 + (omega*a2)*B2
-    // uses blocks pre-scaled by omega when the tile is loaded, so that only two FMAs follow the sums.  Same arithmetic up
-    // to the order of the roundings (5 instead of 7 dependent instructions per update).
-    const p64 B1 = add2(fma2(psl, ul, mul2(psr, ur)), fma2(pst, ut, fma2(psb, ub, q.b1[e][P])));
-    const p64 B2 = add2(fma2(psl, vl, mul2(psr, vr)), fma2(pst, vt, fma2(psb, vb, q.b2[e][P])));
-    // nomega2 holds (1 - omega) here; na11 .. na22 hold +omega * a'
-    q.du[e][P] = fma2(q.na11[e][P], B1, fma2(q.na12[e][P], B2, mul2(nomega2, q.du[e][P])));
-    q.dv[e][P] = fma2(q.na12[e][P], B1, fma2(q.na22[e][P], B2, mul2(nomega2, q.dv[e][P])));
-#else
     const p64 B1 = fma2(psl, ul, fma2(psr, ur, fma2(pst, ut, fma2(psb, ub, q.b1[e][P]))));
     const p64 B2 = fma2(psl, vl, fma2(psr, vr, fma2(pst, vt, fma2(psb, vb, q.b2[e][P]))));
     const p64 nu = fma2(q.na11[e][P], B1, fma2(q.na12[e][P], B2, q.du[e][P]));
     const p64 nv = fma2(q.na12[e][P], B1, fma2(q.na22[e][P], B2, q.dv[e][P]));
     q.du[e][P] = fma2(nomega2, nu, q.du[e][P]);
     q.dv[e][P] = fma2(nomega2, nv, q.dv[e][P]);
-#endif
 }
 
 // relax pairs [P, PEND) of colour C; with SF_SOR_SKIP a pair whose deeper row has depth <= k is skipped
@@ -322,11 +306,7 @@ k_sor_tiled(const __grid_constant__ CUtensorMap tmap_coef, const __grid_constant
         wait_clk += clock64() - w0;
 #endif
     };
-#if SF_SOR_CHAIN
-    const p64 nomega2 = pk(1.0f - a.omega, 1.0f - a.omega);
-#else
     const p64 nomega2 = pk(-a.omega, -a.omega);
-#endif
     const float2 zero2 = make_float2(0.0f, 0.0f);
     // Half sweep k only has to be right for pixels at depth >= k+1 from the tile edge, so (with SF_SOR_SKIP) a
     // row pair whose deeper row has depth <= k is skipped in half sweep k (warp-uniform).
@@ -354,11 +334,7 @@ k_sor_tiled(const __grid_constant__ CUtensorMap tmap_coef, const __grid_constant
             // loads are transposed into two pairs.  Each pair is then passed through one FFMA2 (x*1 + 0, or x*(-1) + 0
             // for the negated blocks) so that it is DEFINED by a 64-bit instruction: ptxas then keeps it in an
             // aligned register pair instead of re-assembling it from two scalars with MOVs in front of every use.
-#if SF_SOR_CHAIN
-            const p64 one2 = pk(a.one, a.one), mone2 = pk(a.omega * a.one, a.omega * a.one), z2 = pk(0.0f, 0.0f); // blocks * omega
-#else
             const p64 one2 = pk(a.one, a.one), mone2 = pk(-a.one, -a.one), z2 = pk(0.0f, 0.0f);
-#endif
             const float2 *row0 = reinterpret_cast<const float2 *>(stage) + lane;
             auto ld2 = [&](int plane, int p, p64 &c0, p64 &c1, p64 scale) {
                 const float2 lo = row0[((plane * SOR_R + p) * SOR_TW) / 2];

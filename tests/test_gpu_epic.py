@@ -92,8 +92,9 @@ def test_epic_filters_off_and_few_matches(ctx, reference):
     p = epic_params_default()
     p.saliency_th, p.pref_nn = 0.0, 0
     rx, ry, gx, gy = Image(w, h), Image(w, h), Image(w, h), Image(w, h)
-    L.sf_ref_epic(rx.ptr(), ry.ptr(), ci.ptr(), m.ctypes.data, n, 4, edges.copy().ctypes.data, C.byref(p))
-    st = ctx.epic(gx, gy, ci, m, edges.copy(), p)
+    e_ref, e_gpu = edges.copy(), edges.copy()  # (named: a temporary would be freed before the call reads it)
+    L.sf_ref_epic(rx.ptr(), ry.ptr(), ci.ptr(), m.ctypes.data, n, 4, e_ref.ctypes.data, C.byref(p))
+    st = ctx.epic(gx, gy, ci, m, e_gpu, p)
     assert st.matches_after_consistency == n
     d = np.sqrt((gx.array - rx.array) ** 2 + (gy.array - ry.array) ** 2)
     assert d.mean() <= 0.01 and d.max() <= 0.1
