@@ -372,6 +372,56 @@ def run_mt_secondary(ctx, torch, with_cpu, reps=3):
                 "gpu_ms_per_outer_iteration": 1e3 * t_win / max(1, stats.outer_iterations)}
         out["config%d" % cid] = line
         del pins, frames
+    out["epic"] = run_epic_secondary(ctx, with_cpu)
+    return out
+
+
+def run_epic_secondary(ctx, with_cpu, reps=3):
+    """EPIC sparse-to-dense interpolation (the step in front of variational(), epicflow.cpp:125): sfgpu_epic on synthetic
+    matches / edge costs at 1024x436 (5,000 matches, the EpicFlow paper's Sintel geometry) and 2560x1440 (20,000 matches),
+    host buffers in, flow planes out; with_cpu: the reference's own epic() (oracle/_ref, one core) on the same inputs."""
+    import ctypes as C
+    import numpy as np
+    from slowflow_b200 import ColorImage, Image, synth
+    from slowflow_b200.api import EpicParams, epic_params_default
+    from slowflow_b200.image import color_image_t, image_t
+    out = {}
+    for (w, h, n) in ((1024, 436, 5000), (2560, 1440, 20000)):
+        im, m, edges = synth.epic_case(w, h, n)
+        ci = ColorImage.from_array(im)
+        p = epic_params_default()
+        fx, fy = Image(w, h), Image(w, h)
+        times, st = [], None
+        for rep in range(reps + 1):
+            e = edges.copy()
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            st = ctx.epic(fx, fy, ci, m, e, p)
+            dt = time.perf_counter() - t0
+            if rep > 0:
+                times.append(dt)
+        times.sort()
+        line = {"workload": "EPIC interpolation %dx%d, %d synthetic matches, LA fit, default parameters" % (w, h, n),
+                "ms_per_call": 1e3 * times[len(times) // 2], "matches_after_filters": st.matches_after_consistency,
+                "distance_transform_sweeps": [st.sweeps_prefilter, st.sweeps_interpolation],
+                "api": "sfgpu_epic (host buffers, uploads and the flow download inside the timed region)"}
+        if with_cpu:
+            from oracle.pyoracle import Reference, have_reference
+            if have_reference():
+                L = Reference().lib
+                IP, CP = C.POINTER(image_t), C.POINTER(color_image_t)
+                L.sf_ref_epic.argtypes = [IP, IP, CP, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(EpicParams)]
+                L.sf_ref_epic.restype = None
+                rx, ry, e = Image(w, h), Image(w, h), edges.copy()
+                with _StdoutToStderr():
+                    t0 = time.perf_counter()
+                    L.sf_ref_epic(rx.ptr(), ry.ptr(), ci.ptr(), m.ctypes.data, n, 4, e.ctypes.data, C.byref(p))
+                    cpu_s = time.perf_counter() - t0
+                d = np.sqrt((fx.array - rx.array) ** 2 + (fy.array - ry.array) ** 2)
+                line["cpu_baseline"] = {"value": cpu_s, "unit": "s per call (1 core)", "cores": 1, "kind": "reference",
+                                        "sample": "the same call through the reference's epic() (sgels from oracle/ref_glue/lapack_stub.c)",
+                                        "gpu_vs_cpu_mean_px": float(d.mean()), "gpu_vs_cpu_max_px": float(d.max())}
+        out["%dx%d" % (w, h)] = line
     return out
 
 
