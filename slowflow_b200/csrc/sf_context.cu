@@ -343,6 +343,7 @@ void sfgpu_destroy(sfgpu_ctx *c) {
     if (c->mtw) sf::mt_work_free(c->mtw);
     if (c->stager) sf::host_stager_free(c->stager);
     if (c->cut) sf::device_cut_free(c->cut);
+    if (c->epic_arena) sf::epic_arena_free(c->epic_arena);
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
     for (auto &ring : c->seq_ev)

@@ -7,6 +7,8 @@
 namespace sf {
 struct MtWork; // multi-frame workspace (sf_mt.cu), kept between calls
 void mt_work_free(MtWork *w);
+struct EpicArena; // workspace of the EPIC interpolation (sf_epic.cu)
+void epic_arena_free(EpicArena *a);
 struct DeviceCut; // device-side grid min-cut workspace (sf_mincut.cu)
 void device_cut_free(DeviceCut *d);
 struct HostStager; // pinned bounce buffers for pageable caller memory (sf_hostcopy.cu)
@@ -62,6 +64,7 @@ struct sfgpu_ctx {
     sf::MtWork *mtw = nullptr;
     sf::HostStager *stager = nullptr;
     sf::DeviceCut *cut = nullptr;
+    sf::EpicArena *epic_arena = nullptr;
     bool host_mincut = false; // env SLOWFLOW_GPU_HOST_MINCUT=1: occlusion labelling on the host (sf_gridcut.hpp), A/B only
     bool staged_host_copies = true; // env SLOWFLOW_GPU_STAGED_COPIES=0 switches the multi-threaded staging off
 

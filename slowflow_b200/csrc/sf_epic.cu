@@ -23,8 +23,11 @@
 //     two weighted 3-parameter fits with one design matrix, solved here per seed by normal equations in DOUBLE with
 //     coordinates centred on the seed (parity unpinned at this call anyway: LAPACK is not part of the reference tree).
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
+
+#include <stdlib.h>
 
 #include <string.h>
 
@@ -165,8 +168,10 @@ constexpr int DT_WARPS = 2; // warps (= tiles in flight) per block: 3 x 4.25 KB 
 // bounded spin on a predecessor tile's done-flag: a protocol error traps instead of hanging the GPU
 __device__ __forceinline__ void dt_wait(const int *flag, int k) {
     unsigned spins = 0;
-    while (ld_acquire_gpu(flag) != k)
-        if (++spins > (1u << 26)) __trap();
+    while (ld_acquire_gpu(flag) != k) {
+        __nanosleep(64); // back off: thousands of polling warps would otherwise flood the L2 the working tiles need
+        if (++spins > (1u << 24)) __trap();
+    }
 }
 __global__ void __launch_bounds__(DT_WARPS * 32) k_dt_sweep(DtSweepArgs a) {
     if (a.k > *reinterpret_cast<volatile int *>(&a.ctrl->end_iter)) return;
@@ -201,14 +206,26 @@ __global__ void __launch_bounds__(DT_WARPS * 32) k_dt_sweep(DtSweepArgs a) {
         }
         __syncwarp();
         // stage the tile (coalesced rows) in sweep coordinates: local (p, q) <-> pixel (x0 + (sx>0 ? p : tw-1-p), y0 + ...)
-        for (int q = 0; q < th; q++) {
-            const int j = y0 + (a.sy > 0 ? q : th - 1 - q);
-            if (lane < tw) {
-                const int i = x0 + (a.sx > 0 ? lane : tw - 1 - lane);
-                const size_t o = (size_t)j * a.W + i;
-                tA[q * DT_PITCH + lane] = __ldcg(a.A + o);
-                tL[q * DT_PITCH + lane] = __ldcg(a.L + o);
-                tC[q * DT_PITCH + lane] = __ldg(a.cost + o);
+        // (all loads of the tile are issued before the first one is stored: a rolled load-store loop would serialise 32 L2
+        // round trips -- that was 22 of the 25 us a tile took in the first version)
+        {
+            float ra[DT_TILE], rc[DT_TILE];
+            int rl[DT_TILE];
+            const int i = x0 + (a.sx > 0 ? lane : tw - 1 - lane);
+#pragma unroll
+            for (int q = 0; q < DT_TILE; q++) {
+                const int j = y0 + (a.sy > 0 ? q : th - 1 - q);
+                const bool ok = q < th && lane < tw;
+                const size_t o = ok ? (size_t)j * a.W + i : 0;
+                ra[q] = ok ? __ldcg(a.A + o) : 0.0f;
+                rl[q] = ok ? __ldcg(a.L + o) : 0;
+                rc[q] = ok ? __ldg(a.cost + o) : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < DT_TILE; q++) {
+                tA[q * DT_PITCH + lane] = ra[q];
+                tL[q * DT_PITCH + lane] = rl[q];
+                tC[q * DT_PITCH + lane] = rc[q];
             }
         }
         __syncwarp();
@@ -516,13 +533,63 @@ __global__ void __launch_bounds__(256) k_apply(Geom g, const int *__restrict__ l
 }
 
 // ------------------------------------------------------------------------------------------ host side
-struct DevBuf { // RAII device allocation
+// All device memory of a call comes from ONE grow-only arena kept by the context (cudaMalloc / cudaFree per buffer cost
+// more than the kernels: 390 ms per call against 20 ms of GPU work at 1024x436).  Buffers are bump-allocated views;
+// mark() / release() give stack discipline to the scratch of a phase.  A call that does not fit reports it, the entry
+// point grows the arena to the recorded high-water mark and runs the call again.
+struct EpicArena {
+    char *base = nullptr;
+    size_t cap = 0, off = 0, high = 0;
+    bool overflow = false;
+    void *take(size_t bytes) {
+        const size_t at = (off + 255) & ~(size_t)255;
+        high = std::max(high, at + bytes);
+        if (at + bytes > cap) {
+            overflow = true;
+            return nullptr;
+        }
+        off = at + bytes;
+        return base + at;
+    }
+    size_t mark() const { return off; }
+    void release(size_t m) { off = m; }
+};
+void epic_arena_free(EpicArena *a) {
+    if (!a) return;
+    if (a->base) cudaFree(a->base);
+    delete a;
+}
+static thread_local EpicArena *g_arena = nullptr; // the arena of the call running on this host thread
+struct DevBuf { // a view into the arena (named like the owning buffer it replaced)
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
     template <typename T> T *as() { return reinterpret_cast<T *>(p); }
-    bool alloc(size_t bytes) { return cuda_ok(cudaMalloc(&p, bytes ? bytes : 4), "cudaMalloc(epic)"); }
+    bool alloc(size_t bytes) {
+        p = g_arena->take(bytes ? bytes : 4);
+        if (!p) set_error("sfgpu_epic: workspace arena too small (the call is repeated with a larger one)");
+        return p != nullptr;
+    }
+};
+struct ArenaScope { // releases everything a phase allocated when it ends
+    size_t m;
+    ArenaScope() : m(g_arena->mark()) {}
+    ~ArenaScope() { g_arena->release(m); }
 };
 static dim3 grid2(int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); }
+
+// phase timer for SLOWFLOW_GPU_TRACE=1 (stderr); synchronises the stream when tracing, otherwise free
+struct EpicTrace {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    explicit EpicTrace(cudaStream_t s) : on(getenv("SLOWFLOW_GPU_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "  epic: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 struct EpicGeo {
     int W, H, TX, TY;
@@ -534,6 +601,8 @@ struct EpicGeo {
 static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns, int nn, const int *d_seeds, float coef, int *d_labels,
                     float *d_dmap, int *d_qnn, float *d_qw, int *sweeps_out) {
     cudaStream_t st = c->stream;
+    EpicTrace tr(st);
+    ArenaScope scope; // (the caller's buffers were allocated before; the stream is idle when the scratch is released)
     const int W = eg.W, H = eg.H;
     const size_t N = (size_t)W * H;
     const int ntiles = eg.TX * eg.TY;
@@ -554,7 +623,10 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
     static const int dx[4] = {-1, 1, 1, -1}, dy[4] = {1, 1, -1, -1};
     int sm_blocks = 0;
     SF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sm_blocks, k_dt_sweep, DT_WARPS * 32, 0));
-    const int grid = std::max(1, std::min((ntiles + DT_WARPS - 1) / DT_WARPS, c->num_sms * std::max(1, sm_blocks)));
+    // an anti-diagonal of tiles holds at most min(TX, TY) tiles: more warps than about twice that only poll
+    const int useful_warps = 2 * std::min(eg.TX, eg.TY) + 2;
+    const int grid = std::max(1, std::min({(ntiles + DT_WARPS - 1) / DT_WARPS, (useful_warps + DT_WARPS - 1) / DT_WARPS,
+                                           c->num_sms * std::max(1, sm_blocks)}));
     for (int k = 1; k <= DT_MAX_SWEEPS; k++) {
         DtSweepArgs a;
         a.W = W; a.H = H; a.TX = eg.TX; a.TY = eg.TY;
@@ -568,9 +640,11 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
         k_dt_control<<<1, 1, 0, st>>>(ctrl.as<DtCtrl>(), k, 1.0f, DT_MAX_SWEEPS); // default dt_params: max_iter 40, min_change 1 (:151-154)
     }
     c->prof_acc.kernel_launches += 4 + 2 * DT_MAX_SWEEPS;
+    tr.mark("distance transform");
 
     // ---- neighbourhood graph
-    const int cap = (int)std::min<size_t>(4 * N, (size_t)1 << 30);
+    // label borders: every border pixel pair emits two entries; ~6 sqrt(N ns) in practice, 4 N at worst
+    const int cap = (int)std::min<size_t>(4 * N, (size_t)(32.0 * sqrt((double)N * (double)ns)) + ((size_t)1 << 20));
     DevBuf keys, vals, keys2, vals2, count, ukeys, uvals, nruns, tmp;
     if (!keys.alloc((size_t)cap * 8) || !vals.alloc((size_t)cap * 4) || !keys2.alloc((size_t)cap * 8) || !vals2.alloc((size_t)cap * 4) ||
         !count.alloc(8) || !nruns.alloc(8))
@@ -583,9 +657,10 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
     SF_CUDA(cudaMemcpyAsync(&h_ctrl, ctrl.p, sizeof(DtCtrl), cudaMemcpyDeviceToHost, st));
     SF_CUDA(cudaStreamSynchronize(st));
     if (sweeps_out) *sweeps_out = h_ctrl.sweeps_run;
+    tr.mark("border emit (+allocs)");
     if (h_count + 1 >= cap) {
-        set_error("sfgpu_epic: label border list overflow");
-        return SFGPU_ERR_NOMEM;
+        set_error("sfgpu_epic: label border list overflow (more than 32 sqrt(N ns) + 1M border entries)");
+        return SFGPU_ERR_UNSUPPORTED;
     }
     int nedges = 0;
     DevBuf indptr, indices;
@@ -608,6 +683,7 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
     }
     if (!indices.alloc((size_t)std::max(nedges, 1) * sizeof(int))) return SFGPU_ERR_CUDA;
     k_csr_rows<<<(ns + 1 + 255) / 256, 256, 0, st>>>(ns, nedges, ukeys.as<unsigned long long>(), indptr.as<int>(), indices.as<int>());
+    tr.mark("sort + reduce + csr");
 
     // ---- k nearest seeds of every seed, then the query step
     const int warps_per_block = 8;
@@ -621,6 +697,7 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
         return SFGPU_ERR_CUDA;
     k_fill_u32<<<592, 256, 0, st>>>(nwarps * ns, done_all.as<unsigned>(), EPIC_UNSEEN);
     SF_CUDA(cudaMemsetAsync(overflow.p, 0, 4, st));
+    tr.mark("knn allocs + fill");
     const size_t smem = (size_t)warps_per_block * KNN_HEAP * sizeof(HeapItem);
     SF_CUDA(cudaFuncSetAttribute(k_knn_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_knn_graph<<<blocks, warps_per_block * 32, smem, st>>>(ns, nn, indptr.as<int>(), indices.as<int>(), uvals.as<float>(), done_all.as<unsigned>(),
@@ -631,6 +708,7 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
     SF_CUDA(cudaStreamSynchronize(st));
     SF_CUDA(cudaGetLastError());
     c->prof_acc.kernel_launches += 6;
+    tr.mark("knn search + query");
     if (h_over) {
         set_error("sfgpu_epic: neighbour search heap overflow (a seed with more than 2048 open graph nodes)");
         return SFGPU_ERR_NOMEM;
@@ -656,8 +734,35 @@ void epic_params_default(epic_params_t *params) { // epic.cpp:131-140
     params->verbose = 0;
 }
 
-int sfgpu_epic(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_image_t *im, const float_image *input_matches, float_image *edges,
-               const epic_params_t *params, sfgpu_epic_stats_t *stats) {
+} // extern "C"
+
+// runs `body` with the context's arena installed, growing the arena and repeating the call while it does not fit
+template <typename F> static int with_arena(sfgpu_ctx *c, size_t first_guess, F body) {
+    if (!c->epic_arena) c->epic_arena = new EpicArena();
+    EpicArena *ar = c->epic_arena;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        const size_t want = std::max(first_guess, ar->high + ar->high / 8);
+        if (want > ar->cap) {
+            SF_CUDA(cudaStreamSynchronize(c->stream));
+            if (ar->base) cudaFree(ar->base);
+            ar->base = nullptr;
+            ar->cap = 0;
+            SF_CUDA(cudaMalloc(&ar->base, want));
+            ar->cap = want;
+        }
+        ar->off = 0;
+        ar->overflow = false;
+        g_arena = ar;
+        const int rc = body();
+        g_arena = nullptr;
+        if (!ar->overflow) return rc;
+    }
+    set_error("sfgpu_epic: workspace arena could not be sized");
+    return SFGPU_ERR_NOMEM;
+}
+
+static int epic_impl(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_image_t *im, const float_image *input_matches, float_image *edges,
+                     const epic_params_t *params, sfgpu_epic_stats_t *stats) {
     if (!c || !flowx || !flowy || !im || !input_matches || !edges || !params || !flowx->data || !flowy->data || !im->c1 ||
         !input_matches->pixels || !edges->pixels) {
         set_error("sfgpu_epic: null argument");
@@ -676,6 +781,7 @@ int sfgpu_epic(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_image_t
     }
     SF_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
+    EpicTrace trace(st);
     const Geom g{W, H, flowx->stride};
     const size_t N = (size_t)W * H, P = g.plane();
     sfgpu_epic_stats_t sstat;
@@ -692,9 +798,7 @@ int sfgpu_epic(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_image_t
         m4[4 * i + 3] = std::max(0.0f, std::min(r[3], (float)(H - 1)));
     }
     sstat.matches_in = nm;
-    // ---- edges += euc, in the caller's array like the reference (:155-163), then to the device
-    if (params->euc)
-        for (size_t i = 0; i < N; i++) edges->pixels[i] += params->euc;
+    // ---- the edge costs (the entry point has already added euc in the caller's array, :155-163) go to the device
     DevBuf d_cost, d_labels, d_dmap;
     if (!d_cost.alloc(N * 4) || !d_labels.alloc(N * 4) || !d_dmap.alloc(N * 4)) return SFGPU_ERR_CUDA;
     SF_CUDA(cudaMemcpyAsync(d_cost.p, edges->pixels, N * 4, cudaMemcpyHostToDevice, st));
@@ -735,6 +839,7 @@ int sfgpu_epic(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_image_t
 
     // ---- saliency filter (epic.cpp:60-77)
     if (params->saliency_th) {
+        ArenaScope sal_scope;
         DevBuf work;
         if (!work.alloc(16 * P * 4)) return SFGPU_ERR_CUDA;
         float *d_im = work.as<float>(), *d_tmp = d_im + 3 * P, *d_sm = d_im + 6 * P, *d_ix = d_im + 9 * P, *d_iy = d_im + 12 * P;
@@ -777,15 +882,15 @@ int sfgpu_epic(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_image_t
         compact(keep);
     }
     sstat.matches_after_saliency = nm;
+    trace.mark("[rectify + saliency filter]");
 
     std::vector<int> seeds;
     std::vector<float> vects;
     DevBuf d_seeds, d_vects, d_qnn, d_qw, d_est, d_keep;
+    const size_t match_mark = g_arena->mark();
     auto upload_matches = [&](int nn) -> int {
         seeds_of(seeds, vects);
-        DevBuf *bufs[] = {&d_seeds, &d_vects, &d_qnn, &d_qw, &d_est, &d_keep};
-        for (DevBuf *b : bufs)
-            if (b->p) { cudaFree(b->p); b->p = nullptr; }
+        g_arena->release(match_mark); // the buffers of the previous (larger) match list
         if (!d_seeds.alloc((size_t)nm * 8) || !d_vects.alloc((size_t)nm * 8) || !d_qnn.alloc((size_t)nm * nn * 4) || !d_qw.alloc((size_t)nm * nn * 4) ||
             !d_est.alloc((size_t)nm * 6 * 4) || !d_keep.alloc((size_t)nm + 4))
             return SFGPU_ERR_CUDA;
@@ -814,6 +919,7 @@ int sfgpu_epic(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_image_t
         compact(keep);
     }
     sstat.matches_after_consistency = nm;
+    trace.mark("[consistency filter total]");
     if (nm <= 0) {
         set_error("sfgpu_epic: no match survived the filters");
         return SFGPU_ERR_ARG;
@@ -833,18 +939,43 @@ int sfgpu_epic(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_image_t
     else k_fit_nw<<<(nm + 127) / 128, 128, 0, st>>>(nm, nns, d_qnn.as<int>(), d_qw.as<float>(), d_vects.as<float>(), d_est.as<float>());
     k_apply<<<grid2(W, H), dim3(32, 8), 0, st>>>(g, d_labels.as<int>(), d_est.as<float>(), la ? 1 : 0, d_flow.as<float>(), d_flow.as<float>() + P);
     c->prof_acc.kernel_launches += 2;
+    trace.mark("[interpolation total]");
     rc = host_copies(c, {{d_flow.p, flowx->data, P * 4}, {d_flow.as<float>() + P, flowy->data, P * 4}}, false);
     if (rc != SFGPU_OK) return rc;
     SF_CUDA(cudaStreamSynchronize(st));
+    trace.mark("[flow download]");
     SF_CUDA(cudaGetLastError());
     if (stats) *stats = sstat;
     return SFGPU_OK;
 }
 
+extern "C" {
+
+int sfgpu_epic(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_image_t *im, const float_image *input_matches, float_image *edges,
+               const epic_params_t *params, sfgpu_epic_stats_t *stats) {
+    if (!c || !im || !edges || !edges->pixels || !params) {
+        set_error("sfgpu_epic: null argument");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    const size_t N = (size_t)im->width * im->height;
+    if (edges->tx != im->width || edges->ty != im->height) {
+        set_error("sfgpu_epic: the edge map must have the image's size");
+        return SFGPU_ERR_ARG;
+    }
+    // edges += euc in the caller's array, like the reference (epic.cpp:155-163); once, whatever the arena does below
+    if (params->euc)
+        for (size_t i = 0; i < N; i++) edges->pixels[i] += params->euc;
+    const size_t guess = N * 4 * 24 + ((size_t)64 << 20);
+    return with_arena(c, guess, [&]() { return epic_impl(c, flowx, flowy, im, input_matches, edges, params, stats); });
+}
+
 // operator twin of dist_trf_nnfield_subset (epic_aux.cpp:350) with the seeds as query points: labels (W*H), best and dist
 // (ns x nn; dist BEFORE the exp kernel) for operator-level parity tests
-int sfgpu_epic_nnfield(sfgpu_ctx *c, int *best, float *dist, int *labels, const int *seeds, int ns, int nn, const float *cost, int w, int h,
-                       int *sweeps) {
+} // extern "C"
+
+static int nnfield_impl(sfgpu_ctx *c, int *best, float *dist, int *labels, const int *seeds, int ns, int nn, const float *cost, int w, int h,
+                        int *sweeps) {
     if (!c || !best || !dist || !labels || !seeds || !cost || ns < 1 || nn < 1 || nn > ns || w < 1 || h < 1) {
         set_error("sfgpu_epic_nnfield: bad argument");
         return SFGPU_ERR_ARG;
@@ -876,6 +1007,19 @@ int sfgpu_epic_nnfield(sfgpu_ctx *c, int *best, float *dist, int *labels, const 
     SF_CUDA(cudaMemcpyAsync(dist, d_qw.p, (size_t)ns * nn * 4, cudaMemcpyDeviceToHost, st));
     SF_CUDA(cudaStreamSynchronize(st));
     return SFGPU_OK;
+}
+
+
+extern "C" {
+
+int sfgpu_epic_nnfield(sfgpu_ctx *c, int *best, float *dist, int *labels, const int *seeds, int ns, int nn, const float *cost, int w, int h,
+                       int *sweeps) {
+    if (!c || w < 1 || h < 1) {
+        set_error("sfgpu_epic_nnfield: bad argument");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    return with_arena(c, (size_t)w * h * 4 * 16 + ((size_t)64 << 20), [&]() { return nnfield_impl(c, best, dist, labels, seeds, ns, nn, cost, w, h, sweeps); });
 }
 
 } // extern "C"
