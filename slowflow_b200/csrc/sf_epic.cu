@@ -10,9 +10,9 @@
 // after the two filters, in the reference's order.
 //   * Distance transform: the reference sweeps the image in raster order in four directions (Gauss-Seidel: a pixel uses
 //     the already updated left / upper neighbour of the SAME sweep).  The sweeps are reproduced exactly -- same operations,
-//     same order per pixel, no FMA contraction -- as a wavefront: 32 x 32 tiles in anti-diagonal order (tickets taken in
-//     wave-major order from an atomic counter, a tile spins on the done-flags of its two predecessors), and inside a tile
-//     one warp walks the 63 local anti-diagonals with the row state in registers and the upper neighbour by shuffle.
+//     same order per pixel, no FMA contraction -- as a pipeline of row strips: a warp owns 32 rows (lane = row) and
+//     marches along the sweep direction with its wavefront in registers (left neighbour = own previous result, upper
+//     neighbour = shuffle), the strip below follows ~70 columns behind on the published last row of the strip above.
 //     The data-dependent number of sweeps (epic_aux.cpp:170-178) is decided on the device: all 40 sweep kernels are queued,
 //     the ones beyond end_iter return at once.
 //   * Neighbourhood graph: every label border emits (row, col, d) in both directions; radix sort by (row, col) and a
@@ -126,15 +126,14 @@ struct DtCtrl {
     int ticket[DT_MAX_SWEEPS + 1];
 };
 struct DtSweepArgs {
-    int W, H, TX, TY;
+    int W, H, NS, NB; // image, strips of 32 rows, blocks of 32 columns
     const float *cost;
     float *A;
     int *L;
     int sx, sy;       // sweep direction (+1 / -1)
     int k;            // sweep index, 1-based
     DtCtrl *ctrl;
-    int *done;        // per tile: index of the last sweep that finished it
-    const int *wave_start; // TX + TY entries: first ticket of every anti-diagonal of tiles
+    int *prog;        // per strip (in sweep order): k * 65536 + column blocks finished and stored in sweep k
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
@@ -143,6 +142,9 @@ __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
     return v;
 }
 __device__ __forceinline__ void st_release_gpu(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 
 // one arg_sweep update (epic_aux.cpp:118-148), operation for operation, without FMA contraction
 __device__ __forceinline__ void dt_update(float t1, int l1, float t2, int l2, float C, float &a, int &l, float &maxdiff) {
@@ -164,124 +166,128 @@ __device__ __forceinline__ void dt_update(float t1, int l1, float t2, int l2, fl
     }
 }
 
-constexpr int DT_WARPS = 2; // warps (= tiles in flight) per block: 3 x 4.25 KB of staging each
-// bounded spin on a predecessor tile's done-flag: a protocol error traps instead of hanging the GPU
-__device__ __forceinline__ void dt_wait(const int *flag, int k) {
+// One raster sweep of arg_sweep as a pipeline of row strips.  In sweep coordinates (p along x, q along y, both in the
+// direction of the sweep) pixel (p, q) needs (p-1, q) and (p, q-1) of the SAME sweep.  A warp owns a strip of 32 rows
+// (lane = row) and marches along p: at step s lane l updates column s - l, so its left neighbour is its own previous
+// result (a register) and its upper neighbour is what lane l-1 produced one step earlier (a shuffle) -- a 32-row
+// wavefront that never leaves the register file.  The strip below follows about 70 columns behind: it takes the last row
+// of this strip from global memory, block of 32 columns by block, as soon as the block has been stored and published
+// (release / acquire on a per-strip progress word).  Strips are handed out in sweep order by an atomic ticket, so a strip
+// only ever waits for one that is already running.  The tile data moves global -> shared with cp.async one block ahead
+// and back with coalesced row stores two blocks behind; a 3-slot ring holds the blocks in flight.
+constexpr int DT_RING = 3;
+// bounded spin on the progress word of the strip above: a protocol error traps instead of hanging the GPU
+__device__ __forceinline__ void dt_wait(const int *flag, int need) {
     unsigned spins = 0;
-    while (ld_acquire_gpu(flag) != k) {
-        __nanosleep(64); // back off: thousands of polling warps would otherwise flood the L2 the working tiles need
+    while (ld_acquire_gpu(flag) < need) {
+        __nanosleep(32);
         if (++spins > (1u << 24)) __trap();
     }
 }
-__global__ void __launch_bounds__(DT_WARPS * 32) k_dt_sweep(DtSweepArgs a) {
+__global__ void __launch_bounds__(32) k_dt_sweep(DtSweepArgs a) {
     if (a.k > *reinterpret_cast<volatile int *>(&a.ctrl->end_iter)) return;
-    __shared__ float sA[DT_WARPS][DT_TILE * DT_PITCH], sC[DT_WARPS][DT_TILE * DT_PITCH];
-    __shared__ int sL[DT_WARPS][DT_TILE * DT_PITCH];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *tA = sA[warp], *tC = sC[warp];
-    int *tL = sL[warp];
-    const int ntiles = a.TX * a.TY, nwaves = a.TX + a.TY - 1;
+    __shared__ float sA[DT_RING][DT_TILE * DT_PITCH], sC[DT_RING][DT_TILE * DT_PITCH];
+    __shared__ int sL[DT_RING][DT_TILE * DT_PITCH];
+    __shared__ float hT[DT_RING][DT_TILE];
+    __shared__ int hL[DT_RING][DT_TILE];
+    const int lane = threadIdx.x;
     const float INF = __int_as_float(0x7f800000);
-    float maxdiff = 0.0f;
-    for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(&a.ctrl->ticket[a.k], 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= ntiles) break;
-        // ticket -> (wave, position) -> tile in sweep coordinates (ta, tb) -> actual tile (cx, cy)
-        int lo = 0, hi = nwaves - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (a.wave_start[mid] <= t) lo = mid; else hi = mid - 1;
-        }
-        const int wave = lo, pos = t - a.wave_start[wave];
-        const int ta = max(0, wave - a.TY + 1) + pos, tb = wave - ta;
-        const int cx = a.sx > 0 ? ta : a.TX - 1 - ta, cy = a.sy > 0 ? tb : a.TY - 1 - tb;
-        const int x0 = cx * DT_TILE, y0 = cy * DT_TILE;
-        const int tw = min(DT_TILE, a.W - x0), th = min(DT_TILE, a.H - y0);
-        // wait for the two predecessor tiles of this sweep
-        if (lane == 0) {
-            if (ta > 0) dt_wait(a.done + cy * a.TX + (cx - a.sx), a.k);
-            if (tb > 0) dt_wait(a.done + (cy - a.sy) * a.TX + cx, a.k);
-        }
-        __syncwarp();
-        // stage the tile (coalesced rows) in sweep coordinates: local (p, q) <-> pixel (x0 + (sx>0 ? p : tw-1-p), y0 + ...)
-        // (all loads of the tile are issued before the first one is stored: a rolled load-store loop would serialise 32 L2
-        // round trips -- that was 22 of the 25 us a tile took in the first version)
-        {
-            float ra[DT_TILE], rc[DT_TILE];
-            int rl[DT_TILE];
-            const int i = x0 + (a.sx > 0 ? lane : tw - 1 - lane);
-#pragma unroll
-            for (int q = 0; q < DT_TILE; q++) {
-                const int j = y0 + (a.sy > 0 ? q : th - 1 - q);
-                const bool ok = q < th && lane < tw;
-                const size_t o = ok ? (size_t)j * a.W + i : 0;
-                ra[q] = ok ? __ldcg(a.A + o) : 0.0f;
-                rl[q] = ok ? __ldcg(a.L + o) : 0;
-                rc[q] = ok ? __ldg(a.cost + o) : 0.0f;
-            }
-#pragma unroll
-            for (int q = 0; q < DT_TILE; q++) {
-                tA[q * DT_PITCH + lane] = ra[q];
-                tL[q * DT_PITCH + lane] = rl[q];
-                tC[q * DT_PITCH + lane] = rc[q];
+    int strip = 0;
+    if (lane == 0) strip = atomicAdd(&a.ctrl->ticket[a.k], 1);
+    strip = __shfl_sync(0xffffffffu, strip, 0);
+    if (strip >= a.NS) return;
+    const int W = a.W, H = a.H, q0 = strip * DT_TILE, rows = min(DT_TILE, H - q0);
+    const bool row_ok = lane < rows;
+    const int jtop = (a.sy > 0) ? q0 - 1 : H - q0; // image row of sweep row q0 - 1 (the last row of the strip above)
+    const int base = a.k << 16;
+
+    auto load_block = [&](int m) { // A, L, cost of columns 32m .. 32m+31, all rows of the strip: lane = column (coalesced)
+        const int slot = m % DT_RING, p = m * DT_TILE + lane;
+        if (p < W) {
+            const int i = a.sx > 0 ? p : W - 1 - p;
+#pragma unroll 8
+            for (int r = 0; r < rows; r++) {
+                const size_t o = (size_t)(a.sy > 0 ? q0 + r : H - 1 - (q0 + r)) * W + i;
+                cp_async4(&sA[slot][r * DT_PITCH + lane], a.A + o);
+                cp_async4(&sL[slot][r * DT_PITCH + lane], a.L + o);
+                cp_async4(&sC[slot][r * DT_PITCH + lane], a.cost + o);
             }
         }
-        __syncwarp();
-        // lane = row q of the tile (sweep order); left neighbour of column 0 from the tile before in x
-        const int q = lane;
-        float left_t = INF;
-        int left_l = -1;
-        if (q < th && ta > 0) {
-            const int j = y0 + (a.sy > 0 ? q : th - 1 - q), i = (a.sx > 0) ? x0 - 1 : x0 + tw;
-            left_t = __ldcg(a.A + (size_t)j * a.W + i);
-            left_l = __ldcg(a.L + (size_t)j * a.W + i);
-        }
-        float cur_t = 0.0f;   // value this lane produced in the previous step (its column p - 1)
-        int cur_l = 0;
-        // row above the tile in sweep order (the upper neighbours of local row 0): lane p holds column p
-        float top_t = INF;
-        int top_l = -1;
-        if (tb > 0 && lane < tw) {
-            const int jup = (a.sy > 0) ? y0 - 1 : y0 + th, i = x0 + (a.sx > 0 ? lane : tw - 1 - lane);
-            top_t = __ldcg(a.A + (size_t)jup * a.W + i);
-            top_l = __ldcg(a.L + (size_t)jup * a.W + i);
-        }
-        for (int s = 0; s < tw + th - 1; s++) {
-            // the upper neighbour of (p, q) is what lane q - 1 produced in the previous step
-            float up_t = __shfl_up_sync(0xffffffffu, cur_t, 1);
-            int up_l = __shfl_up_sync(0xffffffffu, cur_l, 1);
-            const int p = s - q;
-            const float halo_t = __shfl_sync(0xffffffffu, top_t, s & 31); // local row 0 is at column p = s in this step
-            const int halo_l = __shfl_sync(0xffffffffu, top_l, s & 31);
-            if (q < th && p >= 0 && p < tw) {
-                if (q == 0) { up_t = halo_t; up_l = halo_l; }
-                const float t2 = (p == 0) ? left_t : cur_t;
-                const int l2 = (p == 0) ? left_l : cur_l;
-                float av = tA[q * DT_PITCH + p];
-                int lv = tL[q * DT_PITCH + p];
-                dt_update(up_t, up_l, t2, l2, tC[q * DT_PITCH + p], av, lv, maxdiff);
-                tA[q * DT_PITCH + p] = av;
-                tL[q * DT_PITCH + p] = lv;
-                cur_t = av;
-                cur_l = lv;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto store_block = [&](int m) {
+        const int slot = m % DT_RING, p = m * DT_TILE + lane;
+        if (p < W) {
+            const int i = a.sx > 0 ? p : W - 1 - p;
+#pragma unroll 8
+            for (int r = 0; r < rows; r++) {
+                const size_t o = (size_t)(a.sy > 0 ? q0 + r : H - 1 - (q0 + r)) * W + i;
+                a.A[o] = sA[slot][r * DT_PITCH + lane];
+                a.L[o] = sL[slot][r * DT_PITCH + lane];
             }
         }
-        __syncwarp();
-        for (int qq = 0; qq < th; qq++) {
-            const int j = y0 + (a.sy > 0 ? qq : th - 1 - qq);
-            if (lane < tw) {
-                const int i = x0 + (a.sx > 0 ? lane : tw - 1 - lane);
-                const size_t o = (size_t)j * a.W + i;
-                a.A[o] = tA[qq * DT_PITCH + lane];
-                a.L[o] = tL[qq * DT_PITCH + lane];
-            }
-        }
+    };
+    auto publish = [&](int blocks_done) {
         __threadfence();
         __syncwarp();
-        if (lane == 0) st_release_gpu(a.done + cy * a.TX + cx, a.k);
+        if (lane == 0) st_release_gpu(a.prog + strip, base + blocks_done);
+    };
+
+    load_block(0);
+    float cur_t = INF, maxdiff = 0.0f;
+    int cur_l = -1, stored = 0;
+    const int nsteps = W + DT_TILE - 1;
+    for (int s = 0; s < nsteps; s++) {
+        if ((s & (DT_TILE - 1)) == 0) {
+            const int m = s >> 5; // lane 0 enters block m now; lane 31 left block m-2 in the previous step
+            __syncwarp();
+            if (m - 2 >= stored) {
+                store_block(m - 2);
+                stored = m - 1;
+                publish(stored);
+            }
+            __syncwarp();
+            if (m + 1 < a.NB) load_block(m + 1);                       // into the slot block m-2 just left
+            else asm volatile("cp.async.commit_group;" ::: "memory");  // (keeps the group count uniform)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");       // block m has landed
+            if (m < a.NB) {                                            // last row of the strip above, block m
+                const int slot = m % DT_RING, p = m * DT_TILE + lane;
+                float t = INF;
+                int l = -1;
+                if (strip > 0) {
+                    if (lane == 0) dt_wait(a.prog + strip - 1, base + m + 1);
+                    __syncwarp();
+                    if (p < W) {
+                        const int i = a.sx > 0 ? p : W - 1 - p;
+                        t = __ldcg(a.A + (size_t)jtop * W + i);
+                        l = __ldcg(a.L + (size_t)jtop * W + i);
+                    }
+                }
+                hT[slot][lane] = t;
+                hL[slot][lane] = l;
+            }
+            __syncwarp();
+        }
+        const int p = s - lane;
+        float up_t = __shfl_up_sync(0xffffffffu, cur_t, 1);
+        int up_l = __shfl_up_sync(0xffffffffu, cur_l, 1);
+        if (row_ok && p >= 0 && p < W) {
+            const int slot = (p >> 5) % DT_RING, col = p & (DT_TILE - 1), at = lane * DT_PITCH + col;
+            if (lane == 0) { up_t = hT[slot][col]; up_l = hL[slot][col]; }
+            const float t2 = (p == 0) ? INF : cur_t;
+            const int l2 = (p == 0) ? -1 : cur_l;
+            float av = sA[slot][at];
+            int lv = sL[slot][at];
+            dt_update(up_t, up_l, t2, l2, sC[slot][at], av, lv, maxdiff);
+            sA[slot][at] = av;
+            sL[slot][at] = lv;
+            cur_t = av;
+            cur_l = lv;
+        }
     }
+    __syncwarp();
+    for (int m = stored; m < a.NB; m++) store_block(m);
+    publish(a.NB);
     for (int off = 16; off > 0; off >>= 1) maxdiff = fmaxf(maxdiff, __shfl_xor_sync(0xffffffffu, maxdiff, off));
     if (lane == 0 && maxdiff > 0.0f) atomicMax(&a.ctrl->maxdiff[a.k], __float_as_uint(maxdiff));
 }
@@ -592,8 +598,7 @@ struct EpicTrace {
 };
 
 struct EpicGeo {
-    int W, H, TX, TY;
-    std::vector<int> wave_start;
+    int W, H;
 };
 
 // dist_trf_nnfield_subset with the seeds as query points, followed by the kernel weights: fills qnn / qw (ns x nn) and
@@ -605,12 +610,11 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
     ArenaScope scope; // (the caller's buffers were allocated before; the stream is idle when the scratch is released)
     const int W = eg.W, H = eg.H;
     const size_t N = (size_t)W * H;
-    const int ntiles = eg.TX * eg.TY;
-    DevBuf ctrl, done, waves;
-    if (!ctrl.alloc(sizeof(DtCtrl)) || !done.alloc(ntiles * sizeof(int)) || !waves.alloc(eg.wave_start.size() * sizeof(int))) return SFGPU_ERR_CUDA;
+    const int NS = (H + DT_TILE - 1) / DT_TILE, NB = (W + DT_TILE - 1) / DT_TILE;
+    DevBuf ctrl, prog;
+    if (!ctrl.alloc(sizeof(DtCtrl)) || !prog.alloc((size_t)NS * sizeof(int))) return SFGPU_ERR_CUDA;
     SF_CUDA(cudaMemsetAsync(ctrl.p, 0, sizeof(DtCtrl), st));
-    SF_CUDA(cudaMemsetAsync(done.p, 0, ntiles * sizeof(int), st));
-    SF_CUDA(cudaMemcpyAsync(waves.p, eg.wave_start.data(), eg.wave_start.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    SF_CUDA(cudaMemsetAsync(prog.p, 0, (size_t)NS * sizeof(int), st));
     {
         const int four = 4;
         SF_CUDA(cudaMemcpyAsync(&ctrl.as<DtCtrl>()->end_iter, &four, sizeof(int), cudaMemcpyHostToDevice, st)); // end_iter = 4 (:168)
@@ -619,24 +623,23 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
     k_fill_u32<<<592, 256, 0, st>>>(N, reinterpret_cast<unsigned *>(d_labels), 0xFFFFFFFFu);
     k_dt_seed_labels<<<(ns + 255) / 256, 256, 0, st>>>(ns, d_seeds, W, d_labels);
     k_dt_seed_dist<<<(ns + 255) / 256, 256, 0, st>>>(ns, d_seeds, W, d_cost, d_dmap);
-    // sweeps i = 1 .. : direction (x[i % 4], y[i % 4]) with x = {-1, 1, 1, -1}, y = {1, 1, -1, -1} (:165-172)
+    // sweeps i = 1 .. : direction (x[i % 4], y[i % 4]) with x = {-1, 1, 1, -1}, y = {1, 1, -1, -1} (:165-172).  One warp
+    // per strip of 32 rows; every strip must be resident together with the one above it: tickets hand the strips out in
+    // sweep order, and the grid (one block per strip) is far below the 148 x 32 resident blocks for any real image
     static const int dx[4] = {-1, 1, 1, -1}, dy[4] = {1, 1, -1, -1};
-    int sm_blocks = 0;
-    SF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sm_blocks, k_dt_sweep, DT_WARPS * 32, 0));
-    // an anti-diagonal of tiles holds at most min(TX, TY) tiles: more warps than about twice that only poll
-    const int useful_warps = 2 * std::min(eg.TX, eg.TY) + 2;
-    const int grid = std::max(1, std::min({(ntiles + DT_WARPS - 1) / DT_WARPS, (useful_warps + DT_WARPS - 1) / DT_WARPS,
-                                           c->num_sms * std::max(1, sm_blocks)}));
+    if (NS > c->num_sms * 16) {
+        set_error("sfgpu_epic: image too tall for the strip pipeline of the distance transform");
+        return SFGPU_ERR_UNSUPPORTED;
+    }
     for (int k = 1; k <= DT_MAX_SWEEPS; k++) {
         DtSweepArgs a;
-        a.W = W; a.H = H; a.TX = eg.TX; a.TY = eg.TY;
+        a.W = W; a.H = H; a.NS = NS; a.NB = NB;
         a.cost = d_cost; a.A = d_dmap; a.L = d_labels;
         a.sx = dx[k % 4]; a.sy = dy[k % 4];
         a.k = k;
         a.ctrl = ctrl.as<DtCtrl>();
-        a.done = done.as<int>();
-        a.wave_start = waves.as<int>();
-        k_dt_sweep<<<grid, DT_WARPS * 32, 0, st>>>(a);
+        a.prog = prog.as<int>();
+        k_dt_sweep<<<NS, 32, 0, st>>>(a);
         k_dt_control<<<1, 1, 0, st>>>(ctrl.as<DtCtrl>(), k, 1.0f, DT_MAX_SWEEPS); // default dt_params: max_iter 40, min_change 1 (:151-154)
     }
     c->prof_acc.kernel_launches += 4 + 2 * DT_MAX_SWEEPS;
@@ -805,17 +808,6 @@ static int epic_impl(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_i
 
     EpicGeo eg;
     eg.W = W; eg.H = H;
-    eg.TX = (W + DT_TILE - 1) / DT_TILE;
-    eg.TY = (H + DT_TILE - 1) / DT_TILE;
-    {
-        int acc = 0;
-        for (int w = 0; w < eg.TX + eg.TY - 1; w++) {
-            eg.wave_start.push_back(acc);
-            const int lo = std::max(0, w - eg.TY + 1), hi = std::min(w, eg.TX - 1);
-            acc += hi - lo + 1;
-        }
-        eg.wave_start.push_back(acc);
-    }
 
     auto seeds_of = [&](std::vector<int> &seeds, std::vector<float> &vects) { // matches_to_seeds / matches_to_vects (:30-57)
         seeds.resize((size_t)nm * 2);
@@ -985,14 +977,6 @@ static int nnfield_impl(sfgpu_ctx *c, int *best, float *dist, int *labels, const
     const size_t N = (size_t)w * h;
     EpicGeo eg;
     eg.W = w; eg.H = h;
-    eg.TX = (w + DT_TILE - 1) / DT_TILE;
-    eg.TY = (h + DT_TILE - 1) / DT_TILE;
-    int acc = 0;
-    for (int k = 0; k < eg.TX + eg.TY - 1; k++) {
-        eg.wave_start.push_back(acc);
-        acc += std::min(k, eg.TX - 1) - std::max(0, k - eg.TY + 1) + 1;
-    }
-    eg.wave_start.push_back(acc);
     DevBuf d_cost, d_labels, d_dmap, d_seeds, d_qnn, d_qw;
     if (!d_cost.alloc(N * 4) || !d_labels.alloc(N * 4) || !d_dmap.alloc(N * 4) || !d_seeds.alloc((size_t)ns * 8) || !d_qnn.alloc((size_t)ns * nn * 4) ||
         !d_qw.alloc((size_t)ns * nn * 4))
