@@ -744,7 +744,9 @@ template <typename F> static int with_arena(sfgpu_ctx *c, size_t first_guess, F 
     if (!c->epic_arena) c->epic_arena = new EpicArena();
     EpicArena *ar = c->epic_arena;
     for (int attempt = 0; attempt < 4; attempt++) {
-        const size_t want = std::max(first_guess, ar->high + ar->high / 8);
+        // first call: the estimate; after an overflow: the recorded high-water mark plus a margin.  A call that fits
+        // never touches the allocation.
+        const size_t want = ar->overflow ? ar->high + ar->high / 4 : std::max(ar->cap, first_guess);
         if (want > ar->cap) {
             SF_CUDA(cudaStreamSynchronize(c->stream));
             if (ar->base) cudaFree(ar->base);
@@ -754,6 +756,7 @@ template <typename F> static int with_arena(sfgpu_ctx *c, size_t first_guess, F 
             ar->cap = want;
         }
         ar->off = 0;
+        ar->high = 0;
         ar->overflow = false;
         g_arena = ar;
         const int rc = body();
