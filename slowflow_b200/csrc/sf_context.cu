@@ -363,7 +363,7 @@ int sfgpu_synchronize(sfgpu_ctx *c) {
 }
 
 int sfgpu_set_sor_variant(sfgpu_ctx *c, int variant) {
-    if (!c || variant < 0 || variant > 1) return SFGPU_ERR_ARG;
+    if (!c || variant < 0 || variant > 2) return SFGPU_ERR_ARG;
     c->sor_variant = variant;
     return SFGPU_OK;
 }

@@ -94,13 +94,17 @@ __device__ __forceinline__ void term_mt_succ(const Derivs &d, float u, float v, 
                                              const float wc[3], int dt_norm, const Penalty &pc, const Penalty &pg, Acc &acc) {
     const float dnorm = 0.1f * 0.1f;
     const float f = s, f1 = s + 1.0f;
+    const float g = f - f1;
     if (wd != 0.0f) {
+        // The reference writes the effective gradient of the pair as s*I - (s+1)*I and expands the residual term by term
+        // (variational_aux_mt.cpp:196-215); s - (s+1) is exactly -1 in float for every time factor the path uses, so the
+        // gradient is g*I with g = f - f1 and the residual folds to Iz + gx*u + gy*v (same value up to the rounding order).
         float r[3], gx[3], gy[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            r[c] = wc[c] * (d.iz[c] + d.ix[c] * f * u + d.iy[c] * f * v - d.ix[c] * f1 * u - d.iy[c] * f1 * v);
-            gx[c] = f * d.ix[c] - f1 * d.ix[c];
-            gy[c] = f * d.iy[c] - f1 * d.iy[c];
+            gx[c] = g * d.ix[c];
+            gy[c] = g * d.iy[c];
+            r[c] = wc[c] * (d.iz[c] + gx[c] * u + gy[c] * v);
         }
         if (!dt_norm) {
             const float t = m * wd * penalty_deriv_v(pc, r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
@@ -132,11 +136,11 @@ __device__ __forceinline__ void term_mt_succ(const Derivs &d, float u, float v, 
     float rx[3], ry[3], gxx[3], gyy[3], gxy[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        rx[c] = wc[c] * (d.ixz[c] + d.ixx[c] * f * u + d.ixy[c] * f * v - d.ixx[c] * f1 * u - d.ixy[c] * f1 * v);
-        ry[c] = wc[c] * (d.iyz[c] + d.ixy[c] * f * u + d.iyy[c] * f * v - d.ixy[c] * f1 * u - d.iyy[c] * f1 * v);
-        gxx[c] = f * d.ixx[c] - f1 * d.ixx[c];
-        gyy[c] = f * d.iyy[c] - f1 * d.iyy[c];
-        gxy[c] = f * d.ixy[c] - f1 * d.ixy[c];
+        gxx[c] = g * d.ixx[c];
+        gyy[c] = g * d.iyy[c];
+        gxy[c] = g * d.ixy[c];
+        rx[c] = wc[c] * (d.ixz[c] + gxx[c] * u + gxy[c] * v);
+        ry[c] = wc[c] * (d.iyz[c] + gxy[c] * u + gyy[c] * v);
     }
     if (!dt_norm) {
         const float t = m * wg * penalty_deriv_v(pg, rx[0] * rx[0] + ry[0] * ry[0] + rx[1] * rx[1] + ry[1] * ry[1] +

@@ -171,6 +171,7 @@ struct SorPlan {
     CUtensorMap tmap;       // 3-D (x, y, plane) views of the arena: box = a warp's strip of the 7 coefficient planes,
     CUtensorMap tmap_iter;  //   ... of a du,dv plane pair,
     CUtensorMap tmap_row;   //   ... one row of one plane
+    CUtensorMap tmap_s_coef, tmap_s_iter, tmap_s_row; // the same three views with the boxes of the streaming kernel
     bool tmap_valid = false;
     int num_sms = 0;
 };
@@ -181,9 +182,13 @@ bool data_term_device_init();
 bool sor_plan_init(SorPlan &plan, Geom g, float *arena, int num_sms);
 // Runs `iterations` sweeps; the iterate starts in (duA,dvA) when *cur==0 or (duB,dvB) when *cur==1 and
 // *cur is updated to the buffer holding the result.  zero_init: treat the initial iterate as 0.
-// variant 0: tiled / temporally blocked (fuse sweeps per launch), variant 1: one launch per half sweep.
+// variant 0: tiled / temporally blocked (fuse sweeps per launch), variant 1: one launch per half sweep,
+// variant 2: streaming wavefront (sf_sor_stream.cu).
 // Returns the number of kernel launches issued (negative on error).
 int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int variant, int fuse, int *cur,
                bool zero_init);
+bool sor_stream_device_init();
+void sor_stream_boxes(unsigned boxes[3][3]);
+int launch_sor_stream(cudaStream_t st, SorPlan &plan, int iterations, float omega, int fuse, int *cur, bool zero_init);
 
 } // namespace sf

@@ -20,6 +20,7 @@
 // Variant 1 (validation, tiny images): one launch per half sweep straight from global memory.
 #include "sf_internal.cuh"
 #include "sf_pack.cuh"
+#include "sf_tma.cuh"
 
 #ifndef SF_SOR_NW
 #define SF_SOR_NW 8
@@ -95,44 +96,6 @@ struct SorTiledArgs {
     float one;      // 1.0f, opaque to the compiler (see ldp in k_sor_tiled)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// bounded spin: a TMA that never completes (bad descriptor) traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
-        : "memory");
-}
-
 // Per-lane register tile: pixel columns {2l, 2l+1} of the warp's 8 rows.  Every quantity is held as a
 // packed pair (row p, row p+4) of one column in ONE 64-bit register so that the whole relaxation runs on
 // packed-fp32 FFMA2 (fma.rn.f32x2, sm_100): both rows of a pair have the same colour in a given column.
@@ -206,16 +169,6 @@ __device__ __forceinline__ void sor_relax_range(SorRegs &q, const float2 up, con
         if (!SF_SOR_SKIP || k < pdepth[P]) sor_relax_pair<C, P>(q, up, dn, nomega2);
         sor_relax_range<C, P + 1, PEND>(q, up, dn, nomega2, k, pdepth);
     }
-}
-
-// shared-memory flag helpers for the warp-to-warp hand-shake
-__device__ __forceinline__ void st_release_shared(int *p, int v) {
-    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_shared(const int *p) {
-    int v;
-    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
 }
 
 __global__ void __launch_bounds__(SOR_NW * 32, 1)
@@ -461,7 +414,7 @@ bool sor_device_init() {
         set_error("cudaFuncSetAttribute(k_sor_tiled) failed");
         return false;
     }
-    return true;
+    return sor_stream_device_init();
 }
 
 bool sor_plan_init(SorPlan &plan, Geom g, float *arena, int num_sms) {
@@ -479,9 +432,12 @@ bool sor_plan_init(SorPlan &plan, Geom g, float *arena, int num_sms) {
     const cuuint64_t dims[3] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)SP_COUNT};
     const cuuint64_t strides[2] = {(cuuint64_t)g.S * 4, (cuuint64_t)g.plane() * 4};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const cuuint32_t boxes[3][3] = {{SOR_TW, SOR_R, 7}, {SOR_TW, SOR_R, 2}, {SOR_TW, 1, 1}};
-    CUtensorMap *maps[3] = {&plan.tmap, &plan.tmap_iter, &plan.tmap_row};
-    for (int m = 0; m < 3; m++) {
+    unsigned sb[3][3];
+    sor_stream_boxes(sb);
+    const cuuint32_t boxes[6][3] = {{SOR_TW, SOR_R, 7}, {SOR_TW, SOR_R, 2}, {SOR_TW, 1, 1},
+                                    {sb[0][0], sb[0][1], sb[0][2]}, {sb[1][0], sb[1][1], sb[1][2]}, {sb[2][0], sb[2][1], sb[2][2]}};
+    CUtensorMap *maps[6] = {&plan.tmap, &plan.tmap_iter, &plan.tmap_row, &plan.tmap_s_coef, &plan.tmap_s_iter, &plan.tmap_s_row};
+    for (int m = 0; m < 6; m++) {
         const CUresult r = enc(maps[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, arena, dims, strides, boxes[m], estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -527,6 +483,7 @@ int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int 
         }
         return launches;
     }
+    if (variant == 2) return launch_sor_stream(st, plan, iterations, omega, fuse, cur, zero_init);
     if (fuse < 1) fuse = 1;
     const int max_fuse = (SOR_TH - 4) / 4 < 7 ? (SOR_TH - 4) / 4 : 7; // the halo (2*fuse per side) must leave an interior
     if (fuse > max_fuse) fuse = max_fuse;

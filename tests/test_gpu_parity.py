@@ -176,11 +176,34 @@ def test_sor_tiled_matches_cpu_redblack(ctx, oracle, w, h, fuse):
         assert relerr(Ag[k].array, Ar[k].array) < 1e-5
 
 
+@pytest.mark.parametrize("w,h", [(20, 17), (64, 64), (131, 77), (300, 200), (523, 301), (1024, 436)])
+@pytest.mark.parametrize("fuse,iters", [(4, 30), (1, 5), (3, 7), (2, 4)])
+def test_sor_streaming_matches_cpu_redblack(ctx, oracle, w, h, fuse, iters):
+    """Variant 2 (sf_sor_stream.cu): wavefront over strips of 256 columns / row segments; ragged strips, segments shorter
+    than the 18-row window, several strips and segments, non-zero initial iterate."""
+    s = _sor_inputs(oracle, w, h)
+    du0, dv0 = helpers.rng_plane(w, h, 11, -0.2, 0.2), helpers.rng_plane(w, h, 12, -0.2, 0.2)
+    Ar = [a.copy() for a in s["A"]]
+    rdu, rdv = du0.copy(), dv0.copy()
+    oracle.lib.sfo_sor_coupled(rdu.ptr(), rdv.ptr(), *[a.ptr() for a in Ar], s["sh"].ptr(), s["sv"].ptr(), iters, 1.9,
+                               SOR_REDBLACK)
+    ctx.set_sor_variant(2)
+    ctx.set_sor_fuse(fuse)
+    try:
+        Ag = [a.copy() for a in s["A"]]
+        gdu, gdv = du0.copy(), dv0.copy()
+        ctx.sor_coupled(gdu, gdv, *Ag, s["sh"], s["sv"], iters, 1.9)
+    finally:
+        ctx.set_sor_fuse(0)
+        ctx.set_sor_variant(0)
+    assert helpers.maxdiff(gdu.array, rdu.array) < 2e-4 and helpers.maxdiff(gdv.array, rdv.array) < 2e-4
+
+
 def test_sor_variants_agree(ctx, oracle):
     w, h = 257, 131
     s = _sor_inputs(oracle, w, h)
     outs = []
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         ctx.set_sor_variant(variant)
         A = [a.copy() for a in s["A"]]
         du, dv = Image(w, h), Image(w, h)
@@ -188,6 +211,8 @@ def test_sor_variants_agree(ctx, oracle):
         outs.append((du.array.copy(), dv.array.copy()))
     ctx.set_sor_variant(0)
     assert helpers.maxdiff(outs[0][0], outs[1][0]) < 1e-5 and helpers.maxdiff(outs[0][1], outs[1][1]) < 1e-5
+    # the tiled and the streaming kernel run the same FMA chain per pixel and half sweep: identical bits
+    assert np.array_equal(outs[0][0], outs[2][0]) and np.array_equal(outs[0][1], outs[2][1])
 
 
 # ------------------------------------------------------------------ end to end, two-frame

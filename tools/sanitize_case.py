@@ -34,4 +34,30 @@ with Context(0) as ctx:
     for a in wxs + wys:
         a.buf[:] = 0
     ctx.variational_sequence(frames, wxs, wys, None)
-print("sanitize_case: done")
+    # round 2: integer-frame sequence (unpack kernel, resident ring), device min-cut, per-term data variant, EPIC
+    from slowflow_b200 import synth  # noqa: E402
+    w, h, n = 70, 50, 3
+    raws = [np.ascontiguousarray(np.moveaxis(np.rint(synth.frame(w, h, t)).astype(np.uint8), 0, 2)) for t in range(n + 1)]
+    u0, v0 = synth.initial_flow(w, h)
+    xs, ys = [Image.from_array(u0) for _ in range(n)], [Image.from_array(v0) for _ in range(n)]
+    p = variational_params_default()
+    p.niter_outer, p.niter_solver = 2, 7
+    ctx.variational_sequence_int(raws[:3], xs[:2], ys[:2], p)
+    ctx.variational_sequence_int(raws[2:], xs[2:], ys[2:], p, continue_from_previous=True)
+    import ctypes as C  # noqa: E402
+    r = np.random.RandomState(1)
+    d0, d1 = r.rand(37 * 23).astype(np.float32), r.rand(37 * 23).astype(np.float32)
+    lab = np.zeros(37 * 23, np.int32)
+    FP, IPi = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    assert ctx.lib.sfgpu_grid_mincut_dev(ctx.h, 37, 23, d0.ctypes.data_as(FP), d1.ctypes.data_as(FP), C.c_float(0.2), 0,
+                                         lab.ctypes.data_as(IPi), None) == 0
+    im, m, edges = synth.epic_case(97, 61, 120)
+    fx, fy = Image(97, 61), Image(97, 61)
+    ctx.epic(fx, fy, ColorImage.from_array(im), m, edges, None)
+    assert np.isfinite(fx.array).all()
+os.environ["SLOWFLOW_GPU_MT_DATA_VARIANT"] = "1"
+with Context(0) as ctx:
+    ims, wx, wy = mh.window(97, 71, 3)
+    g = mh.run_gpu(ctx, ims, wx, wy, mh.params(3, niter_alter=2, niter_outer=2))
+    assert np.isfinite(g["wx"].array).all()
+print("sanitize_case: ok")
