@@ -237,6 +237,13 @@ int sfgpu_profile_get(sfgpu_ctx *ctx, sfgpu_profile_t *out); /* synchronises the
 /* variational_aux.c:18 / variational_aux_mt.cpp:722 (factor) ; mask may be NULL */
 int sfgpu_image_warp(sfgpu_ctx *ctx, color_image_t *dst, image_t *mask, const color_image_t *src,
                      const image_t *wx, const image_t *wy, int factor);
+/* The multi-frame path's per-frame pass as an operator: image_warp with its time factor (variational_aux_mt.cpp:722)
+ * followed by the five spatial derivative images of the WARPED frame (the filters and border rules of get_derivatives,
+ * variational_mt.cpp:111-166, image.c:400-526).  variant 0 = the production kernel (one fused marching pass,
+ * sf_wderivs.cu), variant 1 = the two-kernel path it replaced (A/B reference). */
+int sfgpu_warp_frame_derivs(sfgpu_ctx *ctx, const color_image_t *src, const image_t *wx, const image_t *wy, int factor,
+                            int variant, color_image_t *warped, image_t *mask, color_image_t *dx, color_image_t *dy,
+                            color_image_t *dxx, color_image_t *dxy, color_image_t *dyy);
 /* variational_aux.c:183 (coef = 5, deriv = 5-tap); result written into dst.
  * MT variant (variational_aux_mt.cpp:673): avg/std/hbit de-normalisation; pass NULL for two-frame. */
 int sfgpu_compute_dpsis_weight(sfgpu_ctx *ctx, image_t *dst, const color_image_t *im, float coef,

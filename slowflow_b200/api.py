@@ -62,7 +62,7 @@ ABI_SYMBOLS = [
     "sfgpu_variational", "sfgpu_variational_dev", "sfgpu_variational_sequence", "sfgpu_variational_sequence_u8",
     "sfgpu_variational_sequence_u16", "sfgpu_host_register",
     "sfgpu_host_unregister", "sfgpu_variational_mt", "sfgpu_normalize", "sfgpu_get_mt_stats", "sfgpu_profile_enable",
-    "sfgpu_profile_reset", "sfgpu_profile_get", "sfgpu_image_warp", "sfgpu_compute_dpsis_weight",
+    "sfgpu_profile_reset", "sfgpu_profile_get", "sfgpu_image_warp", "sfgpu_warp_frame_derivs", "sfgpu_compute_dpsis_weight",
     "sfgpu_compute_smoothness", "sfgpu_compute_data_and_match", "sfgpu_prep_two_frame", "sfgpu_sub_laplacian", "sfgpu_sor_coupled",
     "sfgpu_epic", "sfgpu_epic_nnfield", "epic_params_default", "sfgpu_version", "sfgpu_grid_mincut", "sfgpu_grid_mincut_dev", "sfgpu_prescale_size", "sfgpu_prescale", "sfgpu_raw_weighting",
     "sfgpu_write_flo", "sfgpu_read_flo_size", "sfgpu_read_flo", "sfgpu_write_occlusion_pbm", "sfgpu_set_device", "sfgpu_get_device",
@@ -112,6 +112,7 @@ def load_library(path=None):
     lib.sfgpu_profile_reset.argtypes = [C.c_void_p]
     lib.sfgpu_profile_get.argtypes = [C.c_void_p, C.POINTER(Profile)]
     lib.sfgpu_image_warp.argtypes = [C.c_void_p, CP, IP, CP, IP, IP, C.c_int]
+    lib.sfgpu_warp_frame_derivs.argtypes = [C.c_void_p, CP, IP, IP, C.c_int, C.c_int, CP, IP, CP, CP, CP, CP, CP]
     lib.sfgpu_compute_dpsis_weight.argtypes = [C.c_void_p, IP, CP, C.c_float, FP, FP, C.c_int]
     lib.sfgpu_compute_smoothness.argtypes = [C.c_void_p, IP, IP, IP, IP, IP, C.c_float, C.c_int, C.c_float,
                                              C.c_float, C.c_int]
@@ -321,6 +322,16 @@ class Context:
     def image_warp(self, dst, mask, src, wx, wy, factor=1):
         _check(self.lib, self.lib.sfgpu_image_warp(self.h, dst.ptr(), _ip(mask), src.ptr(), wx.ptr(), wy.ptr(),
                                                    int(factor)), "sfgpu_image_warp")
+
+    def warp_frame_derivs(self, src, wx, wy, factor=1, variant=0):
+        """warped frame, mask, [Ix, Iy, Ixx, Ixy, Iyy] of the warped frame (the multi-frame path's per-frame pass)"""
+        w, h = src.width, src.height
+        warped, mask = ColorImage(w, h), Image(w, h)
+        outs = [ColorImage(w, h) for _ in range(5)]
+        _check(self.lib, self.lib.sfgpu_warp_frame_derivs(self.h, src.ptr(), wx.ptr(), wy.ptr(), int(factor), int(variant),
+                                                           warped.ptr(), mask.ptr(), *[o.ptr() for o in outs]),
+               "sfgpu_warp_frame_derivs")
+        return warped, mask, outs
 
     def compute_dpsis_weight(self, dst, im, coef=5.0, avg=None, std=None, hbit=0):
         a = (C.c_float * 3)(*avg) if avg is not None else None

@@ -319,6 +319,7 @@ int sfgpu_create(int device, void *stream, sfgpu_ctx **out) {
     if (const char *e = getenv("SLOWFLOW_GPU_STAGED_COPIES")) c->staged_host_copies = atoi(e) != 0;
     if (const char *e = getenv("SLOWFLOW_GPU_HOST_MINCUT")) c->host_mincut = atoi(e) != 0;
     if (const char *e = getenv("SLOWFLOW_GPU_MT_DATA_VARIANT")) c->mt_data_variant = atoi(e);
+    if (const char *e = getenv("SLOWFLOW_GPU_MT_WARP_VARIANT")) c->mt_warp_variant = atoi(e);
     c->num_sms = prop.multiProcessorCount;
     if (stream) {
         c->stream = (cudaStream_t)stream;
@@ -509,6 +510,47 @@ int sfgpu_image_warp(sfgpu_ctx *c, color_image_t *dst, image_t *mask, const colo
 }
 
 static bool same_cgeom(const color_image_t *a, int w, int h, int s) { return a && a->c1 && a->width == w && a->height == h && a->stride == s; }
+
+int sfgpu_warp_frame_derivs(sfgpu_ctx *c, const color_image_t *src, const image_t *wx, const image_t *wy, int factor, int variant,
+                            color_image_t *warped, image_t *mask, color_image_t *dx, color_image_t *dy, color_image_t *dxx,
+                            color_image_t *dxy, color_image_t *dyy) {
+    if (!c || !src || !src->c1 || !wx || !wy || !mask || variant < 0 || variant > 1) {
+        set_error("sfgpu_warp_frame_derivs: bad argument");
+        return SFGPU_ERR_ARG;
+    }
+    const int w = src->width, h = src->height, sd = src->stride;
+    color_image_t *outs[6] = {warped, dx, dy, dxx, dxy, dyy};
+    for (int k = 0; k < 6; k++)
+        if (!same_cgeom(outs[k], w, h, sd)) { set_error("sfgpu_warp_frame_derivs: geometry"); return SFGPU_ERR_ARG; }
+    if (wx->width != w || wx->height != h || wx->stride != sd || wy->width != w || wy->height != h || wy->stride != sd ||
+        mask->width != w || mask->height != h || mask->stride != sd) {
+        set_error("sfgpu_warp_frame_derivs: geometry");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    const Geom g{w, h, sd};
+    const size_t P = g.plane();
+    cudaStream_t st = c->stream;
+    DevPlanes d;
+    int rc = d.alloc(24 * P);
+    if (rc) return rc;
+    float *s3 = d.p, *fx = s3 + 3 * P, *fy = fx + P, *o3 = fy + P, *m = o3 + 3 * P, *dv = m + P;
+    H2D(s3, src->c1, 3 * P); H2D(fx, wx->data, P); H2D(fy, wy->data, P);
+    // NaN pre-fill: every element the kernel leaves untouched shows up in the test
+    SF_CUDA(cudaMemsetAsync(o3, 0xff, 19 * P * sizeof(float), st));
+    if (variant == 0) {
+        launch_warp_derivs(st, g, c->num_sms, s3, fx, fy, factor, o3, m, dv);
+    } else {
+        launch_warp(st, g, s3, fx, fy, factor, o3, m);
+        launch_frame_derivs(st, g, o3, dv);
+    }
+    D2H(warped->c1, o3, 3 * P);
+    D2H(mask->data, m, P);
+    for (int k = 0; k < 5; k++) D2H(outs[k + 1]->c1, dv + (size_t)k * 3 * P, 3 * P);
+    SF_CUDA(cudaStreamSynchronize(st));
+    SF_CUDA(cudaGetLastError());
+    return SFGPU_OK;
+}
 
 static int convolve_planes(sfgpu_ctx *c, float *dst, const float *src, Geom g, int planes, int horder, const float *hc, int vorder,
                            const float *vc, const char *what) {

@@ -462,9 +462,20 @@ static void warp_all(LevelCtx &L) { // Variational_MT::get_derivatives, warping 
     const int F = 2 * L.ref + 1;
     for (int f = (L.one_direction ? L.ref + 1 : 0); f < F; f++) {
         if (f == L.ref) continue;
+        if (L.fused_terms && L.c->mt_warp_variant == 0) {
+            // warp + the frame's own derivative images in one marching pass (sf_wderivs.cu); every term that uses the
+            // frame combines the derivative planes linearly
+            cudaEvent_t ev;
+            L.c->prof_begin(1, ev);
+            launch_warp_derivs(L.c->stream, L.g, L.c->num_sms, L.frames[f], L.wx, L.wy, f - L.ref, L.warped[f], L.masks[f],
+                               L.derivs[f]);
+            L.c->prof_end(1, ev);
+            L.c->prof_acc.kernel_launches++;
+            continue;
+        }
         launch_warp(L.c->stream, L.g, L.frames[f], L.wx, L.wy, f - L.ref, L.warped[f], L.masks[f]);
         L.c->prof_acc.kernel_launches++;
-        if (L.fused_terms) { // the frame's own derivative images; every term that uses the frame combines them linearly
+        if (L.fused_terms) { // A/B reference (SLOWFLOW_GPU_MT_WARP_VARIANT=1): separate warp kernel + tile-based derivative kernel
             cudaEvent_t ev;
             L.c->prof_begin(1, ev);
             launch_frame_derivs(L.c->stream, L.g, L.warped[f], L.derivs[f]);

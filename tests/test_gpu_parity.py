@@ -39,6 +39,34 @@ def test_image_warp(ctx, oracle, w, h, factor):
     assert helpers.maxdiff(dst.array, rd.array) < 2e-3  # values up to 255, fp32 + FMA
 
 
+@pytest.mark.parametrize("w,h", [(61, 45), (130, 67), (333, 211), (1280, 1024)])
+@pytest.mark.parametrize("factor", [1, -2])
+def test_warp_frame_derivs_production_kernel(ctx, oracle, w, h, factor):
+    """The multi-frame path's fused warp + per-frame derivative kernel (sf_wderivs.cu) at operator level: every plane,
+    including the first / last rows and columns and the stride padding, against (a) the oracle chain image_warp (time
+    factor) -> get_derivatives of the warped frame, (b) the two-kernel path it replaced."""
+    im1, im2, wx, wy = helpers.pair(w, h)
+    wx.array[2, 3] = -50.0   # far outside on the left -> clamped gather, mask 0
+    wy.array[5, 7] = 1000.0  # far outside below
+    gw, gm, gd = ctx.warp_frame_derivs(im2, wx, wy, factor, 0)
+    bw, bm, bd = ctx.warp_frame_derivs(im2, wx, wy, factor, 1)
+    rw, rm = ColorImage(w, h), Image(w, h)
+    oracle.lib.sfo_image_warp(rw.ptr(), rm.ptr(), im2.ptr(), wx.ptr(), wy.ptr(), factor)
+    refs = [ColorImage(w, h) for _ in range(8)]
+    oracle.lib.sfo_get_derivatives(rw.ptr(), rw.ptr(), *[x.ptr() for x in refs])  # dx dy dt dxx dxy dyy dxt dyt of (I + I)/2
+    assert np.array_equal(gm.array, rm.array) and np.array_equal(gm.array, bm.array)
+    assert np.isfinite(gw.full).all() and not gw.full[:, :, w:].any()          # every element written, zero padding
+    assert not gm.full[:, w:].any()
+    assert helpers.maxdiff(gw.array, rw.array) < 2e-3 and helpers.maxdiff(gw.array, bw.array) < 2e-4  # values up to 255
+    for k, r in zip(range(5), [refs[0], refs[1], refs[3], refs[4], refs[5]]):
+        g, b = gd[k], bd[k]
+        assert np.isfinite(g.full).all() and not g.full[:, :, w:].any(), k
+        scale = max(1.0, float(np.abs(r.array).max()))
+        assert helpers.maxdiff(g.array, b.array) < 2e-5 * scale + 1e-3, k
+        # the oracle differentiates ITS warped frame: a last-bit difference of the warp is amplified by 8/12 per tap
+        assert helpers.maxdiff(g.array, r.array) < 1e-4 * scale + 5e-3, k
+
+
 @pytest.mark.parametrize("w,h", [(96, 64), (61, 45)])
 def test_dpsis_weight(ctx, oracle, w, h):
     im1, _, _, _ = helpers.pair(w, h)
