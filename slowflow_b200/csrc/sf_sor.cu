@@ -62,6 +62,10 @@ __global__ void __launch_bounds__(256) k_sor_half_global(Geom g, const float *__
 #ifndef SF_SOR_PDL
 #define SF_SOR_PDL 1 // chain consecutive launches with programmatic dependent launch
 #endif
+#ifndef SF_SOR_EDGE_TILES
+#define SF_SOR_EDGE_TILES 1 // 1: tiles whose side lies on the image border keep that side's halo as interior (fewer tiles)
+#endif
+#define SOR_EDGE (SF_SOR_EDGE_TILES ? 0 : 1)
 #ifndef SF_SOR_SYNC
 #define SF_SOR_SYNC 0 // 0: one CTA barrier per half sweep; 1: neighbour-to-neighbour publication counters
 #endif
@@ -84,6 +88,11 @@ __device__ unsigned long long g_sor_clk[8]; // tma-wait, load, sweeps, barrier-w
 #else
 #define SOR_CLK(var)
 #endif
+
+// Horizontal halo of a tile for T fused sweeps.  TMA needs the box origin 16-byte aligned along x.  With tile origins at
+// multiples of the interior width (SF_SOR_EDGE_TILES) that holds for the exact halo 2T (interior 64 - 4T is a multiple
+// of 4); with origins shifted by the halo it has to be rounded up to a multiple of 4 floats.
+__host__ __device__ __forceinline__ int sor_halo_x(int T) { return SF_SOR_EDGE_TILES ? 2 * T : ((2 * T + 3) & ~3); }
 
 struct SorTiledArgs {
     Geom g;
@@ -184,9 +193,8 @@ k_sor_tiled(const __grid_constant__ CUtensorMap tmap_coef, const __grid_constant
     int *pub = reinterpret_cast<int *>(base + SOR_NW * SOR_BLOCK_BYTES + SOR_EXCH_BYTES); // publications per warp
     uint64_t *mbar = reinterpret_cast<uint64_t *>(pub + 32) + warp;                        // TMA completion, per warp
 
-    // halo: 2T pixels per side.  TMA needs the box origin 16-byte aligned along x, so the horizontal
-    // halo is rounded up to a multiple of 4 floats (tile origins stay multiples of 4).
-    const int hy = 2 * a.T, hx = (2 * a.T + 3) & ~3;
+    // halo: 2T pixels per side (sor_halo_x: exact with tile origins at multiples of the interior width)
+    const int hy = 2 * a.T, hx = sor_halo_x(a.T);
     const int IW = SOR_TW - 2 * hx, IH = SOR_TH - 2 * hy;
     const int ntiles = a.tiles_x * a.tiles_y;
     const int nhalf = 2 * a.T;
@@ -203,7 +211,7 @@ k_sor_tiled(const __grid_constant__ CUtensorMap tmap_coef, const __grid_constant
     // its iterate (one box over the du,dv plane pair) and the psi_v row above it arrive in the warp's own block
     auto issue = [&](int tile) {
         const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-        const int x0 = tx * IW - hx, y0 = ty * IH - hy + warp * SOR_R;
+        const int x0 = tx * IW - SOR_EDGE * hx, y0 = ty * IH - SOR_EDGE * hy + warp * SOR_R;
         mbar_expect_tx(mbar, (uint32_t)(((a.zero_init ? 7 : 9) * SOR_R + 1) * SOR_TW * 4));
         tma_load_3d(stage, &tmap_coef, mbar, x0, y0, 0);
         if (!a.zero_init) tma_load_3d(stage + 7 * SOR_R * SOR_TW, &tmap_iter, mbar, x0, y0, a.in_du_plane);
@@ -273,7 +281,7 @@ k_sor_tiled(const __grid_constant__ CUtensorMap tmap_coef, const __grid_constant
 
     while (tile < ntiles) {
         const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-        const int x0 = tx * IW - hx, y0 = ty * IH - hy;
+        const int x0 = tx * IW - SOR_EDGE * hx, y0 = ty * IH - SOR_EDGE * hy;
 
         SOR_CLK(c0);
         mbar_wait(mbar, phase);
@@ -357,13 +365,21 @@ k_sor_tiled(const __grid_constant__ CUtensorMap tmap_coef, const __grid_constant
         // ---- interior of the tile -> global (float2 per lane and row: 256 B per warp row)
         SOR_CLK(c3);
         const int cx = 2 * lane, gx = x0 + cx;
-        if (cx >= hx && cx < SOR_TW - hx && gx < a.g.W) {
+#if SF_SOR_EDGE_TILES
+        // a tile side that lies on (or beyond) the image border needs no halo: the boundary condition there is exact,
+        // so the first tile of a row / column keeps its first hx columns / hy rows and the last one its last
+        const int cx_lo = (tx == 0) ? 0 : hx, cx_hi = (x0 + SOR_TW >= a.g.W) ? SOR_TW : SOR_TW - hx;
+        const int tr_lo = (ty == 0) ? 0 : hy, tr_hi = (y0 + SOR_TH >= a.g.H) ? SOR_TH : SOR_TH - hy;
+#else
+        const int cx_lo = hx, cx_hi = SOR_TW - hx, tr_lo = hy, tr_hi = SOR_TH - hy;
+#endif
+        if (cx >= cx_lo && cx < cx_hi && gx < a.g.W) {
 #pragma unroll
             for (int p = 0; p < SOR_HP; p++) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int tr = warp * SOR_R + p + h * SOR_HP, gy = y0 + tr;
-                    if (tr >= hy && tr < SOR_TH - hy && gy < a.g.H) {
+                    if (tr >= tr_lo && tr < tr_hi && gy < a.g.H) {
                         const size_t o = (size_t)gy * a.g.S + gx;
                         *reinterpret_cast<float2 *>(a.out_du + o) = h ? make_float2(hi_of(q.du[0][p]), hi_of(q.du[1][p]))
                                                                       : make_float2(lo_of(q.du[0][p]), lo_of(q.du[1][p]));
@@ -493,9 +509,18 @@ int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int 
         SorTiledArgs a;
         a.g = g;
         a.T = T;
-        const int IW = SOR_TW - 2 * ((2 * T + 3) & ~3), IH = SOR_TH - 4 * T;
+        const int IW = SOR_TW - 2 * sor_halo_x(T), IH = SOR_TH - 4 * T;
+#if SF_SOR_EDGE_TILES
+        // tile origins at multiples of the interior size: the first and the last tile of a row / column keep the halo
+        // side that lies on the image border (exact there), so n tiles cover n * I + 2 * halo pixels
+        a.tiles_x = (g.W - (SOR_TW - IW) + IW - 1) / IW;
+        a.tiles_y = (g.H - (SOR_TH - IH) + IH - 1) / IH;
+        if (a.tiles_x < 1) a.tiles_x = 1;
+        if (a.tiles_y < 1) a.tiles_y = 1;
+#else
         a.tiles_x = (g.W + IW - 1) / IW;
         a.tiles_y = (g.H + IH - 1) / IH;
+#endif
         a.omega = omega;
         a.one = 1.0f;
         a.zero_init = (zero_init && done == 0) ? 1 : 0;
