@@ -346,6 +346,7 @@ void sfgpu_destroy(sfgpu_ctx *c) {
     if (c->cut) sf::device_cut_free(c->cut);
     if (c->epic_arena) sf::epic_arena_free(c->epic_arena);
     if (c->ws) cudaFree(c->ws);
+    sf::sor_plan_release(c->sor);
     if (c->io) cudaFree(c->io);
     for (auto &ring : c->seq_ev)
         for (auto e : ring)

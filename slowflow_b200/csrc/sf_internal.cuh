@@ -171,18 +171,26 @@ enum SorPlane { SP_A11 = 0, SP_A12, SP_A22, SP_B1, SP_B2, SP_PH, SP_PV, SP_DUA, 
 struct SorPlan {
     Geom g{0, 0, 0};
     float *arena = nullptr; // SP_COUNT planes
-    CUtensorMap tmap;       // 3-D (x, y, plane) views of the arena: box = a warp's strip of the 7 coefficient planes,
+    CUtensorMap tmap;       // 3-D (x, y, plane) views of the arena: box = a tile of the first 4 coefficient planes,
+    CUtensorMap tmap_gb;    //   ... of the other 3,
     CUtensorMap tmap_iter;  //   ... of a du,dv plane pair,
     CUtensorMap tmap_row;   //   ... one row of one plane
     CUtensorMap tmap_s_coef, tmap_s_iter, tmap_s_row; // the same three views with the boxes of the streaming kernel
     bool tmap_valid = false;
     int num_sms = 0;
+    // device words of the tiled kernel's multi-pass launches: [0] ticket counter, [1] CTAs that have left, [2] generation,
+    // [4 + tile] generation + passes the tile has completed.  Owned by the plan (sor_plan_release); a plan serves one
+    // stream at a time.
+    static constexpr size_t SYNC_TILES = 1 << 16;
+    unsigned *sync = nullptr;
+    size_t sync_tiles = 0;
 };
 // per-device kernel attributes (dynamic shared memory opt-in); called once per context on its device
 bool sor_device_init();
 bool data_term_device_init();
 // Encode the TMA descriptor for an arena.  Returns false (and sets the error) on failure.
 bool sor_plan_init(SorPlan &plan, Geom g, float *arena, int num_sms);
+void sor_plan_release(SorPlan &plan);
 // Runs `iterations` sweeps; the iterate starts in (duA,dvA) when *cur==0 or (duB,dvB) when *cur==1 and
 // *cur is updated to the buffer holding the result.  zero_init: treat the initial iterate as 0.
 // variant 0: tiled / temporally blocked (fuse sweeps per launch), variant 1: one launch per half sweep,

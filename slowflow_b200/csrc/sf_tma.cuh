@@ -30,11 +30,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking test of a phase
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // bounded spin: a TMA that never completes (bad descriptor) traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 24)) __trap();
+    }
+}
+// polling wait for the helper warps: mbarrier.try_wait suspends the thread and was seen to resume it 1-2 us after the
+// phase had completed; a test_wait poll with a short sleep reacts within ~100 clk and costs few issue slots
+__device__ __forceinline__ void mbar_poll_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_test_wait(bar, parity)) {
+        __nanosleep(32);
+        if (++spins > (1u << 26)) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {

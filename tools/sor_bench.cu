@@ -45,7 +45,7 @@ int main(int argc, char **argv) {
         for (int rep = 0; rep < reps; rep++) {
             int cur = 0;
 #ifdef SF_SOR_CLOCKS
-            unsigned long long z[8] = {0}; cudaMemcpyToSymbol(sf::g_sor_clk, z, sizeof(z));
+            unsigned long long z[8] = {0}; cudaMemcpyToSymbol(sf::g_sor_clk, z, sizeof(z)); cudaMemcpyToSymbol(sf::g_sor_hclk, z, sizeof(z));
 #endif
 #ifdef SF_SS_CLOCKS
             { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(sf::g_ss_clk, z, sizeof(z)); }
@@ -69,8 +69,12 @@ int main(int argc, char **argv) {
 #ifdef SF_SOR_CLOCKS
         unsigned long long c[8]; cudaMemcpyFromSymbol(c, sf::g_sor_clk, sizeof(c));
         const double n = (double)c[7];
-        if (n > 0) printf("   per tile (warp 0, avg over %.0f tiles): tma-wait %.0f  load %.0f  sweeps %.0f (of which barrier wait %.0f)  store %.0f  total %.0f clk\n", n, c[0] / n,
+        if (n > 0) printf("   per tile (warp 0, avg over %.0f tiles): tma-wait %.0f (group B %.0f, %.0f waits > 500 clk)  load %.0f  sweeps %.0f (of which barrier wait %.0f)  store %.0f  total %.0f clk\n", n, c[0] / n, c[5] / n, (double)c[6],
                c[1] / n, c[2] / n, c[3] / n, c[4] / n, (c[0] + c[1] + c[2] + c[4]) / n);
+        unsigned long long hc[8]; cudaMemcpyFromSymbol(hc, sf::g_sor_hclk, sizeof(hc));
+        const double hn = (double)hc[7];
+        if (hn > 0) printf("   helper warp per round (avg over %.0f): wait-free %.0f  issue-B %.0f  fetch+wait-B %.0f  issue-A+deps %.0f clk; warp 0 arrive -> loader sees freeb %.0f clk\n", hn,
+               hc[0] / hn, hc[1] / hn, hc[2] / hn, hc[3] / hn, hc[4] / hn);
 #endif
     }
     // cross-check against the per-half-sweep kernel on a fresh copy of the system (all variants run the same FMA chain)
