@@ -626,7 +626,7 @@ def run_ours(args):
 
     # ---- the UNMODIFIED drop-in call: variational() (variational.h:30) on ordinary malloc'ed buffers, one pair per call,
     # synchronous, exactly what adaptiveFR.cpp:574 / epicflow.cpp:127 would execute after re-linking
-    n_legacy = 6
+    n_legacy = min(6, B)
     lg_frames = [ColorImage.from_array(frames[k].array) for k in range(n_legacy + 1)]  # numpy memory: pageable
     lg_x, lg_y = [Image.from_array(u0) for _ in range(n_legacy)], [Image.from_array(v0) for _ in range(n_legacy)]
     torch.cuda.synchronize()
@@ -646,7 +646,7 @@ def run_ours(args):
     sc = counts.get("k_sor_tiled") or {}
     traffic = sc.get("dram_bytes_per_launch") if (W, H) == (W_FULL, H_FULL) else None
     roofline = {
-        "bound": "hbm", "kernel": "k_sor_tiled (red-black SOR, up to %d sweeps fused per launch)" % fuse,
+        "bound": "hbm", "kernel": "k_sor_tiled (red-black SOR, %d sweeps per pass over the image, all passes of a call chained in one launch)" % fuse,
         "achieved": sor_gbs, "peak": peak, "unit": "GB/s", "frac": sor_gbs / peak, "traffic": traffic,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": sor_bytes / max(1, prof.sor_launches),

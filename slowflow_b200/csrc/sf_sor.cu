@@ -116,8 +116,9 @@ struct SorTiledArgs {
     float *arena;   // plane 0 of the SOR arena (the iterate planes are addressed by plane index)
     int plane_a;    // du plane of the iterate buffer pass 0 reads (dv = du + 1); pass p reads buffer (p & 1), writes the other
     int plane_b;
-    int T;          // sweeps fused per pass
-    int passes;     // passes of T sweeps chained in this launch (tile-level dependencies instead of kernel boundaries)
+    int T;          // sweeps fused per pass (fixes the tiling: halo 2T)
+    int passes;     // passes chained in this launch (tile-level dependencies instead of kernel boundaries)
+    int T_last;     // sweeps of the last pass (<= T)
     int tiles_x, tiles_y;
     float omega;
     int zero_init;  // the initial iterate is 0: pass 0 does not load du,dv
@@ -260,7 +261,6 @@ k_sor_tiled(const __grid_constant__ CUtensorMap tmap_ga, const __grid_constant__
     const int hy = 2 * a.T, hx = sor_halo_x(a.T);
     const int IW = SOR_TW - 2 * hx, IH = SOR_TH - 2 * hy;
     const int ntiles = a.tiles_x * a.tiles_y;
-    const int nhalf = 2 * a.T;
     const unsigned total = (unsigned)(ntiles * a.passes);
 
     if (threadIdx.x == 0) {
@@ -499,6 +499,7 @@ k_sor_tiled(const __grid_constant__ CUtensorMap tmap_ga, const __grid_constant__
         const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
         const int x0 = tx * IW - SOR_EDGE * hx, y0 = ty * IH - SOR_EDGE * hy;
         const bool zero_it = a.zero_init && pass == 0;
+        const int nhalf = 2 * (pass == a.passes - 1 ? a.T_last : a.T);
         SOR_CLK(c1);
 
         // ---- shared -> registers
@@ -752,10 +753,13 @@ int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int 
     if (fuse > max_fuse) fuse = max_fuse;
     int done = 0;
     while (done < iterations) {
-        // all passes of `fuse` sweeps go into ONE launch (tile-level dependencies between the passes); a remainder of
-        // fewer sweeps has another tiling and is a launch of its own
+        // all passes go into ONE launch (tile-level dependencies between the passes).  A remainder of fewer than `fuse`
+        // sweeps is the last pass of that launch: it keeps the tiling (the halo is then deeper than it needs) and runs
+        // fewer half sweeps -- a launch of its own with the tighter tiling costs more than the bytes it saves (2560x1440,
+        // 7 x 4 + 2 sweeps: 43 us for the separate 2-sweep launch).
         const int T = (iterations - done < fuse) ? (iterations - done) : fuse;
-        int passes = (iterations - done) / T;
+        int passes = (iterations - done + T - 1) / T;
+        int T_last = (iterations - done) - (passes - 1) * T;
         SorTiledArgs a;
         a.g = g;
         a.T = T;
@@ -772,8 +776,12 @@ int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int 
         a.tiles_y = (g.H + IH - 1) / IH;
 #endif
         const int ntiles = a.tiles_x * a.tiles_y;
-        if (SF_SOR_MULTIPASS == 0 || (size_t)ntiles > plan.sync_tiles) passes = 1; // (no dependency flags for that many tiles)
+        if (SF_SOR_MULTIPASS == 0 || (size_t)ntiles > plan.sync_tiles) { // (no dependency flags for that many tiles)
+            passes = 1;
+            T_last = T;
+        }
         a.passes = passes;
+        a.T_last = T_last;
         a.omega = omega;
         a.one = 1.0f;
         a.zero_init = (zero_init && done == 0) ? 1 : 0;
@@ -794,7 +802,7 @@ int launch_sor(cudaStream_t st, SorPlan &plan, int iterations, float omega, int 
         k_sor_tiled<<<grid, SOR_THREADS, SOR_SMEM_BYTES, st>>>(plan.tmap, plan.tmap_gb, plan.tmap_iter, plan.tmap_row, a);
 #endif
         if (passes & 1) *cur ^= 1;
-        done += T * passes;
+        done += T * (passes - 1) + T_last;
         launches++;
     }
     return launches;
