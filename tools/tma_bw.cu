@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdint.h>
 #include <vector>
+#include <stdlib.h>
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -49,8 +50,8 @@ __global__ void __launch_bounds__(512, 1) pull(const __grid_constant__ CUtensorM
     }
     if (acc == 12345.678f) sink[0] = acc;
 }
-int main() {
-    const int W = 2560, H = 1440, S = 2560, NP = 11;
+int main(int argc, char **argv) {
+    const int W = argc > 1 ? atoi(argv[1]) : 2560, H = argc > 2 ? atoi(argv[2]) : 1440, S = W, NP = 11;
     size_t P = (size_t)S * H;
     float *d, *sink;
     cudaMalloc(&d, P * NP * 4); cudaMemset(d, 0, P * NP * 4); cudaMalloc(&sink, 4);
@@ -63,7 +64,7 @@ int main() {
                   {128, 16, 8, 4, 2, 9, 1}, {256, 16, 8, 4, 1, 9, 1}, {64, 16, 8, 4, 5, 9, 1}, {64, 64, 0, 0, 1, 9, 1}, {64, 64, 8, 8, 1, 4, 1}, {64, 64, 8, 8, 1, 4, 1}};
     for (auto &c : cfgs) {
         CUtensorMap tm;
-        cuuint64_t dims[3] = {W, H, NP}; cuuint64_t strides[2] = {(cuuint64_t)S * 4, (cuuint64_t)P * 4};
+        cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, NP}; cuuint64_t strides[2] = {(cuuint64_t)S * 4, (cuuint64_t)P * 4};
         cuuint32_t box[3] = {(cuuint32_t)c.BW, (cuuint32_t)c.BH, 1}, es[3] = {1, 1, 1};
         CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                          c.promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (c.promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
