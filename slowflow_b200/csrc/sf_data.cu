@@ -90,6 +90,7 @@ __device__ __forceinline__ void term_two_frame(const Derivs &d, float u, float v
 
 // ---- multi-frame successive term (variational_aux_mt.cpp:186-363): warped frames s and s+1, effective
 // gradient s*I - (s+1)*I evaluated exactly as written; wc = channel weights; psi' pluggable.
+template <int PC = -1, int PG = -1>
 __device__ __forceinline__ void term_mt_succ(const Derivs &d, float u, float v, float m, float wd, float wg, float s,
                                              const float wc[3], int dt_norm, const Penalty &pc, const Penalty &pg, Acc &acc) {
     const float dnorm = 0.1f * 0.1f;
@@ -107,7 +108,7 @@ __device__ __forceinline__ void term_mt_succ(const Derivs &d, float u, float v, 
             r[c] = wc[c] * (d.iz[c] + gx[c] * u + gy[c] * v);
         }
         if (!dt_norm) {
-            const float t = m * wd * penalty_deriv_v(pc, r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+            const float t = m * wd * penalty_deriv_vt<PC>(pc, r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const float g = t * wc[c];
@@ -121,7 +122,7 @@ __device__ __forceinline__ void term_mt_succ(const Derivs &d, float u, float v, 
             float inv[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) inv[c] = fast_rcp(gx[c] * gx[c] + gy[c] * gy[c] + dnorm);
-            const float t = m * wd * penalty_deriv_v(pc, r[0] * r[0] * inv[0] + r[1] * r[1] * inv[1] + r[2] * r[2] * inv[2]);
+            const float t = m * wd * penalty_deriv_vt<PC>(pc, r[0] * r[0] * inv[0] + r[1] * r[1] * inv[1] + r[2] * r[2] * inv[2]);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const float g = t * inv[c] * wc[c];
@@ -143,7 +144,7 @@ __device__ __forceinline__ void term_mt_succ(const Derivs &d, float u, float v, 
         ry[c] = wc[c] * (d.iyz[c] + gxy[c] * u + gyy[c] * v);
     }
     if (!dt_norm) {
-        const float t = m * wg * penalty_deriv_v(pg, rx[0] * rx[0] + ry[0] * ry[0] + rx[1] * rx[1] + ry[1] * ry[1] +
+        const float t = m * wg * penalty_deriv_vt<PG>(pg, rx[0] * rx[0] + ry[0] * ry[0] + rx[1] * rx[1] + ry[1] * ry[1] +
                                                          rx[2] * rx[2] + ry[2] * ry[2]);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
@@ -161,7 +162,7 @@ __device__ __forceinline__ void term_mt_succ(const Derivs &d, float u, float v, 
             ivx[c] = fast_rcp(gxx[c] * gxx[c] + gxy[c] * gxy[c] + dnorm);
             ivy[c] = fast_rcp(gyy[c] * gyy[c] + gxy[c] * gxy[c] + dnorm);
         }
-        const float t = m * wg * penalty_deriv_v(pg, rx[0] * rx[0] * ivx[0] + ry[0] * ry[0] * ivy[0] + rx[1] * rx[1] * ivx[1] +
+        const float t = m * wg * penalty_deriv_vt<PG>(pg, rx[0] * rx[0] * ivx[0] + ry[0] * ry[0] * ivy[0] + rx[1] * rx[1] * ivx[1] +
                                                          ry[1] * ry[1] * ivy[1] + rx[2] * rx[2] * ivx[2] + ry[2] * ry[2] * ivy[2]);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
@@ -178,6 +179,7 @@ __device__ __forceinline__ void term_mt_succ(const Derivs &d, float u, float v, 
 // ---- multi-frame reference term (variational_aux_mt.cpp:416-592): frame vs. unwarped reference frame with
 // time factor s (sign flipped for s >= 0, :424-425).  The un-normalised branch reproduces the reference
 // literally, including its copy-paste slips (:458-471 channel 3, :527-530 channel 1).
+template <int PC = -1, int PG = -1>
 __device__ __forceinline__ void term_mt_ref(const Derivs &d, float u, float v, float m, float wd, float wg, float s,
                                             const float wc[3], int dt_norm, const Penalty &pc, const Penalty &pg, Acc &acc) {
     const float dnorm = 0.1f * 0.1f;
@@ -188,7 +190,7 @@ __device__ __forceinline__ void term_mt_ref(const Derivs &d, float u, float v, f
 #pragma unroll
         for (int c = 0; c < 3; c++) r[c] = wc[c] * (d.iz[c] + d.ix[c] * f * u + d.iy[c] * f * v);
         if (!dt_norm) {
-            float t = m * wd * penalty_deriv_v(pc, r[0] * r[0] / fsq + r[1] * r[1] / fsq + r[2] * r[2] / fsq);
+            float t = m * wd * penalty_deriv_vt<PC>(pc, r[0] * r[0] / fsq + r[1] * r[1] / fsq + r[2] * r[2] / fsq);
             t /= fsq;
 #pragma unroll
             for (int c = 0; c < 3; c++) {
@@ -204,7 +206,7 @@ __device__ __forceinline__ void term_mt_ref(const Derivs &d, float u, float v, f
             float inv[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) inv[c] = fast_rcp(fsq * d.ix[c] * d.ix[c] + fsq * d.iy[c] * d.iy[c] + dnorm);
-            const float t = m * wd * penalty_deriv_v(pc, r[0] * r[0] * inv[0] + r[1] * r[1] * inv[1] + r[2] * r[2] * inv[2]);
+            const float t = m * wd * penalty_deriv_vt<PC>(pc, r[0] * r[0] * inv[0] + r[1] * r[1] * inv[1] + r[2] * r[2] * inv[2]);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 float g = t * inv[c] * wc[c] * f;
@@ -224,7 +226,7 @@ __device__ __forceinline__ void term_mt_ref(const Derivs &d, float u, float v, f
         ry[c] = wc[c] * (d.iyz[c] + d.ixy[c] * f * u + d.iyy[c] * f * v);
     }
     if (!dt_norm) {
-        float t = m * wg * penalty_deriv_v(pg, rx[0] * rx[0] / fsq + ry[0] * ry[0] / fsq + rx[1] * rx[1] / fsq +
+        float t = m * wg * penalty_deriv_vt<PG>(pg, rx[0] * rx[0] / fsq + ry[0] * ry[0] / fsq + rx[1] * rx[1] / fsq +
                                                    ry[1] * ry[1] / fsq + rx[2] * rx[2] / fsq + ry[2] * ry[2] / fsq);
         t /= fsq;
 #pragma unroll
@@ -245,7 +247,7 @@ __device__ __forceinline__ void term_mt_ref(const Derivs &d, float u, float v, f
             ivx[c] = fast_rcp(fsq * d.ixx[c] * d.ixx[c] + fsq * d.ixy[c] * d.ixy[c] + dnorm);
             ivy[c] = fast_rcp(fsq * d.iyy[c] * d.iyy[c] + fsq * d.ixy[c] * d.ixy[c] + dnorm);
         }
-        const float t = m * wg * penalty_deriv_v(pg, rx[0] * rx[0] * ivx[0] + ry[0] * ry[0] * ivy[0] + rx[1] * rx[1] * ivx[1] +
+        const float t = m * wg * penalty_deriv_vt<PG>(pg, rx[0] * rx[0] * ivx[0] + ry[0] * ry[0] * ivy[0] + rx[1] * rx[1] * ivx[1] +
                                                          ry[1] * ry[1] * ivy[1] + rx[2] * rx[2] * ivx[2] + ry[2] * ry[2] * ivy[2]);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
@@ -446,6 +448,9 @@ __global__ void __launch_bounds__(256) k_data_term(Geom g, DataTermDesc t, DataC
 }
 
 // ---- all multi-frame terms of one outer / inner iteration in one pointwise pass (see sf_internal.cuh)
+// PC, PG: the colour / gradient penalties as compile-time functor ids (select_robust_function,
+// variational_aux_mt.cpp:889-926): one instantiation per pair instead of a switch per evaluation
+template <int PC, int PG>
 __global__ void __launch_bounds__(256) k_mt_terms(Geom g, MtTermsArgs ta, DataCommon cm) {
     pdl_enter();
     if (g.cancelled()) return;
@@ -491,8 +496,8 @@ __global__ void __launch_bounds__(256) k_mt_terms(Geom g, MtTermsArgs ta, DataCo
             const float sel = (t.dir == 0) ? ((oc >= 0.0f) ? 1.0f : 0.0f) : ((oc <= 0.0f) ? 1.0f : 0.0f);
             m = (1.0f * (sel / fac)) * m;
         }
-        if (t.kind == DK_MT_SUCC) term_mt_succ(d, u, v, m, t.wd, t.wg, t.s, wc, cm.dt_norm, cm.pc, cm.pg, acc);
-        else term_mt_ref(d, u, v, m, t.wd, t.wg, t.s, wc, cm.dt_norm, cm.pc, cm.pg, acc);
+        if (t.kind == DK_MT_SUCC) term_mt_succ<PC, PG>(d, u, v, m, t.wd, t.wg, t.s, wc, cm.dt_norm, cm.pc, cm.pg, acc);
+        else term_mt_ref<PC, PG>(d, u, v, m, t.wd, t.wg, t.s, wc, cm.dt_norm, cm.pc, cm.pg, acc);
     }
     {
         // b += div(psi grad w) and the 2x2 block inverse, as in k_data_term's fuse_system (variational_aux.c:158-179,
@@ -551,9 +556,28 @@ void launch_frame_derivs(cudaStream_t st, Geom g, const float *image3, float *de
     launch_pdl(k_data_term<DK_DERIVS>, grid, b, DT_SMEM_FLOATS * sizeof(float), st, g, t, cm);
 }
 
+template <int PC>
+static void launch_mt_terms_pg(cudaStream_t st, dim3 grid, dim3 b, Geom g, const MtTermsArgs &ta, const DataCommon &cm) {
+    switch (cm.pg.type) {
+    case SF_ROBUST_QUADRATIC: launch_pdl(k_mt_terms<PC, SF_ROBUST_QUADRATIC>, grid, b, 0, st, g, ta, cm); break;
+    case SF_ROBUST_MODL1: launch_pdl(k_mt_terms<PC, SF_ROBUST_MODL1>, grid, b, 0, st, g, ta, cm); break;
+    case SF_ROBUST_LORENTZIAN: launch_pdl(k_mt_terms<PC, SF_ROBUST_LORENTZIAN>, grid, b, 0, st, g, ta, cm); break;
+    case SF_ROBUST_TRUNC_MODL1: launch_pdl(k_mt_terms<PC, SF_ROBUST_TRUNC_MODL1>, grid, b, 0, st, g, ta, cm); break;
+    case SF_ROBUST_GEMAN_MCCLURE: launch_pdl(k_mt_terms<PC, SF_ROBUST_GEMAN_MCCLURE>, grid, b, 0, st, g, ta, cm); break;
+    default: launch_pdl(k_mt_terms<PC, -1>, grid, b, 0, st, g, ta, cm); break;
+    }
+}
+
 void launch_mt_terms(cudaStream_t st, Geom g, const MtTermsArgs &ta, const DataCommon &cm) {
     dim3 b(32, 8), grid((g.S + 31) / 32, (g.H + 7) / 8);
-    launch_pdl(k_mt_terms, grid, b, 0, st, g, ta, cm);
+    switch (cm.pc.type) {
+    case SF_ROBUST_QUADRATIC: launch_mt_terms_pg<SF_ROBUST_QUADRATIC>(st, grid, b, g, ta, cm); break;
+    case SF_ROBUST_MODL1: launch_mt_terms_pg<SF_ROBUST_MODL1>(st, grid, b, g, ta, cm); break;
+    case SF_ROBUST_LORENTZIAN: launch_mt_terms_pg<SF_ROBUST_LORENTZIAN>(st, grid, b, g, ta, cm); break;
+    case SF_ROBUST_TRUNC_MODL1: launch_mt_terms_pg<SF_ROBUST_TRUNC_MODL1>(st, grid, b, g, ta, cm); break;
+    case SF_ROBUST_GEMAN_MCCLURE: launch_mt_terms_pg<SF_ROBUST_GEMAN_MCCLURE>(st, grid, b, g, ta, cm); break;
+    default: launch_mt_terms_pg<-1>(st, grid, b, g, ta, cm); break;
+    }
 }
 
 } // namespace sf

@@ -23,6 +23,10 @@ __device__ __forceinline__ float penalty_half_rsqrt(float x) { // 1 / (2 sqrt(x)
     const float h = 0.5f * r;
     return fmaf(0.5f * h, fmaf(-x * r, r, 1.0f), h); // one Newton step on rsqrt, r' = r + r/2 (1 - x r^2), halved
 }
+// TYPE: the penalty as a compile-time functor id (SF_ROBUST_*; the multi-frame terms kernel is instantiated per pair
+// of ids), or -1 for the run-time switch below
+template <int TYPE>
+__device__ __forceinline__ float penalty_deriv_vt(const Penalty &p, float xsq);
 __device__ __forceinline__ float penalty_deriv_v(const Penalty &p, float xsq) {
     switch (p.type) {
     case SF_ROBUST_QUADRATIC: return 1.0f;
@@ -37,6 +41,26 @@ __device__ __forceinline__ float penalty_deriv_v(const Penalty &p, float xsq) {
         return penalty_half_rsqrt(xsq + p.eps_sq_f);
     }
     default: return penalty_half_rsqrt(xsq + p.eps_sq_f); // ModifiedL1Norm
+    }
+}
+
+template <int TYPE>
+__device__ __forceinline__ float penalty_deriv_vt(const Penalty &p, float xsq) {
+    if constexpr (TYPE == SF_ROBUST_QUADRATIC) {
+        return 1.0f;
+    } else if constexpr (TYPE == SF_ROBUST_LORENTZIAN) {
+        return penalty_rcp(2.0f * p.eps_sq_f + xsq);
+    } else if constexpr (TYPE == SF_ROBUST_GEMAN_MCCLURE) {
+        float t = p.eps_sq_f + xsq;
+        t = t * t;
+        return (p.eps_sq_f + 2.0f * xsq) * penalty_rcp(t);
+    } else if constexpr (TYPE == SF_ROBUST_TRUNC_MODL1) {
+        if (sqrtf(xsq) > p.trunc) return 0.0f;
+        return penalty_half_rsqrt(xsq + p.eps_sq_f);
+    } else if constexpr (TYPE == SF_ROBUST_MODL1) {
+        return penalty_half_rsqrt(xsq + p.eps_sq_f);
+    } else {
+        return penalty_deriv_v(p, xsq);
     }
 }
 

@@ -6,17 +6,19 @@
 // The reference visits pixels row-major (Gauss-Seidel, serial in i).  Here colour (i+j)&1 == 0 is
 // updated first, then colour 1, per sweep -- the ordering of the oracle's CPU red-black mode.
 //
-// Variant 0 (production): temporally blocked.  A persistent CTA (16 warps) owns a 64 x 64 pixel tile.
-//   * TMA (cp.async.bulk.tensor, 3-D map over the 11-plane SOR arena) stages the 9 input planes of the
-//     NEXT tile in shared memory while the current tile is being relaxed; out-of-image texels are
-//     zero-filled by the TMA unit, which gives psi = 0 / a' = 0 boundary handling for free.
-//   * The 7 coefficient planes and du,dv of the current tile live in REGISTERS: lane l of warp w owns
-//     pixel columns {2l, 2l+1} of rows 4w..4w+3.  Horizontal neighbours come from warp shuffles,
-//     vertical neighbours across warps through a 16 KB double-buffered exchange area.
-//   * T sweeps (2T half sweeps) run per HBM round trip; the outer 2T pixels of the tile are halo that
-//     is recomputed by the neighbouring tile.  HBM traffic per sweep drops from 44 B/px to
-//     (36/f + 8)/T B/px with f = the interior fraction of the tile (e.g. 56x56/64x64 for T = 2).
-//   * du,dv ping-pong between two arena buffers (a tile's halo is another tile's interior).
+// Variant 0 (production): temporally blocked, ONE launch per sor_coupled call.  A persistent CTA (8 compute warps + a
+// helper warp group) owns one 64 x 64 pixel tile at a time.
+//   * T sweeps (2T half sweeps) run per pass over the image; the outer 2T pixels of a tile are halo that is recomputed
+//     by the neighbouring tile.  HBM traffic per sweep drops from 44 B/px to (36/f + 8)/T B/px with f = the interior
+//     fraction of the tile (48x48/64x64 for T = 4).  du,dv ping-pong between two arena buffers from pass to pass.
+//   * All passes of the call run inside the launch: tiles are tickets (pass-major) from an atomic counter and tile (tx,ty)
+//     of pass p waits for the 3x3 tile neighbourhood of pass p-1 through per-tile flags -- see k_sor_tiled.
+//   * TMA (cp.async.bulk.tensor, 3-D maps over the 11-plane SOR arena) stages the 9 input planes of the coming tiles in
+//     shared memory while the current tile is being relaxed; out-of-image texels are zero-filled by the TMA unit, which
+//     gives psi = 0 / a' = 0 boundary handling for free.
+//   * The 7 coefficient planes and du,dv of the current tile live in REGISTERS: lane l of warp w owns pixel columns
+//     {2l, 2l+1} of rows 8w..8w+7.  Horizontal neighbours come from warp shuffles, vertical neighbours across warps
+//     through a double-buffered exchange area in shared memory.
 // Variant 1 (validation, tiny images): one launch per half sweep straight from global memory.
 #include "sf_internal.cuh"
 #include "sf_pack.cuh"
@@ -131,11 +133,6 @@ struct SorTiledArgs {
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
