@@ -64,7 +64,9 @@ struct PrepArgs {
 };
 
 // One warp marches down its (strip, segment).  EDGE: the strip touches the left or right image border.
-template <bool COLOR, bool EDGE>
+// INC: the data term is linearised around a non-zero increment (du,dv); the default two-frame path (niter_inner == 1)
+// evaluates it at du = dv = 0, where the residuals are Iz / Ixz / Iyz themselves
+template <bool COLOR, bool EDGE, bool INC>
 __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, const int seg, const int lane, p64 *ring_sm) {
     const Geom g = a.g;
     const int W = g.W, H = g.H, H1 = H - 1, S = g.S;
@@ -140,7 +142,7 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
         const p64 lu_p = load_pair<EDGE>(a.wx, on, L), lv_p = load_pair<EDGE>(a.wy, on, L); // flow of row o+1
         const p64 hr = load_pair<EDGE>(a.ph, oo, L), vb = load_pair<EDGE>(a.pv, oo, L);
         p64 u = zero2, v = zero2;
-        if (a.du) {
+        if (INC) {
             u = load_pair<EDGE>(a.du, oo, L);
             v = load_pair<EDGE>(a.dv, oo, L);
         }
@@ -191,8 +193,8 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
             // gradient constancy (variational_aux.c:268-296)
             const p64 ivx = rcp2(fma2(ixx[c], ixx[c], fma2(ixy[c], ixy[c], dnorm2)));
             const p64 ivy = rcp2(fma2(iyy, iyy, fma2(ixy[c], ixy[c], dnorm2)));
-            const p64 rx = fma2(ixy[c], v, fma2(ixx[c], u, ixz[c]));
-            const p64 ry = fma2(iyy, v, fma2(ixy[c], u, iyz));
+            const p64 rx = INC ? fma2(ixy[c], v, fma2(ixx[c], u, ixz[c])) : ixz[c];
+            const p64 ry = INC ? fma2(iyy, v, fma2(ixy[c], u, iyz)) : iyz;
             n = fma2(mul2(rx, rx), ivx, n);
             n = fma2(mul2(ry, ry), ivy, n);
             const p64 px = mul2(ixx[c], ivx), sx = mul2(ixy[c], ivx), qy = mul2(ixy[c], ivy), ty = mul2(iyy, ivy);
@@ -204,7 +206,7 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
             if (COLOR) { // colour constancy (variational_aux.c:241-266)
                 const p64 ix = rd(RG_IX, c, U), iy = iy_c, iz = rd(RG_Z, c, U);
                 const p64 inv = rcp2(fma2(iy, iy, fma2(ix, ix, dnorm2)));
-                const p64 rc = fma2(iy, v, fma2(ix, u, iz));
+                const p64 rc = INC ? fma2(iy, v, fma2(ix, u, iz)) : iz;
                 cn = fma2(mul2(rc, rc), inv, cn);
                 const p64 gx = mul2(ix, inv), gy = mul2(iy, inv);
                 c11 = fma2(gx, ix, c11);
@@ -330,7 +332,7 @@ __device__ __forceinline__ void prep_march(const PrepArgs &a, const int strip, c
 #endif
 }
 
-template <bool COLOR>
+template <bool COLOR, bool INC>
 __global__ void __launch_bounds__(PR_WARPS * 32, SF_PREP_MINB) k_prep_two_frame(PrepArgs a) {
     pdl_enter();
     __shared__ p64 ring[PR_WARPS * PR_RING];
@@ -340,8 +342,8 @@ __global__ void __launch_bounds__(PR_WARPS * 32, SF_PREP_MINB) k_prep_two_frame(
     const int strip = work % a.strips, seg = work / a.strips;
     const int X0 = strip * PR_OUT_W - 2 * PR_OUT_LO;
     p64 *ring_sm = ring + (threadIdx.x >> 5) * PR_RING;
-    if ((X0 < 0) || (X0 + 63 > a.g.W - 1)) prep_march<COLOR, true>(a, strip, seg, lane, ring_sm);
-    else prep_march<COLOR, false>(a, strip, seg, lane, ring_sm);
+    if ((X0 < 0) || (X0 + 63 > a.g.W - 1)) prep_march<COLOR, true, INC>(a, strip, seg, lane, ring_sm);
+    else prep_march<COLOR, false, INC>(a, strip, seg, lane, ring_sm);
 }
 
 // rows per segment: the largest number of (strip, segment) work items that is still ONE wave of resident warps
@@ -355,7 +357,7 @@ static int prep_seg_rows(Geom g, int num_sms, int resident_warps_per_sm) {
     return (rows + 3) & ~3;
 }
 
-template <bool COLOR>
+template <bool COLOR, bool INC>
 static void launch_prep_variant(cudaStream_t st, Geom g, int num_sms, PrepArgs &a) {
     // resident warps per SM (the same on every device of the box: all are sm_100a; relaxed atomics because one host
     // thread per device may get here at the same time)
@@ -363,7 +365,7 @@ static void launch_prep_variant(cudaStream_t st, Geom g, int num_sms, PrepArgs &
     int res = resident.load(std::memory_order_relaxed);
     if (!res) {
         int blocks_per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_prep_two_frame<COLOR>, PR_WARPS * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_prep_two_frame<COLOR, INC>, PR_WARPS * 32, 0);
         res = (blocks_per_sm > 0 ? blocks_per_sm : 1) * PR_WARPS;
         resident.store(res, std::memory_order_relaxed);
     }
@@ -371,7 +373,7 @@ static void launch_prep_variant(cudaStream_t st, Geom g, int num_sms, PrepArgs &
     const int segs = (g.H + a.seg_rows - 1) / a.seg_rows;
     a.nwork = a.strips * segs;
     const int blocks = (a.nwork + PR_WARPS - 1) / PR_WARPS;
-    launch_pdl(k_prep_two_frame<COLOR>, dim3(blocks), dim3(PR_WARPS * 32), 0, st, a);
+    launch_pdl(k_prep_two_frame<COLOR, INC>, dim3(blocks), dim3(PR_WARPS * 32), 0, st, a);
 }
 
 void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im1, const float *im2, const float *wx, const float *wy, const float *du, const float *dv, const float *ph, const float *pv,
@@ -383,8 +385,14 @@ void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im
     a.a11 = a11; a.a12 = a12; a.a22 = a22; a.b1 = b1; a.b2 = b2;
     a.hd = half_delta_over3; a.hg = half_gamma_over3;
     a.strips = (g.S + PR_OUT_W - 1) / PR_OUT_W;
-    if (half_delta_over3 != 0.0f) launch_prep_variant<true>(st, g, num_sms, a);
-    else launch_prep_variant<false>(st, g, num_sms, a);
+    const bool inc = du != nullptr;
+    if (half_delta_over3 != 0.0f) {
+        if (inc) launch_prep_variant<true, true>(st, g, num_sms, a);
+        else launch_prep_variant<true, false>(st, g, num_sms, a);
+    } else {
+        if (inc) launch_prep_variant<false, true>(st, g, num_sms, a);
+        else launch_prep_variant<false, false>(st, g, num_sms, a);
+    }
 }
 
 } // namespace sf
