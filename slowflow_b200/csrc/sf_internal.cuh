@@ -145,6 +145,10 @@ void launch_frame_derivs(cudaStream_t st, Geom g, const float *image3, float *de
 // launch_warp + launch_frame_derivs of ONE frame in one marching pass (sf_wderivs.cu)
 void launch_warp_derivs(cudaStream_t st, Geom g, int num_sms, const float *src3, const float *wx, const float *wy, int factor,
                         float *warped3, float *mask, float *derivs15);
+// ... of all warped frames of a window in ONE launch (they share the flow of the reference frame)
+void launch_warp_derivs_batch(cudaStream_t st, Geom g, int num_sms, const float *wx, const float *wy, int nframes,
+                              const float *const *src3, const int *factor, float *const *warped3, float *const *mask,
+                              float *const *derivs15);
 void launch_mt_terms(cudaStream_t st, Geom g, const MtTermsArgs &ta, const DataCommon &cm);
 // K1+K2 fused, marching form (sf_prep.cu): warp + derivatives + two-frame data term + Laplacian + block inverse.
 // Writes the same five planes as launch_warp + launch_data_term(fuse_system) without the warped image in HBM.

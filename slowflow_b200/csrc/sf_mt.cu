@@ -460,19 +460,26 @@ static int read_partials(LevelCtx &L, dim3 grid, double out[4]) {
 
 static void warp_all(LevelCtx &L) { // Variational_MT::get_derivatives, warping part (variational_mt.cpp:96-110)
     const int F = 2 * L.ref + 1;
+    if (L.fused_terms && L.c->mt_warp_variant == 0) {
+        // warp + the frames' own derivative images in one marching pass over ALL warped frames (sf_wderivs.cu); every
+        // term that uses a frame combines its derivative planes linearly
+        const float *src[MT_MAX_FRAMES];
+        float *warped[MT_MAX_FRAMES], *masks[MT_MAX_FRAMES], *derivs[MT_MAX_FRAMES];
+        int factor[MT_MAX_FRAMES], n = 0;
+        for (int f = (L.one_direction ? L.ref + 1 : 0); f < F; f++) {
+            if (f == L.ref) continue;
+            src[n] = L.frames[f]; factor[n] = f - L.ref; warped[n] = L.warped[f]; masks[n] = L.masks[f]; derivs[n] = L.derivs[f];
+            n++;
+        }
+        cudaEvent_t ev;
+        L.c->prof_begin(1, ev);
+        launch_warp_derivs_batch(L.c->stream, L.g, L.c->num_sms, L.wx, L.wy, n, src, factor, warped, masks, derivs);
+        L.c->prof_end(1, ev);
+        L.c->prof_acc.kernel_launches += (n + 7) / 8;
+        return;
+    }
     for (int f = (L.one_direction ? L.ref + 1 : 0); f < F; f++) {
         if (f == L.ref) continue;
-        if (L.fused_terms && L.c->mt_warp_variant == 0) {
-            // warp + the frame's own derivative images in one marching pass (sf_wderivs.cu); every term that uses the
-            // frame combines the derivative planes linearly
-            cudaEvent_t ev;
-            L.c->prof_begin(1, ev);
-            launch_warp_derivs(L.c->stream, L.g, L.c->num_sms, L.frames[f], L.wx, L.wy, f - L.ref, L.warped[f], L.masks[f],
-                               L.derivs[f]);
-            L.c->prof_end(1, ev);
-            L.c->prof_acc.kernel_launches++;
-            continue;
-        }
         launch_warp(L.c->stream, L.g, L.frames[f], L.wx, L.wy, f - L.ref, L.warped[f], L.masks[f]);
         L.c->prof_acc.kernel_launches++;
         if (L.fused_terms) { // A/B reference (SLOWFLOW_GPU_MT_WARP_VARIANT=1): separate warp kernel + tile-based derivative kernel

@@ -21,6 +21,7 @@
 namespace sf {
 
 constexpr int WD_WARPS = 2;          // warps per CTA (independent)
+constexpr int SF_WD_MAX_FRAMES = 8;  // frames per launch (2S warped frames of a window; more go into further launches)
 constexpr int WD_RING = 36 * 32;     // packed values of one warp's windows: I, Ix, Iy x 3 channels x 4 rows
 #ifndef SF_WD_MINB
 #define SF_WD_MINB 8
@@ -29,19 +30,27 @@ constexpr int WD_RING = 36 * 32;     // packed values of one warp's windows: I, 
 // tuning knobs (tools/wderivs_bench.cu): minimum rows per segment, resident-warp override
 int g_wd_min_rows = 4, g_wd_warps_per_sm = 0; // (short segments: the kernel is parallelism-bound at 1 Mpx, tools/wderivs_bench.cu)
 
-struct WdArgs {
-    Geom g;
+// one frame of a launch
+struct WdFrame {
     const float *src;     // the frame (3 planes)
-    const float *wx, *wy; // flow of the reference frame
     float factor;         // time factor of the frame
     float *warped, *mask; // 3 planes, 1 plane
     float *derivs;        // 15 planes [Ix Iy Ixx Ixy Iyy][channel]
-    int strips, seg_rows, nwork;
+};
+// All warped frames of a window go into ONE launch: the (strip, segment) items of every frame share the one wave of
+// resident warps, so the segments are F times longer and the 8 window-filling rows of a segment weigh F times less
+// (1280x1024, 4 frames: 44-row instead of 12-row segments).
+struct WdArgs {
+    Geom g;
+    const float *wx, *wy; // flow of the reference frame
+    WdFrame f[SF_WD_MAX_FRAMES];
+    int nframes;
+    int strips, seg_rows, segs, nwork;
 };
 
 template <bool EDGE>
-__device__ __forceinline__ void wd_march(const WdArgs &a, const int strip, const int seg, const int lane, p64 *ring_sm) {
-    const Geom g = a.g;
+__device__ __forceinline__ void wd_march(const WdArgs &wa, const WdFrame &a, const int strip, const int seg, const int lane, p64 *ring_sm) {
+    const Geom g = wa.g;
     const int W = g.W, H = g.H, H1 = H - 1, S = g.S;
     const size_t P = g.plane();
 
@@ -54,8 +63,8 @@ __device__ __forceinline__ void wd_march(const WdArgs &a, const int strip, const
     L.lane_r = clampi((W - 1 - X0) >> 1, 0, 31);
     L.comp_r = (W - 1 - X0) & 1;
 
-    const int Y0 = seg * a.seg_rows;
-    const int Yend = min(Y0 + a.seg_rows, H);
+    const int Y0 = seg * wa.seg_rows;
+    const int Yend = min(Y0 + wa.seg_rows, H);
     const int Rbase = Y0 - 4;
 
     const bool out_lane = (lane >= PR_OUT_LO) && (lane <= PR_OUT_HI) && (L.x0 < S);
@@ -75,8 +84,8 @@ __device__ __forceinline__ void wd_march(const WdArgs &a, const int strip, const
     p64 fx, fy;
     {
         const int ro = clampi(Rbase, 0, H1) * S;
-        fx = load_pair<EDGE>(a.wx, ro, L);
-        fy = load_pair<EDGE>(a.wy, ro, L);
+        fx = load_pair<EDGE>(wa.wx, ro, L);
+        fy = load_pair<EDGE>(wa.wy, ro, L);
     }
 
     // warp row r (clamped), store it when it is a row of this segment, return the three channel pairs
@@ -89,8 +98,8 @@ __device__ __forceinline__ void wd_march(const WdArgs &a, const int strip, const
         for (int c = 0; c < 3; c++) B[c] = pk(warp_fetch(a.src + c * P, t0), warp_fetch(a.src + c * P, t1));
         {
             const int rn = clampi(r + 1, 0, H1) * S;
-            fx = load_pair<EDGE>(a.wx, rn, L);
-            fy = load_pair<EDGE>(a.wy, rn, L);
+            fx = load_pair<EDGE>(wa.wx, rn, L);
+            fy = load_pair<EDGE>(wa.wy, rn, L);
         }
         if (r >= Y0 && r < Yend && out_lane) { // (rows of the segment are never clamped)
             const size_t off = (size_t)r * S + L.x0;
@@ -161,15 +170,17 @@ __global__ void __launch_bounds__(WD_WARPS * 32, SF_WD_MINB) k_warp_derivs(WdArg
     const int lane = threadIdx.x & 31;
     const int work = blockIdx.x * WD_WARPS + (threadIdx.x >> 5);
     if (work >= a.nwork) return; // whole warp
-    const int strip = work % a.strips, seg = work / a.strips;
+    const int strip = work % a.strips, rest = work / a.strips, seg = rest % a.segs;
+    const WdFrame fr = a.f[rest / a.segs];
     const int X0 = strip * PR_OUT_W - 2 * PR_OUT_LO;
     p64 *ring_sm = ring + (threadIdx.x >> 5) * WD_RING;
-    if ((X0 < 0) || (X0 + 63 > a.g.W - 1)) wd_march<true>(a, strip, seg, lane, ring_sm);
-    else wd_march<false>(a, strip, seg, lane, ring_sm);
+    if ((X0 < 0) || (X0 + 63 > a.g.W - 1)) wd_march<true>(a, fr, strip, seg, lane, ring_sm);
+    else wd_march<false>(a, fr, strip, seg, lane, ring_sm);
 }
 
-void launch_warp_derivs(cudaStream_t st, Geom g, int num_sms, const float *src3, const float *wx, const float *wy, int factor,
-                        float *warped3, float *mask, float *derivs15) {
+void launch_warp_derivs_batch(cudaStream_t st, Geom g, int num_sms, const float *wx, const float *wy, int nframes,
+                              const float *const *src3, const int *factor, float *const *warped3, float *const *mask,
+                              float *const *derivs15) {
     // resident warps per SM (the same on every device of the box; relaxed atomics: one host thread per device may get here
     // at the same time)
     static std::atomic<int> resident{0};
@@ -180,21 +191,33 @@ void launch_warp_derivs(cudaStream_t st, Geom g, int num_sms, const float *src3,
         res = (blocks_per_sm > 0 ? blocks_per_sm : 1) * WD_WARPS;
         resident.store(res, std::memory_order_relaxed);
     }
-    WdArgs a;
-    a.g = g;
-    a.src = src3; a.wx = wx; a.wy = wy; a.factor = (float)factor;
-    a.warped = warped3; a.mask = mask; a.derivs = derivs15;
-    a.strips = (g.S + PR_OUT_W - 1) / PR_OUT_W;
-    // rows per segment: as many (strip, segment) items as fit ONE wave of resident warps, at least 16 rows
     if (g_wd_warps_per_sm > 0) res = g_wd_warps_per_sm;
-    int segs = (num_sms * res) / a.strips;
-    if (segs < 1) segs = 1;
-    int rows = (g.H + segs - 1) / segs;
-    if (rows < g_wd_min_rows) rows = g_wd_min_rows;
-    a.seg_rows = (rows + 3) & ~3;
-    segs = (g.H + a.seg_rows - 1) / a.seg_rows;
-    a.nwork = a.strips * segs;
-    launch_pdl(k_warp_derivs, dim3((a.nwork + WD_WARPS - 1) / WD_WARPS), dim3(WD_WARPS * 32), 0, st, a);
+    for (int f0 = 0; f0 < nframes; f0 += SF_WD_MAX_FRAMES) {
+        WdArgs a;
+        a.g = g;
+        a.wx = wx; a.wy = wy;
+        a.nframes = nframes - f0 < SF_WD_MAX_FRAMES ? nframes - f0 : SF_WD_MAX_FRAMES;
+        for (int k = 0; k < SF_WD_MAX_FRAMES; k++) {
+            const int f = f0 + (k < a.nframes ? k : 0);
+            a.f[k].src = src3[f]; a.f[k].factor = (float)factor[f];
+            a.f[k].warped = warped3[f]; a.f[k].mask = mask[f]; a.f[k].derivs = derivs15[f];
+        }
+        a.strips = (g.S + PR_OUT_W - 1) / PR_OUT_W;
+        // rows per segment: as many (frame, strip, segment) items as fit ONE wave of resident warps
+        int segs = (num_sms * res) / (a.strips * a.nframes);
+        if (segs < 1) segs = 1;
+        int rows = (g.H + segs - 1) / segs;
+        if (rows < g_wd_min_rows) rows = g_wd_min_rows;
+        a.seg_rows = (rows + 3) & ~3;
+        a.segs = (g.H + a.seg_rows - 1) / a.seg_rows;
+        a.nwork = a.strips * a.segs * a.nframes;
+        launch_pdl(k_warp_derivs, dim3((a.nwork + WD_WARPS - 1) / WD_WARPS), dim3(WD_WARPS * 32), 0, st, a);
+    }
+}
+
+void launch_warp_derivs(cudaStream_t st, Geom g, int num_sms, const float *src3, const float *wx, const float *wy, int factor,
+                        float *warped3, float *mask, float *derivs15) {
+    launch_warp_derivs_batch(st, g, num_sms, wx, wy, 1, &src3, &factor, &warped3, &mask, &derivs15);
 }
 
 } // namespace sf
