@@ -83,6 +83,17 @@ def test_mt_parity_S2_and_S4(ctx, mt_checker):
         check(g, r, "S=%d" % S)
 
 
+def test_mt_parity_S6_more_frames_than_one_warp_launch_takes(ctx, mt_checker):
+    """S = 6: 10 warped frames, i.e. two launches of the batched warp + derivative kernel (8 frames per launch,
+    sf_wderivs.cu)."""
+    S = 6
+    ims, wx, wy = mh.window(160, 96, S)
+    p = mh.params(S, niter_alter=1, niter_outer=2, rho=[1, 1, 1, 1, 1], omega=[0, 2, 1, 1, 1])
+    r = mh.run_cpu(*mt_checker, ims, wx, wy, p, SOR_REDBLACK)
+    g = mh.run_gpu(ctx, ims, wx, wy, p)
+    check(g, r, "S=%d" % S)
+
+
 def test_mt_pyramid_three_layers_zero_init(ctx, mt_checker):
     """Config 4 in small: layers = 3, p_scale = 0.9, zero initial flow, odd level widths (stride != width)."""
     ims, wx, wy = mh.window(250, 163, 3, zero_flow=True)
