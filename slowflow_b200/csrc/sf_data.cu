@@ -448,10 +448,13 @@ __global__ void __launch_bounds__(256) k_data_term(Geom g, DataTermDesc t, DataC
 }
 
 // ---- all multi-frame terms of one outer / inner iteration in one pointwise pass (see sf_internal.cuh)
+#ifndef SF_MT_TERMS_MINB
+#define SF_MT_TERMS_MINB 4 // resident CTAs per SM the register allocation aims at: 64 registers, 32 warps per SM (2: 101 registers, 12.5 ms per config-3 window; 3: 11.9; 4: 11.8; 5: 12.2)
+#endif
 // PC, PG: the colour / gradient penalties as compile-time functor ids (select_robust_function,
 // variational_aux_mt.cpp:889-926): one instantiation per pair instead of a switch per evaluation
 template <int PC, int PG>
-__global__ void __launch_bounds__(256) k_mt_terms(Geom g, MtTermsArgs ta, DataCommon cm) {
+__global__ void __launch_bounds__(256, SF_MT_TERMS_MINB) k_mt_terms(Geom g, MtTermsArgs ta, DataCommon cm) {
     pdl_enter();
     if (g.cancelled()) return;
     const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
