@@ -319,6 +319,7 @@ int sfgpu_create(int device, void *stream, sfgpu_ctx **out) {
     if (const char *e = getenv("SLOWFLOW_GPU_STAGED_COPIES")) c->staged_host_copies = atoi(e) != 0;
     if (const char *e = getenv("SLOWFLOW_GPU_HOST_MINCUT")) c->host_mincut = atoi(e) != 0;
     if (const char *e = getenv("SLOWFLOW_GPU_MT_DATA_VARIANT")) c->mt_data_variant = atoi(e);
+    if (const char *e = getenv("SLOWFLOW_GPU_MT_TERMS_SCALAR")) c->mt_terms_scalar = atoi(e) != 0;
     if (const char *e = getenv("SLOWFLOW_GPU_MT_WARP_VARIANT")) c->mt_warp_variant = atoi(e);
     c->num_sms = prop.multiProcessorCount;
     if (stream) {

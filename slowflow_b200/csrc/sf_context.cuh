@@ -30,6 +30,7 @@ struct sfgpu_ctx {
     int data_variant = 0; // 0 fused marching warp+data-term kernel, 1 separate warp + tile kernel (env SLOWFLOW_GPU_DATA_VARIANT)
     int sor_fuse = 0;    // 0 = auto
     int mt_warp_variant = 0; // 0: fused warp + per-frame derivatives (sf_wderivs.cu), 1: k_warp + k_data_term<DK_DERIVS> (env SLOWFLOW_GPU_MT_WARP_VARIANT)
+    bool mt_terms_scalar = false; // env SLOWFLOW_GPU_MT_TERMS_SCALAR: one column per thread in the all-terms pass (A/B switch)
     int mt_data_variant = 0; // 0: per-frame derivative planes + one pointwise all-terms pass, 1: one fused kernel per term (env SLOWFLOW_GPU_MT_DATA_VARIANT)
 
     // ---- level workspace (one allocation, re-made when the geometry grows)

@@ -18,6 +18,7 @@
 // Border semantics follow image.c:400-526 (clamped columns, folded vertical taps); tiles that do not
 // touch the image border take a branch-free path.
 #include "sf_internal.cuh"
+#include "sf_pack.cuh"
 #include "sf_penalty.cuh"
 #include "sf_stencil.cuh"
 
@@ -533,6 +534,295 @@ __global__ void __launch_bounds__(256, SF_MT_TERMS_MINB) k_mt_terms(Geom g, MtTe
     cm.a11[o] = acc.a11; cm.a12[o] = acc.a12; cm.a22[o] = acc.a22; cm.b1[o] = acc.b1; cm.b2[o] = acc.b2;
 }
 
+// ---- the same pass with TWO columns per thread on the packed-fp32 pipe (sf_pack.cuh).  k_mt_terms is instruction bound
+// (ncu: ~3200 thread instructions per pixel for the six terms of config 3, issue slots 59 % busy at 33 % of the DRAM
+// peak): with a (column 2l, column 2l+1) pair in every 64-bit register the loads become LDG.64 and the term arithmetic
+// FFMA2 / FMUL2, i.e. half the instructions per pixel.  The terms below are term_mt_succ / term_mt_ref with the products
+// grouped so that every update of A,b is one packed fma (h = g * I_a once, then fma(h, I_b, acc)); the results agree with
+// the scalar forms -- which stay the operator twins (k_data_term<DK_MT_*>) -- to rounding.
+struct Derivs2 {
+    p64 ix[3], iy[3], iz[3], ixx[3], ixy[3], iyy[3], ixz[3], iyz[3];
+};
+struct Acc2 {
+    p64 a11, a12, a22, b1, b2;
+};
+
+// colour part shared by both terms: acc += g * (gx, gy) (x) (gx, gy), b -= g * iz * (gx, gy)
+__device__ __forceinline__ void acc_color2(Acc2 &acc, p64 ga, p64 gb, p64 gx, p64 gy, p64 niz) {
+    const p64 kx = mul2(ga, gx), ky = mul2(ga, gy);
+    acc.a11 = fma2(kx, gx, acc.a11);
+    acc.a12 = fma2(kx, gy, acc.a12);
+    acc.a22 = fma2(ky, gy, acc.a22);
+    acc.b1 = fma2(mul2(gb, gx), niz, acc.b1);
+    acc.b2 = fma2(mul2(gb, gy), niz, acc.b2);
+}
+// gradient part: ga1/ga2 weight the A updates of the x / y residual, gb1/gb2 the b updates
+__device__ __forceinline__ void acc_grad2(Acc2 &acc, p64 ga1, p64 ga2, p64 gb1, p64 gb2, p64 gxx, p64 gxy, p64 gyy, p64 nixz,
+                                          p64 niyz) {
+    const p64 k1x = mul2(ga1, gxx), k1y = mul2(ga1, gxy), k2x = mul2(ga2, gxy), k2y = mul2(ga2, gyy);
+    acc.a11 = fma2(k1x, gxx, fma2(k2x, gxy, acc.a11));
+    acc.a12 = fma2(k1x, gxy, fma2(k2x, gyy, acc.a12));
+    acc.a22 = fma2(k2y, gyy, fma2(k1y, gxy, acc.a22));
+    acc.b1 = fma2(mul2(gb1, gxx), nixz, fma2(mul2(gb2, gxy), niyz, acc.b1));
+    acc.b2 = fma2(mul2(gb2, gyy), niyz, fma2(mul2(gb1, gxy), nixz, acc.b2));
+}
+
+template <int PC, int PG>
+__device__ __forceinline__ void term_mt_succ2(const Derivs2 &d, p64 u, p64 v, p64 m, float wd, float wg, float s, const p64 wc[3],
+                                              int dt_norm, const Penalty &pc, const Penalty &pg, Acc2 &acc) {
+    const p64 dnorm = splat2(0.1f * 0.1f), mone = splat2(-1.0f);
+    const float f = s, f1 = s + 1.0f;
+    const p64 g = splat2(f - f1); // -1 for every time factor of the path (see term_mt_succ)
+    if (wd != 0.0f) {
+        p64 r[3], gx[3], gy[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            gx[c] = mul2(g, d.ix[c]);
+            gy[c] = mul2(g, d.iy[c]);
+            r[c] = mul2(wc[c], fma2(gy[c], v, fma2(gx[c], u, d.iz[c])));
+        }
+        const p64 mw = mul2(m, splat2(wd));
+        if (!dt_norm) {
+            const p64 t = mul2(mw, penalty_deriv_v2<PC>(pc, fma2(r[2], r[2], fma2(r[1], r[1], mul2(r[0], r[0])))));
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const p64 gg = mul2(t, wc[c]);
+                acc_color2(acc, gg, gg, gx[c], gy[c], mul2(d.iz[c], mone));
+            }
+        } else {
+            p64 inv[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) inv[c] = rcp2(fma2(gy[c], gy[c], fma2(gx[c], gx[c], dnorm)));
+            const p64 x = fma2(mul2(r[2], r[2]), inv[2], fma2(mul2(r[1], r[1]), inv[1], mul2(mul2(r[0], r[0]), inv[0])));
+            const p64 t = mul2(mw, penalty_deriv_v2<PC>(pc, x));
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const p64 gg = mul2(mul2(t, inv[c]), wc[c]);
+                acc_color2(acc, gg, gg, gx[c], gy[c], mul2(d.iz[c], mone));
+            }
+        }
+    }
+    p64 rx[3], ry[3], gxx[3], gyy[3], gxy[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        gxx[c] = mul2(g, d.ixx[c]);
+        gyy[c] = mul2(g, d.iyy[c]);
+        gxy[c] = mul2(g, d.ixy[c]);
+        rx[c] = mul2(wc[c], fma2(gxy[c], v, fma2(gxx[c], u, d.ixz[c])));
+        ry[c] = mul2(wc[c], fma2(gyy[c], v, fma2(gxy[c], u, d.iyz[c])));
+    }
+    const p64 mw = mul2(m, splat2(wg));
+    if (!dt_norm) {
+        p64 x = mul2(rx[0], rx[0]);
+        x = fma2(ry[0], ry[0], x);
+        x = fma2(rx[1], rx[1], x);
+        x = fma2(ry[1], ry[1], x);
+        x = fma2(rx[2], rx[2], x);
+        x = fma2(ry[2], ry[2], x);
+        const p64 t = mul2(mw, penalty_deriv_v2<PG>(pg, x));
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const p64 gg = mul2(t, wc[c]);
+            acc_grad2(acc, gg, gg, gg, gg, gxx[c], gxy[c], gyy[c], mul2(d.ixz[c], mone), mul2(d.iyz[c], mone));
+        }
+    } else {
+        p64 ivx[3], ivy[3];
+        p64 x = splat2(0.0f);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const p64 xy = fma2(gxy[c], gxy[c], dnorm);
+            ivx[c] = rcp2(fma2(gxx[c], gxx[c], xy));
+            ivy[c] = rcp2(fma2(gyy[c], gyy[c], xy));
+            x = fma2(mul2(rx[c], rx[c]), ivx[c], x);
+            x = fma2(mul2(ry[c], ry[c]), ivy[c], x);
+        }
+        const p64 t = mul2(mw, penalty_deriv_v2<PG>(pg, x));
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const p64 tw = mul2(t, wc[c]);
+            const p64 g1 = mul2(tw, ivx[c]), g2 = mul2(tw, ivy[c]);
+            acc_grad2(acc, g1, g2, g1, g2, gxx[c], gxy[c], gyy[c], mul2(d.ixz[c], mone), mul2(d.iyz[c], mone));
+        }
+    }
+}
+
+template <int PC, int PG>
+__device__ __forceinline__ void term_mt_ref2(const Derivs2 &d, p64 u, p64 v, p64 m, float wd, float wg, float s, const p64 wc[3],
+                                             int dt_norm, const Penalty &pc, const Penalty &pg, Acc2 &acc) {
+    const p64 dnorm = splat2(0.1f * 0.1f), mone = splat2(-1.0f);
+    const float fsq = s * s;
+    const float f = (s >= 0.0f) ? -s : s;
+    const p64 f2 = splat2(f), fsq2 = splat2(fsq);
+    const p64 fu = mul2(f2, u), fv = mul2(f2, v);
+    const p64 ifsq = splat2(1.0f / fsq); // the un-normalised branches divide by factorsq (:452-471, :518-530)
+    if (wd != 0.0f) {
+        p64 r[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) r[c] = mul2(wc[c], fma2(d.iy[c], fv, fma2(d.ix[c], fu, d.iz[c])));
+        const p64 mw = mul2(m, splat2(wd));
+        if (!dt_norm) {
+            const p64 x = mul2(fma2(r[2], r[2], fma2(r[1], r[1], mul2(r[0], r[0]))), ifsq);
+            const p64 t = mul2(mul2(mw, penalty_deriv_v2<PC>(pc, x)), ifsq);
+            const p64 tf = mul2(t, f2);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const p64 gb = mul2(tf, wc[c]);
+                const p64 ga = (c == 2) ? tf : mul2(gb, f2); // channel 3 drops the weight and one factor (as written, :469)
+                acc_color2(acc, ga, gb, d.ix[c], d.iy[c], mul2(d.iz[c], mone));
+            }
+        } else {
+            p64 inv[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                inv[c] = rcp2(fma2(mul2(fsq2, d.iy[c]), d.iy[c], fma2(mul2(fsq2, d.ix[c]), d.ix[c], dnorm)));
+            const p64 x = fma2(mul2(r[2], r[2]), inv[2], fma2(mul2(r[1], r[1]), inv[1], mul2(mul2(r[0], r[0]), inv[0])));
+            const p64 tf = mul2(mul2(mw, penalty_deriv_v2<PC>(pc, x)), f2);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const p64 gb = mul2(mul2(tf, inv[c]), wc[c]);
+                acc_color2(acc, mul2(gb, f2), gb, d.ix[c], d.iy[c], mul2(d.iz[c], mone));
+            }
+        }
+    }
+    p64 rx[3], ry[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        rx[c] = mul2(wc[c], fma2(d.ixy[c], fv, fma2(d.ixx[c], fu, d.ixz[c])));
+        ry[c] = mul2(wc[c], fma2(d.iyy[c], fv, fma2(d.ixy[c], fu, d.iyz[c])));
+    }
+    const p64 mw = mul2(m, splat2(wg));
+    if (!dt_norm) {
+        p64 x = mul2(rx[0], rx[0]);
+        x = fma2(ry[0], ry[0], x);
+        x = fma2(rx[1], rx[1], x);
+        x = fma2(ry[1], ry[1], x);
+        x = fma2(rx[2], rx[2], x);
+        x = fma2(ry[2], ry[2], x);
+        const p64 t = mul2(mul2(mw, penalty_deriv_v2<PG>(pg, mul2(x, ifsq))), ifsq);
+        const p64 tf = mul2(t, f2);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const p64 gb = mul2(tf, wc[c]);
+            p64 ga = mul2(gb, f2);
+            if (c == 0) ga = mul2(ga, fsq2); // channel 1 carries an extra factorsq (as written, :528-530)
+            acc_grad2(acc, ga, ga, gb, gb, d.ixx[c], d.ixy[c], d.iyy[c], mul2(d.ixz[c], mone), mul2(d.iyz[c], mone));
+        }
+    } else {
+        p64 ivx[3], ivy[3];
+        p64 x = splat2(0.0f);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const p64 xy = fma2(mul2(fsq2, d.ixy[c]), d.ixy[c], dnorm);
+            ivx[c] = rcp2(fma2(mul2(fsq2, d.ixx[c]), d.ixx[c], xy));
+            ivy[c] = rcp2(fma2(mul2(fsq2, d.iyy[c]), d.iyy[c], xy));
+            x = fma2(mul2(rx[c], rx[c]), ivx[c], x);
+            x = fma2(mul2(ry[c], ry[c]), ivy[c], x);
+        }
+        const p64 tf = mul2(mul2(mw, penalty_deriv_v2<PG>(pg, x)), f2);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const p64 tw = mul2(tf, wc[c]);
+            const p64 gb1 = mul2(tw, ivx[c]), gb2 = mul2(tw, ivy[c]);
+            acc_grad2(acc, mul2(gb1, f2), mul2(gb2, f2), gb1, gb2, d.ixx[c], d.ixy[c], d.iyy[c], mul2(d.ixz[c], mone),
+                      mul2(d.iyz[c], mone));
+        }
+    }
+}
+
+#ifndef SF_MT_TERMS2_MINB
+#define SF_MT_TERMS2_MINB 2 // resident CTAs per SM the register allocation aims at (128 registers, 16 warps = 1024 pixels per SM)
+#endif
+template <int PC, int PG>
+__global__ void __launch_bounds__(256, SF_MT_TERMS2_MINB) k_mt_terms2(Geom g, MtTermsArgs ta, DataCommon cm) {
+    pdl_enter();
+    if (g.cancelled()) return;
+    const int i = (blockIdx.x * 32 + threadIdx.x) * 2, j = blockIdx.y * 8 + threadIdx.y; // columns i, i + 1
+    if (i >= g.S || j >= g.H) return;
+    const size_t P = g.plane(), o = (size_t)j * g.S + i;
+    auto store2 = [](float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); };
+    if (i >= g.W) { // padding columns: defined zeros
+        store2(cm.a11 + o, 0.f, 0.f); store2(cm.a12 + o, 0.f, 0.f); store2(cm.a22 + o, 0.f, 0.f);
+        store2(cm.b1 + o, 0.f, 0.f); store2(cm.b2 + o, 0.f, 0.f);
+        return;
+    }
+    const int W1 = g.W - 1, H1 = g.H - 1;
+    const bool v1 = i + 1 <= W1; // the pair's second column is a pixel (else padding: computed on whatever is there, stored as 0)
+    const p64 zero2 = splat2(0.0f), one2 = splat2(1.0f), half2 = splat2(0.5f), mone = splat2(-1.0f);
+    const p64 u = cm.du ? ldg2(cm.du + o) : zero2, v = cm.dv ? ldg2(cm.dv + o) : zero2;
+    p64 wc[3] = {one2, one2, one2};
+    if (cm.chw) {
+        wc[0] = ldg2(cm.chw + o); wc[1] = ldg2(cm.chw + o + cm.chw_pstride); wc[2] = ldg2(cm.chw + o + 2 * cm.chw_pstride);
+    }
+    // occlusion / window factor of variational_mt.cpp:293-320 per direction: (1 * (sel / fac)) with sel in {0, 1}
+    p64 occ_past = one2, occ_future = one2;
+    if (cm.occ) {
+        const p64 oc = ldg2(cm.occ + o);
+        const float oc0 = lo_of(oc), oc1 = hi_of(oc);
+        const float q0 = 1.0f / ((1.0f + ((oc0 == 0.0f) ? 1.0f : 0.0f)) * cm.data_norm);
+        const float q1 = 1.0f / ((1.0f + ((oc1 == 0.0f) ? 1.0f : 0.0f)) * cm.data_norm);
+        occ_past = pk(oc0 >= 0.0f ? q0 : 0.0f, oc1 >= 0.0f ? q1 : 0.0f);
+        occ_future = pk(oc0 <= 0.0f ? q0 : 0.0f, oc1 <= 0.0f ? q1 : 0.0f);
+    }
+    Acc2 acc;
+    acc.a11 = acc.a12 = acc.a22 = acc.b1 = acc.b2 = zero2;
+#pragma unroll 1
+    for (int k = 0; k < ta.nterms; k++) {
+        const MtTerm t = ta.term[k];
+        const float *IA = ta.I[t.fa] + o, *IB = ta.I[t.fb] + o, *DA = ta.D[t.fa] + o, *DB = ta.D[t.fb] + o;
+        Derivs2 d;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            d.iz[c] = sub2(ldg2(IA + c * P), ldg2(IB + c * P));
+            const p64 xa = ldg2(DA + (0 + c) * P), xb = ldg2(DB + (0 + c) * P);
+            const p64 ya = ldg2(DA + (3 + c) * P), yb = ldg2(DB + (3 + c) * P);
+            d.ix[c] = mul2(add2(xb, xa), half2);
+            d.iy[c] = mul2(add2(yb, ya), half2);
+            d.ixz[c] = sub2(xa, xb);
+            d.iyz[c] = sub2(ya, yb);
+            d.ixx[c] = mul2(add2(ldg2(DB + (6 + c) * P), ldg2(DA + (6 + c) * P)), half2);
+            d.ixy[c] = mul2(add2(ldg2(DB + (9 + c) * P), ldg2(DA + (9 + c) * P)), half2);
+            d.iyy[c] = mul2(add2(ldg2(DB + (12 + c) * P), ldg2(DA + (12 + c) * P)), half2);
+        }
+        p64 m = ldg2(ta.mask[t.mask_frame] + o);
+        if (cm.occ) m = mul2((t.dir == 0) ? occ_past : occ_future, m);
+        if (t.kind == DK_MT_SUCC) term_mt_succ2<PC, PG>(d, u, v, m, t.wd, t.wg, t.s, wc, cm.dt_norm, cm.pc, cm.pg, acc);
+        else term_mt_ref2<PC, PG>(d, u, v, m, t.wd, t.wg, t.s, wc, cm.dt_norm, cm.pc, cm.pg, acc);
+    }
+    {
+        // b += div(psi grad w) and the 2x2 block inverse (variational_aux.c:158-179, solver.c:101-106): left edge, right
+        // edge, upper edge, lower edge; neighbours outside the image are the pixel itself, their diffusivities 0
+        const p64 hr = ldg2(cm.ph + o), vb = ldg2(cm.pv + o);
+        const p64 hl = pk((i > 0) ? __ldg(cm.ph + o - 1) : 0.0f, lo_of(hr));
+        const p64 vt = (j > 0) ? ldg2(cm.pv + o - g.S) : zero2;
+        const size_t ot = (j > 0) ? o - g.S : o, ob = (j < H1) ? o + g.S : o;
+        const p64 nhl = mul2(hl, mone), nvt = mul2(vt, mone);
+        auto lap = [&](const float *w, p64 b) {
+            const p64 wcn = ldg2(w + o), wt = ldg2(w + ot), wb = ldg2(w + ob);
+            const float c0 = lo_of(wcn), c1 = hi_of(wcn);
+            const p64 wl = pk((i > 0) ? __ldg(w + o - 1) : c0, c0);
+            const p64 wr = pk((i < W1) ? c1 : c0, (i + 1 < W1) ? __ldg(w + o + 2) : c1);
+            b = fma2(nhl, sub2(wcn, wl), b);
+            b = fma2(hr, sub2(wr, wcn), b);
+            b = fma2(nvt, sub2(wcn, wt), b);
+            return fma2(vb, sub2(wb, wcn), b);
+        };
+        acc.b1 = lap(cm.lap_u, acc.b1);
+        acc.b2 = lap(cm.lap_v, acc.b2);
+        const p64 sp = add2(add2(add2(hl, hr), vt), vb);
+        const p64 D11 = add2(acc.a22, sp), D22 = add2(acc.a11, sp);
+        const p64 det = fma2(mul2(acc.a12, acc.a12), mone, mul2(D11, D22));
+        const p64 rdet = rcp2(det);
+        acc.a11 = mul2(D11, rdet);
+        acc.a22 = mul2(D22, rdet);
+        acc.a12 = mul2(mul2(acc.a12, mone), rdet);
+    }
+    store2(cm.a11 + o, lo_of(acc.a11), v1 ? hi_of(acc.a11) : 0.0f);
+    store2(cm.a12 + o, lo_of(acc.a12), v1 ? hi_of(acc.a12) : 0.0f);
+    store2(cm.a22 + o, lo_of(acc.a22), v1 ? hi_of(acc.a22) : 0.0f);
+    store2(cm.b1 + o, lo_of(acc.b1), v1 ? hi_of(acc.b1) : 0.0f);
+    store2(cm.b2 + o, lo_of(acc.b2), v1 ? hi_of(acc.b2) : 0.0f);
+}
+
 bool data_term_device_init() { // per device, called by sfgpu_create
     const int smem = (int)(DT_SMEM_FLOATS * sizeof(float));
     return cudaFuncSetAttribute(k_data_term<DK_TWO_FRAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
@@ -562,17 +852,34 @@ void launch_frame_derivs(cudaStream_t st, Geom g, const float *image3, float *de
 template <int PC>
 static void launch_mt_terms_pg(cudaStream_t st, dim3 grid, dim3 b, Geom g, const MtTermsArgs &ta, const DataCommon &cm) {
     switch (cm.pg.type) {
-    case SF_ROBUST_QUADRATIC: launch_pdl(k_mt_terms<PC, SF_ROBUST_QUADRATIC>, grid, b, 0, st, g, ta, cm); break;
-    case SF_ROBUST_MODL1: launch_pdl(k_mt_terms<PC, SF_ROBUST_MODL1>, grid, b, 0, st, g, ta, cm); break;
-    case SF_ROBUST_LORENTZIAN: launch_pdl(k_mt_terms<PC, SF_ROBUST_LORENTZIAN>, grid, b, 0, st, g, ta, cm); break;
-    case SF_ROBUST_TRUNC_MODL1: launch_pdl(k_mt_terms<PC, SF_ROBUST_TRUNC_MODL1>, grid, b, 0, st, g, ta, cm); break;
-    case SF_ROBUST_GEMAN_MCCLURE: launch_pdl(k_mt_terms<PC, SF_ROBUST_GEMAN_MCCLURE>, grid, b, 0, st, g, ta, cm); break;
-    default: launch_pdl(k_mt_terms<PC, -1>, grid, b, 0, st, g, ta, cm); break;
+    case SF_ROBUST_QUADRATIC: launch_pdl(k_mt_terms2<PC, SF_ROBUST_QUADRATIC>, grid, b, 0, st, g, ta, cm); break;
+    case SF_ROBUST_MODL1: launch_pdl(k_mt_terms2<PC, SF_ROBUST_MODL1>, grid, b, 0, st, g, ta, cm); break;
+    case SF_ROBUST_LORENTZIAN: launch_pdl(k_mt_terms2<PC, SF_ROBUST_LORENTZIAN>, grid, b, 0, st, g, ta, cm); break;
+    case SF_ROBUST_TRUNC_MODL1: launch_pdl(k_mt_terms2<PC, SF_ROBUST_TRUNC_MODL1>, grid, b, 0, st, g, ta, cm); break;
+    case SF_ROBUST_GEMAN_MCCLURE: launch_pdl(k_mt_terms2<PC, SF_ROBUST_GEMAN_MCCLURE>, grid, b, 0, st, g, ta, cm); break;
+    default: launch_pdl(k_mt_terms2<PC, -1>, grid, b, 0, st, g, ta, cm); break;
     }
 }
 
-void launch_mt_terms(cudaStream_t st, Geom g, const MtTermsArgs &ta, const DataCommon &cm) {
-    dim3 b(32, 8), grid((g.S + 31) / 32, (g.H + 7) / 8);
+// every plane the packed kernel touches must start on an 8-byte boundary (rows do: S is a multiple of 4 floats)
+static bool mt_terms_pairs_aligned(const MtTermsArgs &ta, const DataCommon &cm) {
+    uintptr_t bits = 0;
+    auto add = [&](const void *p) { bits |= reinterpret_cast<uintptr_t>(p); };
+    for (int k = 0; k < ta.nterms; k++) {
+        const MtTerm &t = ta.term[k];
+        add(ta.I[t.fa]); add(ta.I[t.fb]); add(ta.D[t.fa]); add(ta.D[t.fb]); add(ta.mask[t.mask_frame]);
+    }
+    add(cm.du); add(cm.dv); add(cm.chw); add(cm.occ); add(cm.ph); add(cm.pv); add(cm.lap_u); add(cm.lap_v);
+    add(cm.a11); add(cm.a12); add(cm.a22); add(cm.b1); add(cm.b2);
+    return (bits & 7) == 0 && (cm.chw_pstride & 1) == 0;
+}
+
+void launch_mt_terms(cudaStream_t st, Geom g, const MtTermsArgs &ta, const DataCommon &cm, bool force_scalar) {
+    if (force_scalar || !mt_terms_pairs_aligned(ta, cm)) { // one column per thread, penalties by run-time switch
+        launch_pdl(k_mt_terms<-1, -1>, dim3((g.S + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, st, g, ta, cm);
+        return;
+    }
+    dim3 b(32, 8), grid((g.S + 63) / 64, (g.H + 7) / 8);
     switch (cm.pc.type) {
     case SF_ROBUST_QUADRATIC: launch_mt_terms_pg<SF_ROBUST_QUADRATIC>(st, grid, b, g, ta, cm); break;
     case SF_ROBUST_MODL1: launch_mt_terms_pg<SF_ROBUST_MODL1>(st, grid, b, g, ta, cm); break;

@@ -149,7 +149,9 @@ void launch_warp_derivs(cudaStream_t st, Geom g, int num_sms, const float *src3,
 void launch_warp_derivs_batch(cudaStream_t st, Geom g, int num_sms, const float *wx, const float *wy, int nframes,
                               const float *const *src3, const int *factor, float *const *warped3, float *const *mask,
                               float *const *derivs15);
-void launch_mt_terms(cudaStream_t st, Geom g, const MtTermsArgs &ta, const DataCommon &cm);
+// force_scalar: the one-column-per-thread form with run-time penalty switch (A/B switch of the tests; also taken when a
+// plane is not 8-byte aligned) instead of the packed two-columns-per-thread kernel
+void launch_mt_terms(cudaStream_t st, Geom g, const MtTermsArgs &ta, const DataCommon &cm, bool force_scalar = false);
 // K1+K2 fused, marching form (sf_prep.cu): warp + derivatives + two-frame data term + Laplacian + block inverse.
 // Writes the same five planes as launch_warp + launch_data_term(fuse_system) without the warped image in HBM.
 void launch_prep_two_frame(cudaStream_t st, Geom g, int num_sms, const float *im1, const float *im2, const float *wx, const float *wy, const float *du, const float *dv, const float *ph, const float *pv,

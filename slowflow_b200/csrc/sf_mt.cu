@@ -614,7 +614,7 @@ static int compute_one_level(LevelCtx &L, float avg_change[2]) { // variational_
     }
     auto launch_terms = [&](const Geom &gk, DataCommon &cm) { // all data terms of one linearisation (:343-361)
         if (L.fused_terms) {
-            launch_mt_terms(st, gk, ta, cm);
+            launch_mt_terms(st, gk, ta, cm, c->mt_terms_scalar);
             c->prof_acc.kernel_launches++;
             c->prof_acc.data_launches++;
             c->prof_acc.data_pixels += (long long)g.W * g.H;

@@ -53,4 +53,18 @@ __device__ __forceinline__ p64 shfl_down2(p64 v) {
     return pk(__shfl_down_sync(0xffffffffu, lo_of(v), 1), __shfl_down_sync(0xffffffffu, hi_of(v), 1));
 }
 
+// 1/x: MUFU.RCP (1 ulp) refined by one Newton step on the packed pipe (~0.5 ulp; the reference divides, divps)
+__device__ __forceinline__ p64 rcp2(p64 x) {
+    float a, b;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(lo_of(x)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(hi_of(x)));
+    const p64 r = pk(a, b);
+    const p64 e = fma2(mul2(x, splat2(-1.0f)), r, splat2(1.0f)); // 1 - x*r
+    return fma2(r, e, r);
+}
+// a - b on the packed pipe
+__device__ __forceinline__ p64 sub2(p64 a, p64 b) { return fma2(b, splat2(-1.0f), a); }
+// two consecutive floats (8-byte aligned) through the read-only path
+__device__ __forceinline__ p64 ldg2(const float *p) { return __ldg(reinterpret_cast<const p64 *>(p)); }
+
 } // namespace sf

@@ -8,6 +8,7 @@
 // sqrt(s^2) against tau (trunc_modified_l1_norm.h:20-54).
 #pragma once
 #include "sf_internal.cuh"
+#include "sf_pack.cuh"
 
 namespace sf {
 
@@ -61,6 +62,31 @@ __device__ __forceinline__ float penalty_deriv_vt(const Penalty &p, float xsq) {
         return penalty_half_rsqrt(xsq + p.eps_sq_f);
     } else {
         return penalty_deriv_v(p, xsq);
+    }
+}
+
+// psi'(s^2) of TWO pixels on the packed pipe (multi-frame terms kernel, two columns per thread): the same formulas with
+// the MUFU seeds taken per half and the Newton steps / products as FFMA2 / FMUL2
+template <int TYPE>
+__device__ __forceinline__ p64 penalty_deriv_v2(const Penalty &p, p64 xsq) {
+    if constexpr (TYPE == SF_ROBUST_QUADRATIC) {
+        return splat2(1.0f);
+    } else if constexpr (TYPE == SF_ROBUST_LORENTZIAN) {
+        return rcp2(add2(xsq, splat2(2.0f * p.eps_sq_f)));
+    } else if constexpr (TYPE == SF_ROBUST_GEMAN_MCCLURE) {
+        const p64 e = splat2(p.eps_sq_f);
+        p64 t = add2(e, xsq);
+        t = mul2(t, t);
+        return mul2(fma2(splat2(2.0f), xsq, e), rcp2(t));
+    } else if constexpr (TYPE == SF_ROBUST_MODL1) {
+        const p64 x = add2(xsq, splat2(p.eps_sq_f));
+        const p64 r = pk(rsqrtf(lo_of(x)), rsqrtf(hi_of(x)));
+        const p64 h = mul2(r, splat2(0.5f));
+        // one Newton step on rsqrt, halved: h + h/2 (1 - x r^2)
+        const p64 e = fma2(mul2(mul2(x, splat2(-1.0f)), r), r, splat2(1.0f));
+        return fma2(mul2(h, splat2(0.5f)), e, h);
+    } else { // truncated L1 (a compare per pixel) and the run-time switch: per half
+        return pk(penalty_deriv_vt<TYPE>(p, lo_of(xsq)), penalty_deriv_vt<TYPE>(p, hi_of(xsq)));
     }
 }
 

@@ -42,16 +42,6 @@ constexpr int PR_WARPS = 2;                             // warps per CTA (indepe
 constexpr int PR_RING = 60 * 32;                        // packed values of one warp's windows
 
 
-// 1/x: MUFU.RCP (1 ulp) refined by one Newton step on the packed pipe (~0.5 ulp; the reference divides, divps)
-__device__ __forceinline__ p64 rcp2(p64 x) {
-    float a, b;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(lo_of(x)));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(hi_of(x)));
-    const p64 r = pk(a, b);
-    const p64 e = fma2(mul2(x, splat2(-1.0f)), r, splat2(1.0f)); // 1 - x*r
-    return fma2(r, e, r);
-}
-
 struct PrepArgs {
     Geom g;
     const float *im1, *im2; // 3 planes each

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import mt_helpers as mh
+from slowflow_b200 import ColorImage
 from slowflow_b200.metrics import epe
 from oracle.pyoracle import SOR_LEX, SOR_REDBLACK
 
@@ -247,3 +248,50 @@ def test_mt_data_pass_variants_agree(monkeypatch):
     print("fused vs per-term data pass: mean %.3e max %.3e" % (mean, mx))
     assert mean <= 1e-4 and mx <= 1e-2
     assert float((a["occ"].array != b["occ"].array).mean()) <= 0.002
+
+
+@pytest.mark.parametrize("kw", [
+    dict(robust_color=4, robust_color_eps=0.5),
+    dict(robust_color=1),
+    dict(robust_color=2, robust_color_eps=0.5, robust_grad=4, robust_grad_eps=0.5),
+    dict(robust_color=3, robust_color_eps=0.001, robust_color_truncation=5.0),
+    # quadratic data penalty: unstable reference iteration (see test_mt_parity_small) -> the arithmetic over one iteration
+    dict(robust_color=0, robust_reg=2, robust_reg_eps=0.5, niter_alter=1, niter_outer=1),
+    dict(dataterm=0),
+    dict(dataterm=0, omega=[0, 0], niter_inner=2),
+    dict(one_direction=1, niter_inner=2),
+])
+def test_mt_terms_packed_vs_scalar(monkeypatch, kw):
+    """The all-terms pass with two columns per thread on the packed pipe (k_mt_terms2, the default) against the
+    one-column-per-thread kernel with the scalar term functions (SLOWFLOW_GPU_MT_TERMS_SCALAR=1), on an ODD width
+    (the last pair of a row is pixel + padding), with channel weights, over every penalty and both dataterm branches."""
+    from slowflow_b200 import Context
+    w, h = 253, 97
+    ims, wx, wy = mh.window(w, h, 3)
+    rng = np.random.default_rng(5)
+    chw = ColorImage.from_array(rng.uniform(0.5, 1.5, size=(3, h, w)).astype(np.float32))
+    p = mh.params(3, **{**dict(niter_alter=2, niter_outer=2), **kw})
+    with Context(0) as c0:
+        a = mh.run_gpu(c0, ims, wx, wy, p, chw)
+    monkeypatch.setenv("SLOWFLOW_GPU_MT_TERMS_SCALAR", "1")
+    with Context(0) as c1:
+        b = mh.run_gpu(c1, ims, wx, wy, p, chw)
+    assert np.isfinite(a["wx"].array).all() and np.isfinite(a["wy"].array).all()
+    mean, mx = epe(a["wx"].array, a["wy"].array, b["wx"].array, b["wy"].array, border=0)
+    moved = float(np.abs(a["wx"].array - wx.array).mean())
+    print("packed vs scalar terms %s: mean %.3e max %.3e (moved %.3f)" % (kw, mean, mx, moved))
+    assert moved > 1e-3
+    assert mean <= 1e-4 and mx <= 1e-2
+
+
+def test_mt_channel_weights_parity(ctx, mt_checker):
+    """channel_w (the rawWeighting planes, variational_mt.cpp:343-361) through the default all-terms pass against the
+    reference driver, on an odd width."""
+    w, h = 253, 131
+    ims, wx, wy = mh.window(w, h, 3)
+    rng = np.random.default_rng(11)
+    chw = ColorImage.from_array(rng.uniform(0.5, 1.5, size=(3, h, w)).astype(np.float32))
+    p = mh.params(3, niter_alter=2, niter_outer=3, robust_color=4, robust_color_eps=0.5)
+    r = mh.run_cpu(*mt_checker, ims, wx, wy, p, SOR_REDBLACK, chw)
+    g = mh.run_gpu(ctx, ims, wx, wy, p, chw)
+    check(g, r, "channel weights")
