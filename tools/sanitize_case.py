@@ -55,6 +55,17 @@ with Context(0) as ctx:
     fx, fy = Image(97, 61), Image(97, 61)
     ctx.epic(fx, fy, ColorImage.from_array(im), m, edges, None)
     assert np.isfinite(fx.array).all()
+    # packed all-terms pass (two columns per thread): odd width with channel weights, un-normalised data term
+    ims, wx, wy = mh.window(93, 41, 3)
+    chw = ColorImage.from_array(np.random.RandomState(3).uniform(0.5, 1.5, size=(3, 41, 93)).astype(np.float32))
+    for kw in (dict(robust_color=4, robust_color_eps=0.5), dict(dataterm=0, robust_color=3, robust_color_truncation=5.0)):
+        g = mh.run_gpu(ctx, ims, wx, wy, mh.params(3, niter_alter=1, niter_outer=1, **kw), chw)
+        assert np.isfinite(g["wx"].array).all()
+os.environ["SLOWFLOW_GPU_MT_TERMS_SCALAR"] = "1"
+with Context(0) as ctx:
+    ims, wx, wy = mh.window(93, 41, 3)
+    g = mh.run_gpu(ctx, ims, wx, wy, mh.params(3, niter_alter=1, niter_outer=1))
+    assert np.isfinite(g["wx"].array).all()
 os.environ["SLOWFLOW_GPU_MT_DATA_VARIANT"] = "1"
 with Context(0) as ctx:
     ims, wx, wy = mh.window(97, 71, 3)
