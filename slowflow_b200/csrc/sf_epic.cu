@@ -146,19 +146,19 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 
-// one arg_sweep update (epic_aux.cpp:118-148), operation for operation, without FMA contraction
-__device__ __forceinline__ void dt_update(float t1, int l1, float t2, int l2, float C, float &a, int &l, float &maxdiff) {
+// one arg_sweep update (epic_aux.cpp:118-148), operation for operation, without FMA contraction.  Branch-free: this is
+// the serial chain of the wavefront (one update per step and lane), so both forms of t0 are computed and one is
+// selected; the label is the one of the smaller neighbour in either form.  The square root keeps IEEE rounding; lanes
+// that take the "far apart" form feed it a harmless 1.0 so that its slow path (negative argument) is never entered.
+__device__ __forceinline__ void dt_update(float t1, int l1, float t2, int l2, float C, float twoCC, float &a, int &l, float &maxdiff) {
     const float dt12 = fabsf(__fsub_rn(t1, t2));
-    float t0;
-    int l0;
-    if (dt12 > C) {
-        if (t1 < t2) { t0 = __fadd_rn(t1, C); l0 = l1; }
-        else { t0 = __fadd_rn(t2, C); l0 = l2; }
-    } else {
-        const float r = sqrtf(__fsub_rn(__fmul_rn(__fmul_rn(2.0f, C), C), __fmul_rn(dt12, dt12)));
-        t0 = 0.5f * __fadd_rn(__fadd_rn(t1, t2), r);
-        l0 = (t1 < t2) ? l1 : l2;
-    }
+    const bool lt = t1 < t2, far = dt12 > C;
+    const float tmin = lt ? t1 : t2;
+    const int l0 = lt ? l1 : l2;
+    const float arg = __fsub_rn(twoCC, __fmul_rn(dt12, dt12)); // twoCC = (2 C) C
+    const float r = sqrtf(far ? 1.0f : arg);
+    const float tn = 0.5f * __fadd_rn(__fadd_rn(t1, t2), r);
+    const float t0 = far ? __fadd_rn(tmin, C) : tn;
     if (t0 < a) {
         maxdiff = fmaxf(maxdiff, __fsub_rn(a, t0));
         a = t0;
@@ -175,7 +175,12 @@ __device__ __forceinline__ void dt_update(float t1, int l1, float t2, int l2, fl
 // (release / acquire on a per-strip progress word).  Strips are handed out in sweep order by an atomic ticket, so a strip
 // only ever waits for one that is already running.  The tile data moves global -> shared with cp.async one block ahead
 // and back with coalesced row stores two blocks behind; a 3-slot ring holds the blocks in flight.
+// The sweep is latency-bound on the chain shuffle -> update -> shuffle of a step, so everything else is kept off it: the
+// step's operands come from shared memory through a per-lane address that is advanced incrementally (no index
+// arithmetic in front of the loads), the update is branch-free, and the last row of the strip above is fetched one block
+// ahead whenever it is already published (its L2 latency then overlaps 32 steps instead of stalling the block change).
 constexpr int DT_RING = 3;
+constexpr int DT_SLOT = DT_TILE * DT_PITCH; // elements of one ring slot
 // bounded spin on the progress word of the strip above: a protocol error traps instead of hanging the GPU
 __device__ __forceinline__ void dt_wait(const int *flag, int need) {
     unsigned spins = 0;
@@ -184,12 +189,28 @@ __device__ __forceinline__ void dt_wait(const int *flag, int need) {
         if (++spins > (1u << 24)) __trap();
     }
 }
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(unsigned addr, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
 __global__ void __launch_bounds__(32) k_dt_sweep(DtSweepArgs a) {
     if (a.k > *reinterpret_cast<volatile int *>(&a.ctrl->end_iter)) return;
-    __shared__ float sA[DT_RING][DT_TILE * DT_PITCH], sC[DT_RING][DT_TILE * DT_PITCH];
-    __shared__ int sL[DT_RING][DT_TILE * DT_PITCH];
-    __shared__ float hT[DT_RING][DT_TILE];
-    __shared__ int hL[DT_RING][DT_TILE];
+    // one array: [A | L | cost] x ring slots, then the halo rows (t, label) x ring slots
+    __shared__ __align__(16) float smem[3 * DT_RING * DT_SLOT + 2 * DT_RING * DT_TILE];
+    float *const sA = smem, *const sC = smem + 2 * DT_RING * DT_SLOT;
+    int *const sL = reinterpret_cast<int *>(smem + DT_RING * DT_SLOT);
+    float *const hT = smem + 3 * DT_RING * DT_SLOT;
+    int *const hL = reinterpret_cast<int *>(hT + DT_RING * DT_TILE);
+    constexpr unsigned OFF_L = DT_RING * DT_SLOT * 4, OFF_C = 2 * DT_RING * DT_SLOT * 4; // byte offsets from an sA address
     const int lane = threadIdx.x;
     const float INF = __int_as_float(0x7f800000);
     int strip = 0;
@@ -208,9 +229,10 @@ __global__ void __launch_bounds__(32) k_dt_sweep(DtSweepArgs a) {
 #pragma unroll 8
             for (int r = 0; r < rows; r++) {
                 const size_t o = (size_t)(a.sy > 0 ? q0 + r : H - 1 - (q0 + r)) * W + i;
-                cp_async4(&sA[slot][r * DT_PITCH + lane], a.A + o);
-                cp_async4(&sL[slot][r * DT_PITCH + lane], a.L + o);
-                cp_async4(&sC[slot][r * DT_PITCH + lane], a.cost + o);
+                const int e = slot * DT_SLOT + r * DT_PITCH + lane;
+                cp_async4(&sA[e], a.A + o);
+                cp_async4(&sL[e], a.L + o);
+                cp_async4(&sC[e], a.cost + o);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -222,22 +244,46 @@ __global__ void __launch_bounds__(32) k_dt_sweep(DtSweepArgs a) {
 #pragma unroll 8
             for (int r = 0; r < rows; r++) {
                 const size_t o = (size_t)(a.sy > 0 ? q0 + r : H - 1 - (q0 + r)) * W + i;
-                a.A[o] = sA[slot][r * DT_PITCH + lane];
-                a.L[o] = sL[slot][r * DT_PITCH + lane];
+                const int e = slot * DT_SLOT + r * DT_PITCH + lane;
+                a.A[o] = sA[e];
+                a.L[o] = sL[e];
             }
         }
     };
+    // the lanes' stores become visible with lane 0's release: __syncwarp orders them before it, the release is cumulative
     auto publish = [&](int blocks_done) {
-        __threadfence();
         __syncwarp();
         if (lane == 0) st_release_gpu(a.prog + strip, base + blocks_done);
+    };
+    // last row of the strip above, block m: (t, label) of column 32m + lane
+    auto halo_fetch = [&](int m, float &t, int &l) {
+        const int p = m * DT_TILE + lane;
+        t = INF;
+        l = -1;
+        if (p < W) {
+            const int i = a.sx > 0 ? p : W - 1 - p;
+            t = __ldcg(a.A + (size_t)jtop * W + i);
+            l = __ldcg(a.L + (size_t)jtop * W + i);
+        }
     };
 
     load_block(0);
     float cur_t = INF, maxdiff = 0.0f;
     int cur_l = -1, stored = 0;
+    float nh_t = INF; // halo of the NEXT block, fetched ahead when the strip above had already published it
+    int nh_l = -1;
+    bool have_next = false;
+    // per-lane cursor: column p = s - lane of the current step lives at shared byte address `addr` (array A; L and cost at
+    // fixed offsets); col = p & 31, slot = (p >> 5) % 3.  Lanes that have not started (p < 0) sit in a virtual block -1
+    // = slot 2, so that the wrap into column 0 lands on slot 0.
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    int col = (DT_TILE - lane) & (DT_TILE - 1), slot = lane ? DT_RING - 1 : 0;
+    unsigned addr = sbase + 4u * (unsigned)(slot * DT_SLOT + lane * DT_PITCH + col);
+    const unsigned hbase = sbase + 4u * 3 * DT_RING * DT_SLOT;
+    int p = -lane;
     const int nsteps = W + DT_TILE - 1;
-    for (int s = 0; s < nsteps; s++) {
+#pragma unroll 1
+    for (int s = 0; s < nsteps; s++, p++) {
         if ((s & (DT_TILE - 1)) == 0) {
             const int m = s >> 5; // lane 0 enters block m now; lane 31 left block m-2 in the previous step
             __syncwarp();
@@ -249,40 +295,63 @@ __global__ void __launch_bounds__(32) k_dt_sweep(DtSweepArgs a) {
             __syncwarp();
             if (m + 1 < a.NB) load_block(m + 1);                       // into the slot block m-2 just left
             else asm volatile("cp.async.commit_group;" ::: "memory");  // (keeps the group count uniform)
-            asm volatile("cp.async.wait_group 1;" ::: "memory");       // block m has landed
-            if (m < a.NB) {                                            // last row of the strip above, block m
-                const int slot = m % DT_RING, p = m * DT_TILE + lane;
+            if (m < a.NB) {
                 float t = INF;
                 int l = -1;
                 if (strip > 0) {
-                    if (lane == 0) dt_wait(a.prog + strip - 1, base + m + 1);
-                    __syncwarp();
-                    if (p < W) {
-                        const int i = a.sx > 0 ? p : W - 1 - p;
-                        t = __ldcg(a.A + (size_t)jtop * W + i);
-                        l = __ldcg(a.L + (size_t)jtop * W + i);
+                    if (have_next) { t = nh_t; l = nh_l; }
+                    else {
+                        if (lane == 0) dt_wait(a.prog + strip - 1, base + m + 1);
+                        __syncwarp();
+                        halo_fetch(m, t, l);
+                    }
+                    // block m + 1 of the row above, if it is there already: consumed at the next block change
+                    have_next = false;
+                    if (m + 1 < a.NB) {
+                        int ready = 0;
+                        if (lane == 0) ready = ld_acquire_gpu(a.prog + strip - 1) >= base + m + 2;
+                        ready = __shfl_sync(0xffffffffu, ready, 0);
+                        __syncwarp(); // (the shuffle itself orders nothing: lane 0's acquire before the lanes' loads)
+                        if (ready) {
+                            halo_fetch(m + 1, nh_t, nh_l);
+                            have_next = true;
+                        }
                     }
                 }
-                hT[slot][lane] = t;
-                hL[slot][lane] = l;
+                hT[(m % DT_RING) * DT_TILE + lane] = t;
+                hL[(m % DT_RING) * DT_TILE + lane] = l;
             }
+            asm volatile("cp.async.wait_group 1;" ::: "memory");       // block m has landed
             __syncwarp();
         }
-        const int p = s - lane;
         float up_t = __shfl_up_sync(0xffffffffu, cur_t, 1);
         int up_l = __shfl_up_sync(0xffffffffu, cur_l, 1);
         if (row_ok && p >= 0 && p < W) {
-            const int slot = (p >> 5) % DT_RING, col = p & (DT_TILE - 1), at = lane * DT_PITCH + col;
-            if (lane == 0) { up_t = hT[slot][col]; up_l = hL[slot][col]; }
+            float av = lds_f32(addr);
+            int lv = lds_s32(addr + OFF_L);
+            const float C = lds_f32(addr + OFF_C);
+            if (lane == 0) {
+                const unsigned h = hbase + 4u * (unsigned)(slot * DT_TILE + col);
+                up_t = lds_f32(h);
+                up_l = lds_s32(h + 4u * DT_RING * DT_TILE);
+            }
             const float t2 = (p == 0) ? INF : cur_t;
             const int l2 = (p == 0) ? -1 : cur_l;
-            float av = sA[slot][at];
-            int lv = sL[slot][at];
-            dt_update(up_t, up_l, t2, l2, sC[slot][at], av, lv, maxdiff);
-            sA[slot][at] = av;
-            sL[slot][at] = lv;
+            dt_update(up_t, up_l, t2, l2, C, __fmul_rn(__fmul_rn(2.0f, C), C), av, lv, maxdiff);
+            sts_f32(addr, av);
+            sts_s32(addr + OFF_L, lv);
             cur_t = av;
             cur_l = lv;
+        }
+        // advance the cursor by one column
+        addr += 4u;
+        if (++col == DT_TILE) {
+            col = 0;
+            addr += 4u * (DT_SLOT - DT_TILE);
+            if (++slot == DT_RING) {
+                slot = 0;
+                addr -= 4u * DT_RING * DT_SLOT;
+            }
         }
     }
     __syncwarp();
