@@ -15,16 +15,26 @@
 namespace sf {
 
 constexpr size_t HC_CHUNK = (size_t)1 << 20; // bytes per slot
-constexpr int HC_WORKERS = 4, HC_SLOTS = 4;
+constexpr int HC_MAX_WORKERS = 8, HC_SLOTS = 4;
+// copy threads per call: SLOWFLOW_GPU_COPY_THREADS (1..8), default 4
+static int hc_workers() {
+    static const int n = [] {
+        const char *e = getenv("SLOWFLOW_GPU_COPY_THREADS");
+        const int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : (v > HC_MAX_WORKERS ? HC_MAX_WORKERS : v);
+    }();
+    return n;
+}
 
 struct HostStager {
-    unsigned char *slot[HC_WORKERS][HC_SLOTS] = {};
-    cudaEvent_t done[HC_WORKERS][HC_SLOTS] = {};
-    cudaStream_t stream[HC_WORKERS] = {};
+    unsigned char *slot[HC_MAX_WORKERS][HC_SLOTS] = {};
+    cudaEvent_t done[HC_MAX_WORKERS][HC_SLOTS] = {};
+    cudaStream_t stream[HC_MAX_WORKERS] = {};
+    int workers = 0;
     cudaEvent_t gate = nullptr; // recorded on the context's stream: device data ready (D2H) / buffers free (H2D)
     bool ok = false;
     ~HostStager() {
-        for (int w = 0; w < HC_WORKERS; w++) {
+        for (int w = 0; w < HC_MAX_WORKERS; w++) {
             for (int s = 0; s < HC_SLOTS; s++) {
                 if (slot[w][s]) cudaFreeHost(slot[w][s]);
                 if (done[w][s]) cudaEventDestroy(done[w][s]);
@@ -35,7 +45,8 @@ struct HostStager {
     }
     bool init() {
         if (ok) return true;
-        for (int w = 0; w < HC_WORKERS; w++) {
+        workers = hc_workers();
+        for (int w = 0; w < workers; w++) {
             if (cudaStreamCreateWithFlags(&stream[w], cudaStreamNonBlocking) != cudaSuccess) return false;
             for (int s = 0; s < HC_SLOTS; s++) {
                 if (cudaMallocHost(&slot[w][s], HC_CHUNK) != cudaSuccess) return false;
@@ -70,6 +81,7 @@ static int staged_batch(sfgpu_ctx *c, const std::vector<HostCopy> &list, bool h2
         return SFGPU_ERR_CUDA;
     }
     // everything already queued on the context's stream comes first (D2H: the results; H2D: earlier users of dst)
+    const int HC_WORKERS = hs.workers;
     SF_CUDA(cudaEventRecord(hs.gate, c->stream));
     for (int w = 0; w < HC_WORKERS; w++) SF_CUDA(cudaStreamWaitEvent(hs.stream[w], hs.gate, 0));
     struct Piece { unsigned char *dev; unsigned char *host; size_t bytes; };
@@ -78,7 +90,7 @@ static int staged_batch(sfgpu_ctx *c, const std::vector<HostCopy> &list, bool h2
         for (size_t off = 0; off < hc.bytes; off += HC_CHUNK)
             pieces.push_back(Piece{(unsigned char *)hc.dev + off, (unsigned char *)hc.host + off, std::min(HC_CHUNK, hc.bytes - off)});
     const int device = c->device;
-    bool failed[HC_WORKERS] = {};
+    bool failed[HC_MAX_WORKERS] = {};
     auto work = [&](int w) {
         if (cudaSetDevice(device) != cudaSuccess) { failed[w] = true; return; }
         int used[HC_SLOTS] = {};
