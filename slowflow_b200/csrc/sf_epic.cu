@@ -202,77 +202,122 @@ __device__ __forceinline__ int lds_s32(unsigned addr) {
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_s32(unsigned addr, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
-__global__ void __launch_bounds__(32) k_dt_sweep(DtSweepArgs a) {
+// bounded spin on a shared-memory counter of the other warp of the CTA (a protocol error traps instead of hanging)
+__device__ __forceinline__ void dt_wait_smem(const volatile int *cnt, int need) {
+    unsigned spins = 0;
+    while (*cnt < need)
+        if (++spins > (1u << 26)) __trap();
+}
+
+// CTA = two warps on one strip.  Warp 0 runs the wavefront and nothing else; warp 1 (the mover) loads the blocks ahead of
+// it, fetches the halo row of the strip above, and stores / publishes the blocks behind it -- the ~3000 clk of block
+// moves per 32 steps (row stores, the fence of the publication, 96 cp.async) left the serial chain of the strip this way.
+// The warps meet on two shared-memory counters: `full` = blocks ready for the wavefront (written by the mover),
+// `done` = blocks the wavefront has left (written by warp 0).  Ring of 3 slots: block i goes into the slot block i-3
+// was stored from.
+//   mover, iteration i:  A  block i-1 has landed, its halo row is in place        -> full = i
+//                        B  wait done >= i-2, store block i-3, publish             (strip below may read it)
+//                        C  cp.async block i into slot i % 3
+//   wavefront, step 32b: lane 31 has left block b-2 -> done = b-1;  wait full >= b+1;  32 steps of block b (lane 0)
+__global__ void __launch_bounds__(64) k_dt_sweep(DtSweepArgs a) {
     if (a.k > *reinterpret_cast<volatile int *>(&a.ctrl->end_iter)) return;
     // one array: [A | L | cost] x ring slots, then the halo rows (t, label) x ring slots
     __shared__ __align__(16) float smem[3 * DT_RING * DT_SLOT + 2 * DT_RING * DT_TILE];
+    __shared__ int s_strip;
+    __shared__ volatile int s_full, s_done;
     float *const sA = smem, *const sC = smem + 2 * DT_RING * DT_SLOT;
     int *const sL = reinterpret_cast<int *>(smem + DT_RING * DT_SLOT);
     float *const hT = smem + 3 * DT_RING * DT_SLOT;
     int *const hL = reinterpret_cast<int *>(hT + DT_RING * DT_TILE);
     constexpr unsigned OFF_L = DT_RING * DT_SLOT * 4, OFF_C = 2 * DT_RING * DT_SLOT * 4; // byte offsets from an sA address
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool mover = threadIdx.x >= 32;
     const float INF = __int_as_float(0x7f800000);
-    int strip = 0;
-    if (lane == 0) strip = atomicAdd(&a.ctrl->ticket[a.k], 1);
-    strip = __shfl_sync(0xffffffffu, strip, 0);
+    if (threadIdx.x == 0) {
+        s_strip = atomicAdd(&a.ctrl->ticket[a.k], 1);
+        s_full = 0;
+        s_done = 0;
+    }
+    __syncthreads();
+    const int strip = s_strip;
     if (strip >= a.NS) return;
     const int W = a.W, H = a.H, q0 = strip * DT_TILE, rows = min(DT_TILE, H - q0);
+    const int NB = a.NB;
+
+    if (mover) {
+        const int jtop = (a.sy > 0) ? q0 - 1 : H - q0; // image row of sweep row q0 - 1 (the last row of the strip above)
+        const int base = a.k << 16;
+        auto load_block = [&](int m) { // A, L, cost of columns 32m .. 32m+31, all rows of the strip: lane = column (coalesced)
+            const int slot = m % DT_RING, p = m * DT_TILE + lane;
+            if (p < W) {
+                const int i = a.sx > 0 ? p : W - 1 - p;
+#pragma unroll 8
+                for (int r = 0; r < rows; r++) {
+                    const size_t o = (size_t)(a.sy > 0 ? q0 + r : H - 1 - (q0 + r)) * W + i;
+                    const int e = slot * DT_SLOT + r * DT_PITCH + lane;
+                    cp_async4(&sA[e], a.A + o);
+                    cp_async4(&sL[e], a.L + o);
+                    cp_async4(&sC[e], a.cost + o);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto store_block = [&](int m) {
+            const int slot = m % DT_RING, p = m * DT_TILE + lane;
+            if (p < W) {
+                const int i = a.sx > 0 ? p : W - 1 - p;
+#pragma unroll 8
+                for (int r = 0; r < rows; r++) {
+                    const size_t o = (size_t)(a.sy > 0 ? q0 + r : H - 1 - (q0 + r)) * W + i;
+                    const int e = slot * DT_SLOT + r * DT_PITCH + lane;
+                    a.A[o] = sA[e];
+                    a.L[o] = sL[e];
+                }
+            }
+        };
+#pragma unroll 1
+        for (int i = 0; i < NB + 3; i++) {
+            if (i >= 1 && i <= NB) { // A: block i-1
+                const int m = i - 1, p = m * DT_TILE + lane;
+                float t = INF;
+                int l = -1;
+                if (strip > 0) {
+                    if (lane == 0) dt_wait(a.prog + strip - 1, base + m + 1);
+                    __syncwarp();
+                    if (p < W) {
+                        const int ii = a.sx > 0 ? p : W - 1 - p;
+                        t = __ldcg(a.A + (size_t)jtop * W + ii);
+                        l = __ldcg(a.L + (size_t)jtop * W + ii);
+                    }
+                }
+                hT[(m % DT_RING) * DT_TILE + lane] = t;
+                hL[(m % DT_RING) * DT_TILE + lane] = l;
+                asm volatile("cp.async.wait_group 0;" ::: "memory"); // block i-1 has landed (the lanes' copies: next line)
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) s_full = i;
+            }
+            if (i >= 3) { // B: block i-3 (i - 3 < NB by the loop bound)
+                if (lane == 0) dt_wait_smem(&s_done, i - 2);
+                __syncwarp();
+                __threadfence_block();
+                store_block(i - 3);
+            }
+            if (i < NB) load_block(i); // C (after the store: the slot is the one block i-3 was read out of just now)
+            if (i >= 3) {
+                // the lanes' stores become visible with lane 0's release: __syncwarp orders them before it, the release is
+                // cumulative (its fence comes after the cp.async of C were issued, so the next block is already under way)
+                __syncwarp();
+                if (lane == 0) st_release_gpu(a.prog + strip, base + i - 2);
+            }
+        }
+        return;
+    }
+
+    // ---- the wavefront
     const bool row_ok = lane < rows;
-    const int jtop = (a.sy > 0) ? q0 - 1 : H - q0; // image row of sweep row q0 - 1 (the last row of the strip above)
-    const int base = a.k << 16;
-
-    auto load_block = [&](int m) { // A, L, cost of columns 32m .. 32m+31, all rows of the strip: lane = column (coalesced)
-        const int slot = m % DT_RING, p = m * DT_TILE + lane;
-        if (p < W) {
-            const int i = a.sx > 0 ? p : W - 1 - p;
-#pragma unroll 8
-            for (int r = 0; r < rows; r++) {
-                const size_t o = (size_t)(a.sy > 0 ? q0 + r : H - 1 - (q0 + r)) * W + i;
-                const int e = slot * DT_SLOT + r * DT_PITCH + lane;
-                cp_async4(&sA[e], a.A + o);
-                cp_async4(&sL[e], a.L + o);
-                cp_async4(&sC[e], a.cost + o);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto store_block = [&](int m) {
-        const int slot = m % DT_RING, p = m * DT_TILE + lane;
-        if (p < W) {
-            const int i = a.sx > 0 ? p : W - 1 - p;
-#pragma unroll 8
-            for (int r = 0; r < rows; r++) {
-                const size_t o = (size_t)(a.sy > 0 ? q0 + r : H - 1 - (q0 + r)) * W + i;
-                const int e = slot * DT_SLOT + r * DT_PITCH + lane;
-                a.A[o] = sA[e];
-                a.L[o] = sL[e];
-            }
-        }
-    };
-    // the lanes' stores become visible with lane 0's release: __syncwarp orders them before it, the release is cumulative
-    auto publish = [&](int blocks_done) {
-        __syncwarp();
-        if (lane == 0) st_release_gpu(a.prog + strip, base + blocks_done);
-    };
-    // last row of the strip above, block m: (t, label) of column 32m + lane
-    auto halo_fetch = [&](int m, float &t, int &l) {
-        const int p = m * DT_TILE + lane;
-        t = INF;
-        l = -1;
-        if (p < W) {
-            const int i = a.sx > 0 ? p : W - 1 - p;
-            t = __ldcg(a.A + (size_t)jtop * W + i);
-            l = __ldcg(a.L + (size_t)jtop * W + i);
-        }
-    };
-
-    load_block(0);
     float cur_t = INF, maxdiff = 0.0f;
-    int cur_l = -1, stored = 0;
-    float nh_t = INF; // halo of the NEXT block, fetched ahead when the strip above had already published it
-    int nh_l = -1;
-    bool have_next = false;
+    int cur_l = -1;
     // per-lane cursor: column p = s - lane of the current step lives at shared byte address `addr` (array A; L and cost at
     // fixed offsets); col = p & 31, slot = (p >> 5) % 3.  Lanes that have not started (p < 0) sit in a virtual block -1
     // = slot 2, so that the wrap into column 0 lands on slot 0.
@@ -285,44 +330,17 @@ __global__ void __launch_bounds__(32) k_dt_sweep(DtSweepArgs a) {
 #pragma unroll 1
     for (int s = 0; s < nsteps; s++, p++) {
         if ((s & (DT_TILE - 1)) == 0) {
-            const int m = s >> 5; // lane 0 enters block m now; lane 31 left block m-2 in the previous step
+            const int b = s >> 5; // lane 0 enters block b now; lane 31 left block b-2 in the previous step
             __syncwarp();
-            if (m - 2 >= stored) {
-                store_block(m - 2);
-                stored = m - 1;
-                publish(stored);
+            if (b >= 2 && b - 2 < NB) {
+                __threadfence_block();
+                if (lane == 0) s_done = b - 1;
             }
-            __syncwarp();
-            if (m + 1 < a.NB) load_block(m + 1);                       // into the slot block m-2 just left
-            else asm volatile("cp.async.commit_group;" ::: "memory");  // (keeps the group count uniform)
-            if (m < a.NB) {
-                float t = INF;
-                int l = -1;
-                if (strip > 0) {
-                    if (have_next) { t = nh_t; l = nh_l; }
-                    else {
-                        if (lane == 0) dt_wait(a.prog + strip - 1, base + m + 1);
-                        __syncwarp();
-                        halo_fetch(m, t, l);
-                    }
-                    // block m + 1 of the row above, if it is there already: consumed at the next block change
-                    have_next = false;
-                    if (m + 1 < a.NB) {
-                        int ready = 0;
-                        if (lane == 0) ready = ld_acquire_gpu(a.prog + strip - 1) >= base + m + 2;
-                        ready = __shfl_sync(0xffffffffu, ready, 0);
-                        __syncwarp(); // (the shuffle itself orders nothing: lane 0's acquire before the lanes' loads)
-                        if (ready) {
-                            halo_fetch(m + 1, nh_t, nh_l);
-                            have_next = true;
-                        }
-                    }
-                }
-                hT[(m % DT_RING) * DT_TILE + lane] = t;
-                hL[(m % DT_RING) * DT_TILE + lane] = l;
+            if (b < NB) {
+                if (lane == 0) dt_wait_smem(&s_full, b + 1);
+                __syncwarp();
+                __threadfence_block();
             }
-            asm volatile("cp.async.wait_group 1;" ::: "memory");       // block m has landed
-            __syncwarp();
         }
         float up_t = __shfl_up_sync(0xffffffffu, cur_t, 1);
         int up_l = __shfl_up_sync(0xffffffffu, cur_l, 1);
@@ -355,8 +373,8 @@ __global__ void __launch_bounds__(32) k_dt_sweep(DtSweepArgs a) {
         }
     }
     __syncwarp();
-    for (int m = stored; m < a.NB; m++) store_block(m);
-    publish(a.NB);
+    __threadfence_block();
+    if (lane == 0) s_done = NB; // every block may be stored now
     for (int off = 16; off > 0; off >>= 1) maxdiff = fmaxf(maxdiff, __shfl_xor_sync(0xffffffffu, maxdiff, off));
     if (lane == 0 && maxdiff > 0.0f) atomicMax(&a.ctrl->maxdiff[a.k], __float_as_uint(maxdiff));
 }
@@ -694,9 +712,10 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
     k_dt_seed_dist<<<(ns + 255) / 256, 256, 0, st>>>(ns, d_seeds, W, d_cost, d_dmap);
     // sweeps i = 1 .. : direction (x[i % 4], y[i % 4]) with x = {-1, 1, 1, -1}, y = {1, 1, -1, -1} (:165-172).  One warp
     // per strip of 32 rows; every strip must be resident together with the one above it: tickets hand the strips out in
-    // sweep order, and the grid (one block per strip) is far below the 148 x 32 resident blocks for any real image
+    // sweep order, and the grid (one block of two warps and 40 KB of shared memory per strip) is far below the 148 x 5
+    // resident blocks for any real image
     static const int dx[4] = {-1, 1, 1, -1}, dy[4] = {1, 1, -1, -1};
-    if (NS > c->num_sms * 16) {
+    if (NS > c->num_sms * 4) {
         set_error("sfgpu_epic: image too tall for the strip pipeline of the distance transform");
         return SFGPU_ERR_UNSUPPORTED;
     }
@@ -708,7 +727,7 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
         a.k = k;
         a.ctrl = ctrl.as<DtCtrl>();
         a.prog = prog.as<int>();
-        k_dt_sweep<<<NS, 32, 0, st>>>(a);
+        k_dt_sweep<<<NS, 64, 0, st>>>(a);
         k_dt_control<<<1, 1, 0, st>>>(ctrl.as<DtCtrl>(), k, 1.0f, DT_MAX_SWEEPS); // default dt_params: max_iter 40, min_change 1 (:151-154)
     }
     c->prof_acc.kernel_launches += 4 + 2 * DT_MAX_SWEEPS;
@@ -729,6 +748,7 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
     SF_CUDA(cudaMemcpyAsync(&h_ctrl, ctrl.p, sizeof(DtCtrl), cudaMemcpyDeviceToHost, st));
     SF_CUDA(cudaStreamSynchronize(st));
     if (sweeps_out) *sweeps_out = h_ctrl.sweeps_run;
+    if (tr.on) fprintf(stderr, "  epic: (distance transform: %d sweeps, %d strips x %d blocks)\n", h_ctrl.sweeps_run, NS, NB);
     tr.mark("border emit (+allocs)");
     if (h_count + 1 >= cap) {
         set_error("sfgpu_epic: label border list overflow (more than 32 sqrt(N ns) + 1M border entries)");
