@@ -482,11 +482,11 @@ __device__ HeapItem heap_pop(HeapItem *h, int &len) { // pop_heap + pop_back
 // one warp per seed (lane 0 runs the search, the warp restores the tentative-distance array afterwards)
 __global__ void __launch_bounds__(256) k_knn_graph(int ns, int nn, const int *__restrict__ indptr, const int *__restrict__ indices,
                                                    const float *__restrict__ data, unsigned *__restrict__ done_all, int *__restrict__ touched_all,
-                                                   int *__restrict__ nnf, float *__restrict__ dis, int *__restrict__ overflow) {
+                                                   int *__restrict__ nnf, float *__restrict__ dis, int *__restrict__ overflow, int heap_cap) {
     extern __shared__ HeapItem heaps[];
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_block, nwarps = gridDim.x * (blockDim.x >> 5);
-    HeapItem *h = heaps + warp_in_block * KNN_HEAP;
+    HeapItem *h = heaps + warp_in_block * heap_cap; // heap_cap <= KNN_HEAP entries of shared memory per warp
     unsigned *done = done_all + (size_t)gwarp * ns; // float bits; EPIC_UNSEEN = not reached (memset 0x7F in the reference)
     int *touched = touched_all + (size_t)gwarp * KNN_HEAP * 2;
     for (int seed = gwarp; seed < ns; seed += nwarps) {
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(256) k_knn_graph(int ns, int nn, const int *__
                     const int ngh = indices[e];
                     const float nd = cur.dis + data[e];
                     if (nd >= __uint_as_float(done[ngh])) continue;
-                    if (len >= KNN_HEAP || ntouched >= 2 * KNN_HEAP) { atomicExch(overflow, 1); continue; }
+                    if (len >= heap_cap || ntouched >= 2 * KNN_HEAP) { atomicExch(overflow, 1); continue; }
                     heap_push(h, len, HeapItem{ngh, nd});
                     if (done[ngh] == EPIC_UNSEEN) touched[ntouched++] = ngh;
                     done[ngh] = __float_as_uint(nd);
@@ -777,9 +777,14 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
     k_csr_rows<<<(ns + 1 + 255) / 256, 256, 0, st>>>(ns, nedges, ukeys.as<unsigned long long>(), indptr.as<int>(), indices.as<int>());
     tr.mark("sort + reduce + csr");
 
-    // ---- k nearest seeds of every seed, then the query step
+    // ---- k nearest seeds of every seed, then the query step.  The search is one serial thread per seed, i.e. bound by the
+    // latency of its dependent loads: what counts is how many searches are in flight.  The heap lives in shared memory, so
+    // its capacity sets the residency: first a pass with 1024 entries per warp (3 blocks of 8 warps per SM; a search for
+    // nn = 100 neighbours on the planar seed graph keeps a few hundred entries open), and only if a heap overflowed the
+    // pass with the full 2048 entries (1 block per SM).
     const int warps_per_block = 8;
-    int blocks = std::min((ns + warps_per_block - 1) / warps_per_block, c->num_sms);
+    int blocks_per_sm = 3;
+    int blocks = std::min((ns + warps_per_block - 1) / warps_per_block, c->num_sms * blocks_per_sm);
     // the per-warp tentative-distance arrays: ns floats per resident warp (bounded to 1 GB)
     while (blocks > 1 && (size_t)blocks * warps_per_block * ns * 4 > ((size_t)1 << 30)) blocks /= 2;
     DevBuf done_all, touched, nnf, dis, overflow;
@@ -790,16 +795,23 @@ static int nn_field(sfgpu_ctx *c, const EpicGeo &eg, const float *d_cost, int ns
     k_fill_u32<<<592, 256, 0, st>>>(nwarps * ns, done_all.as<unsigned>(), EPIC_UNSEEN);
     SF_CUDA(cudaMemsetAsync(overflow.p, 0, 4, st));
     tr.mark("knn allocs + fill");
-    const size_t smem = (size_t)warps_per_block * KNN_HEAP * sizeof(HeapItem);
-    SF_CUDA(cudaFuncSetAttribute(k_knn_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_graph<<<blocks, warps_per_block * 32, smem, st>>>(ns, nn, indptr.as<int>(), indices.as<int>(), uvals.as<float>(), done_all.as<unsigned>(),
-                                                            touched.as<int>(), nnf.as<int>(), dis.as<float>(), overflow.as<int>());
-    k_query_weights<<<ns, 128, 0, st>>>(ns, nn, d_seeds, W, d_labels, d_dmap, nnf.as<int>(), dis.as<float>(), coef, d_qnn, d_qw);
+    SF_CUDA(cudaFuncSetAttribute(k_knn_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)warps_per_block * KNN_HEAP * sizeof(HeapItem))));
     int h_over = 0;
-    SF_CUDA(cudaMemcpyAsync(&h_over, overflow.p, 4, cudaMemcpyDeviceToHost, st));
+    for (int heap_cap = KNN_HEAP / 2; heap_cap <= KNN_HEAP; heap_cap *= 2) {
+        const size_t smem = (size_t)warps_per_block * heap_cap * sizeof(HeapItem);
+        const int nblocks = heap_cap == KNN_HEAP ? std::min(blocks, c->num_sms) : blocks; // (a retry: every entry of done_all is EPIC_UNSEEN again)
+        k_knn_graph<<<nblocks, warps_per_block * 32, smem, st>>>(ns, nn, indptr.as<int>(), indices.as<int>(), uvals.as<float>(), done_all.as<unsigned>(),
+                                                                 touched.as<int>(), nnf.as<int>(), dis.as<float>(), overflow.as<int>(), heap_cap);
+        c->prof_acc.kernel_launches++;
+        SF_CUDA(cudaMemcpyAsync(&h_over, overflow.p, 4, cudaMemcpyDeviceToHost, st));
+        SF_CUDA(cudaStreamSynchronize(st));
+        if (!h_over) break;
+        if (heap_cap < KNN_HEAP) SF_CUDA(cudaMemsetAsync(overflow.p, 0, 4, st));
+    }
+    k_query_weights<<<ns, 128, 0, st>>>(ns, nn, d_seeds, W, d_labels, d_dmap, nnf.as<int>(), dis.as<float>(), coef, d_qnn, d_qw);
     SF_CUDA(cudaStreamSynchronize(st));
     SF_CUDA(cudaGetLastError());
-    c->prof_acc.kernel_launches += 6;
+    c->prof_acc.kernel_launches += 5;
     tr.mark("knn search + query");
     if (h_over) {
         set_error("sfgpu_epic: neighbour search heap overflow (a seed with more than 2048 open graph nodes)");
