@@ -40,7 +40,6 @@
 namespace sf {
 
 constexpr int DT_TILE = 32;
-constexpr int DT_PITCH = 34; // shared-memory row pitch: lane l at step s reads (l, s - l) -> bank (l + s) % 32
 constexpr int DT_MAX_SWEEPS = 40;
 constexpr unsigned EPIC_UNSEEN = 0x7F7F7F7Fu; // memset(…, 0x7F, …) pattern of the reference: 3.39e38f
 
@@ -180,7 +179,6 @@ __device__ __forceinline__ void dt_update(float t1, int l1, float t2, int l2, fl
 // arithmetic in front of the loads), the update is branch-free, and the last row of the strip above is fetched one block
 // ahead whenever it is already published (its L2 latency then overlaps 32 steps instead of stalling the block change).
 constexpr int DT_RING = 3;
-constexpr int DT_SLOT = DT_TILE * DT_PITCH; // elements of one ring slot
 // bounded spin on the progress word of the strip above: a protocol error traps instead of hanging the GPU
 __device__ __forceinline__ void dt_wait(const int *flag, int need) {
     unsigned spins = 0;
@@ -219,17 +217,23 @@ __device__ __forceinline__ void dt_wait_smem(const volatile int *cnt, int need) 
 //                        B  wait done >= i-2, store block i-3, publish             (strip below may read it)
 //                        C  cp.async block i into slot i % 3
 //   wavefront, step 32b: lane 31 has left block b-2 -> done = b-1;  wait full >= b+1;  32 steps of block b (lane 0)
+// Shared-memory layout: per array (A, L, cost) every strip row keeps a circular window of DT_COLS = 3 x 32 columns
+// (the three ring slots side by side), so the wavefront's per-lane cursor is one address that advances by a column per
+// step and wraps once per 96 steps.  Row pitch 98 floats: lane l reads column (s - l) of row l at step s -> bank
+// (2 l + s - l) % 32 = (l + s) % 32, conflict-free; the mover's row-wise accesses are conflict-free anyway.
+constexpr int DT_COLS = DT_RING * DT_TILE, DT_ROWP = DT_COLS + 2, DT_ARR = DT_TILE * DT_ROWP;
 __global__ void __launch_bounds__(64) k_dt_sweep(DtSweepArgs a) {
     if (a.k > *reinterpret_cast<volatile int *>(&a.ctrl->end_iter)) return;
-    // one array: [A | L | cost] x ring slots, then the halo rows (t, label) x ring slots
-    __shared__ __align__(16) float smem[3 * DT_RING * DT_SLOT + 2 * DT_RING * DT_TILE];
+    // [A | L | cost] arrays, then the halo row (t, label) of the strip above in the same circular column index
+    __shared__ __align__(16) float smem[3 * DT_ARR + 2 * DT_COLS];
     __shared__ int s_strip;
     __shared__ volatile int s_full, s_done;
-    float *const sA = smem, *const sC = smem + 2 * DT_RING * DT_SLOT;
-    int *const sL = reinterpret_cast<int *>(smem + DT_RING * DT_SLOT);
-    float *const hT = smem + 3 * DT_RING * DT_SLOT;
-    int *const hL = reinterpret_cast<int *>(hT + DT_RING * DT_TILE);
-    constexpr unsigned OFF_L = DT_RING * DT_SLOT * 4, OFF_C = 2 * DT_RING * DT_SLOT * 4; // byte offsets from an sA address
+    float *const sA = smem, *const sC = smem + 2 * DT_ARR;
+    int *const sL = reinterpret_cast<int *>(smem + DT_ARR);
+    float *const hT = smem + 3 * DT_ARR;
+    int *const hL = reinterpret_cast<int *>(hT + DT_COLS);
+    // byte offsets from an address in sA: the same element of L / cost; from lane 0's cursor (row 0): the halo entries
+    constexpr unsigned OFF_L = DT_ARR * 4, OFF_C = 2 * DT_ARR * 4, OFF_HT = 3 * DT_ARR * 4, OFF_HL = (3 * DT_ARR + DT_COLS) * 4;
     const int lane = threadIdx.x & 31;
     const bool mover = threadIdx.x >= 32;
     const float INF = __int_as_float(0x7f800000);
@@ -248,13 +252,14 @@ __global__ void __launch_bounds__(64) k_dt_sweep(DtSweepArgs a) {
         const int jtop = (a.sy > 0) ? q0 - 1 : H - q0; // image row of sweep row q0 - 1 (the last row of the strip above)
         const int base = a.k << 16;
         auto load_block = [&](int m) { // A, L, cost of columns 32m .. 32m+31, all rows of the strip: lane = column (coalesced)
-            const int slot = m % DT_RING, p = m * DT_TILE + lane;
+            const int p = m * DT_TILE + lane;
             if (p < W) {
                 const int i = a.sx > 0 ? p : W - 1 - p;
+                const int e0 = (m % DT_RING) * DT_TILE + lane;
 #pragma unroll 8
                 for (int r = 0; r < rows; r++) {
                     const size_t o = (size_t)(a.sy > 0 ? q0 + r : H - 1 - (q0 + r)) * W + i;
-                    const int e = slot * DT_SLOT + r * DT_PITCH + lane;
+                    const int e = r * DT_ROWP + e0;
                     cp_async4(&sA[e], a.A + o);
                     cp_async4(&sL[e], a.L + o);
                     cp_async4(&sC[e], a.cost + o);
@@ -262,14 +267,16 @@ __global__ void __launch_bounds__(64) k_dt_sweep(DtSweepArgs a) {
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        auto store_block = [&](int m) {
-            const int slot = m % DT_RING, p = m * DT_TILE + lane;
+        // rows [r0, r1) of block m back to the image
+        auto store_rows = [&](int m, int r0, int r1) {
+            const int p = m * DT_TILE + lane;
             if (p < W) {
                 const int i = a.sx > 0 ? p : W - 1 - p;
+                const int e0 = (m % DT_RING) * DT_TILE + lane;
 #pragma unroll 8
-                for (int r = 0; r < rows; r++) {
+                for (int r = r0; r < r1; r++) {
                     const size_t o = (size_t)(a.sy > 0 ? q0 + r : H - 1 - (q0 + r)) * W + i;
-                    const int e = slot * DT_SLOT + r * DT_PITCH + lane;
+                    const int e = r * DT_ROWP + e0;
                     a.A[o] = sA[e];
                     a.L[o] = sL[e];
                 }
@@ -301,75 +308,61 @@ __global__ void __launch_bounds__(64) k_dt_sweep(DtSweepArgs a) {
                 if (lane == 0) dt_wait_smem(&s_done, i - 2);
                 __syncwarp();
                 __threadfence_block();
-                store_block(i - 3);
-            }
-            if (i < NB) load_block(i); // C (after the store: the slot is the one block i-3 was read out of just now)
-            if (i >= 3) {
-                // the lanes' stores become visible with lane 0's release: __syncwarp orders them before it, the release is
-                // cumulative (its fence comes after the cp.async of C were issued, so the next block is already under way)
+                // The strip below only reads the LAST row of this strip, and its start is the critical path of the sweep
+                // (one hand-over per strip): that row goes out and is published first -- the fence of the release then has
+                // two stores per lane to wait for instead of 64 -- the other rows follow.  The lanes' stores become
+                // visible with lane 0's release: __syncwarp orders them before it, the release is cumulative.
+                store_rows(i - 3, rows - 1, rows);
                 __syncwarp();
                 if (lane == 0) st_release_gpu(a.prog + strip, base + i - 2);
+                store_rows(i - 3, 0, rows - 1);
             }
+            if (i < NB) load_block(i); // C (after the store: the slot is the one block i-3 was read out of just now)
         }
         return;
     }
 
-    // ---- the wavefront
-    const bool row_ok = lane < rows;
-    float cur_t = INF, maxdiff = 0.0f;
+    // ---- the wavefront.  Lane l works on column p = s - l at step s; rows below the image never become valid.
+    float cur_t = INF, maxdiff = 0.0f; // (left neighbour of column 0: INF / -1, the initial values)
     int cur_l = -1;
-    // per-lane cursor: column p = s - lane of the current step lives at shared byte address `addr` (array A; L and cost at
-    // fixed offsets); col = p & 31, slot = (p >> 5) % 3.  Lanes that have not started (p < 0) sit in a virtual block -1
-    // = slot 2, so that the wrap into column 0 lands on slot 0.
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
-    int col = (DT_TILE - lane) & (DT_TILE - 1), slot = lane ? DT_RING - 1 : 0;
-    unsigned addr = sbase + 4u * (unsigned)(slot * DT_SLOT + lane * DT_PITCH + col);
-    const unsigned hbase = sbase + 4u * 3 * DT_RING * DT_SLOT;
-    int p = -lane;
+    const unsigned row_lo = (unsigned)__cvta_generic_to_shared(smem) + 4u * (unsigned)(lane * DT_ROWP), row_hi = row_lo + 4u * DT_COLS;
+    unsigned addr = lane ? row_hi - 4u * (unsigned)lane : row_lo; // cursor: element (row l, column p mod 96) of A
+    int p = (lane < rows) ? -lane : -(1 << 30);
     const int nsteps = W + DT_TILE - 1;
 #pragma unroll 1
-    for (int s = 0; s < nsteps; s++, p++) {
-        if ((s & (DT_TILE - 1)) == 0) {
-            const int b = s >> 5; // lane 0 enters block b now; lane 31 left block b-2 in the previous step
+    for (int b = 0; b * DT_TILE < nsteps; b++) {
+        // lane 0 enters block b now; lane 31 left block b-2 in the previous step
+        __syncwarp();
+        if (b >= 2 && b - 2 < NB) {
+            __threadfence_block();
+            if (lane == 0) s_done = b - 1;
+        }
+        if (b < NB) {
+            if (lane == 0) dt_wait_smem(&s_full, b + 1);
             __syncwarp();
-            if (b >= 2 && b - 2 < NB) {
-                __threadfence_block();
-                if (lane == 0) s_done = b - 1;
-            }
-            if (b < NB) {
-                if (lane == 0) dt_wait_smem(&s_full, b + 1);
-                __syncwarp();
-                __threadfence_block();
-            }
+            __threadfence_block();
         }
-        float up_t = __shfl_up_sync(0xffffffffu, cur_t, 1);
-        int up_l = __shfl_up_sync(0xffffffffu, cur_l, 1);
-        if (row_ok && p >= 0 && p < W) {
-            float av = lds_f32(addr);
-            int lv = lds_s32(addr + OFF_L);
-            const float C = lds_f32(addr + OFF_C);
-            if (lane == 0) {
-                const unsigned h = hbase + 4u * (unsigned)(slot * DT_TILE + col);
-                up_t = lds_f32(h);
-                up_l = lds_s32(h + 4u * DT_RING * DT_TILE);
+        const int jn = min(DT_TILE, nsteps - b * DT_TILE);
+#pragma unroll 1
+        for (int j = 0; j < jn; j++, p++) {
+            float up_t = __shfl_up_sync(0xffffffffu, cur_t, 1);
+            int up_l = __shfl_up_sync(0xffffffffu, cur_l, 1);
+            if ((unsigned)p < (unsigned)W) {
+                float av = lds_f32(addr);
+                int lv = lds_s32(addr + OFF_L);
+                const float C = lds_f32(addr + OFF_C);
+                if (lane == 0) { // (row_lo of lane 0 is the start of the array: the cursor doubles as the halo index)
+                    up_t = lds_f32(addr + OFF_HT);
+                    up_l = lds_s32(addr + OFF_HL);
+                }
+                dt_update(up_t, up_l, cur_t, cur_l, C, __fmul_rn(__fmul_rn(2.0f, C), C), av, lv, maxdiff);
+                sts_f32(addr, av);
+                sts_s32(addr + OFF_L, lv);
+                cur_t = av;
+                cur_l = lv;
             }
-            const float t2 = (p == 0) ? INF : cur_t;
-            const int l2 = (p == 0) ? -1 : cur_l;
-            dt_update(up_t, up_l, t2, l2, C, __fmul_rn(__fmul_rn(2.0f, C), C), av, lv, maxdiff);
-            sts_f32(addr, av);
-            sts_s32(addr + OFF_L, lv);
-            cur_t = av;
-            cur_l = lv;
-        }
-        // advance the cursor by one column
-        addr += 4u;
-        if (++col == DT_TILE) {
-            col = 0;
-            addr += 4u * (DT_SLOT - DT_TILE);
-            if (++slot == DT_RING) {
-                slot = 0;
-                addr -= 4u * DT_RING * DT_SLOT;
-            }
+            addr += 4u;
+            if (addr == row_hi) addr = row_lo;
         }
     }
     __syncwarp();
@@ -908,7 +901,10 @@ static int epic_impl(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_i
     // ---- the edge costs (the entry point has already added euc in the caller's array, :155-163) go to the device
     DevBuf d_cost, d_labels, d_dmap;
     if (!d_cost.alloc(N * 4) || !d_labels.alloc(N * 4) || !d_dmap.alloc(N * 4)) return SFGPU_ERR_CUDA;
-    SF_CUDA(cudaMemcpyAsync(d_cost.p, edges->pixels, N * 4, cudaMemcpyHostToDevice, st));
+    {   // (pageable caller arrays go through the multi-threaded staging path, sf_hostcopy.cu: 30+ instead of 11 GB/s)
+        const int rcu = host_copies(c, {{d_cost.p, edges->pixels, N * 4}}, true);
+        if (rcu != SFGPU_OK) return rcu;
+    }
 
     EpicGeo eg;
     eg.W = W; eg.H = H;
@@ -940,7 +936,10 @@ static int epic_impl(sfgpu_ctx *c, image_t *flowx, image_t *flowy, const color_i
         if (!work.alloc(16 * P * 4)) return SFGPU_ERR_CUDA;
         float *d_im = work.as<float>(), *d_tmp = d_im + 3 * P, *d_sm = d_im + 6 * P, *d_ix = d_im + 9 * P, *d_iy = d_im + 12 * P;
         float *d_xx = d_im + 15 * P; // xy, yy reuse d_tmp / d_sm planes below
-        SF_CUDA(cudaMemcpyAsync(d_im, im->c1, 3 * P * 4, cudaMemcpyHostToDevice, st));
+        {
+            const int rcu = host_copies(c, {{d_im, im->c1, 3 * P * 4}}, true);
+            if (rcu != SFGPU_OK) return rcu;
+        }
         const ConvTaps pre = gaussian_taps(0.8f), post = gaussian_taps(1.0f);
         ConvTaps der;
         memset(&der, 0, sizeof(der));
