@@ -395,7 +395,7 @@ int sfgpu_profile_get(sfgpu_ctx *c, sfgpu_profile_t *out) {
 }
 
 int sfgpu_host_register(void *ptr, unsigned long long bytes) {
-    SF_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    SF_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable)); // pinned for every device's context
     return SFGPU_OK;
 }
 int sfgpu_host_unregister(void *ptr) {

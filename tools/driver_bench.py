@@ -30,4 +30,4 @@ with tempfile.TemporaryDirectory() as d:
                             "--set", "slow_flow_smoothing=1", "--set", "slow_flow_omega_0=0", "--set", "slow_flow_omega_1=2",
                             "--set", "slow_flow_occlusion_penalty=0.1", "--set", "slow_flow_occlusion_alpha=0.1"],
                            capture_output=True, text=True)
-        print("threads per GPU %d: %s" % (tpg, [l for l in r.stdout.splitlines() if "window loop" in l or "jets," in l]), r.stderr[-300:])
+        print("threads per GPU %d: %s" % (tpg, [l for l in r.stdout.splitlines() if "window loop" in l or "jets," in l or "worker" in l]), r.stderr[-300:])

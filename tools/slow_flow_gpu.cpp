@@ -190,6 +190,13 @@ int main(int argc, char **argv) {
     color_image_t *channel_weights = new_color_image(W, H);            // :596-598
     for (size_t k = 0; k < (size_t)3 * channel_weights->stride * H; k++) channel_weights->c1[k] = 1.0f;
 
+    // The frames and the channel weights are read by every window: page-lock them once, so that the per-window uploads are
+    // plain DMA at PCIe speed instead of chunked staging through host threads (sf_hostcopy.cu)
+    if (sfgpu_set_device(0) == SFGPU_OK) {
+        for (int k = 0; k < frames; k++) sfgpu_host_register(seq[k]->c1, sizeof(float) * 3 * (unsigned long long)seq[k]->stride * H);
+        sfgpu_host_register(channel_weights->c1, sizeof(float) * 3 * (unsigned long long)channel_weights->stride * H);
+    }
+
     make_dir(out);
     const bool write_occ = cfg.parameter<bool>("slow_flow_output_occlusions", "0");
     if (write_occ) make_dir(out + "occlusion");
@@ -201,6 +208,7 @@ int main(int argc, char **argv) {
     const auto t_loop = std::chrono::steady_clock::now();
     std::vector<std::thread> pool;
     std::vector<int> done(workers, 0), skipped(workers, 0);
+    std::vector<double> t_solve(workers, 0.0), t_out(workers, 0.0); // seconds inside variational() / writing results, per worker
     for (int t = 0; t < workers; t++) {
         pool.emplace_back([&, t]() {
             if (sfgpu_set_device(t % gpus) != SFGPU_OK) die(sfgpu_last_error());
@@ -219,7 +227,10 @@ int main(int argc, char **argv) {
                 if (resume && access(path, F_OK) == 0) skipped[t]++; // skip finished frames (slow_flow.cpp:794)
                 else {   // forward
                     image_t *wx = new_image(W, H), *wy = new_image(W, H); // zero initial flow (:865-868)
+                    const auto t0 = std::chrono::steady_clock::now();
                     minimzer_f.variational(wx, wy, im, thread_params);
+                    const auto t1 = std::chrono::steady_clock::now();
+                    t_solve[t] += std::chrono::duration<double>(t1 - t0).count();
                     if (write_occ) {
                         snprintf(path, sizeof(path), "%socclusion/frame_%i.pbm", out.c_str(), start + f * skip);
                         if (sfgpu_write_occlusion_pbm(path, minimzer_f.getOcclusions()) != SFGPU_OK) die(sfgpu_last_error());
@@ -228,16 +239,21 @@ int main(int argc, char **argv) {
                     snprintf(path, sizeof(path), (out + name + ".flo").c_str(), start + f * skip);
                     if (sfgpu_write_flo(path, wx, wy) != SFGPU_OK) die(sfgpu_last_error());
                     free_image(wx); free_image(wy);
+                    t_out[t] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
                 }
                 snprintf(path, sizeof(path), (out + name + "_back.flo").c_str(), start + f * skip + steps * skip);
                 if (resume && access(path, F_OK) == 0) skipped[t]++; // (slow_flow.cpp:958)
                 else {   // backward
                     image_t *wx = new_image(W, H), *wy = new_image(W, H);
+                    const auto t0 = std::chrono::steady_clock::now();
                     minimzer_b.variational(wx, wy, im_back, thread_params);
+                    const auto t1 = std::chrono::steady_clock::now();
+                    t_solve[t] += std::chrono::duration<double>(t1 - t0).count();
                     for (size_t k = 0; k < (size_t)wx->stride * H; k++) { wx->data[k] *= steps; wy->data[k] *= steps; } // :1026-1027
                     snprintf(path, sizeof(path), (out + name + "_back.flo").c_str(), start + f * skip + steps * skip);
                     if (sfgpu_write_flo(path, wx, wy) != SFGPU_OK) die(sfgpu_last_error());
                     free_image(wx); free_image(wy);
+                    t_out[t] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
                 }
                 done[t]++;
             }
@@ -259,11 +275,13 @@ int main(int argc, char **argv) {
     }
     int total = 0;
     for (int t = 0; t < workers; t++) {
-        printf("worker %d (device %d): %d jets, %d finished flow files skipped\n", t, t % gpus, done[t], skipped[t]);
+        printf("worker %d (device %d): %d jets, %d finished flow files skipped; %.3f s in variational(), %.3f s scaling + writing results\n", t, t % gpus,
+               done[t], skipped[t], t_solve[t], t_out[t]);
         total += done[t];
     }
     printf("%d jets, %dx%d, S=%d, %d device(s), %d host thread(s) per device\n", total, W, H, steps + 1, gpus, per_gpu);
-    for (auto im : seq) free_color_image(im);
+    for (auto im : seq) { sfgpu_host_unregister(im->c1); free_color_image(im); } // (unregistering a buffer that was not registered only returns an error code)
+    sfgpu_host_unregister(channel_weights->c1);
     free_color_image(channel_weights);
     return total == jets ? 0 : 1;
 }
