@@ -37,6 +37,9 @@ def unique_seeds(w, h, n, seed):
 @pytest.mark.parametrize("w,h,ns,nn,kind", [
     (97, 61, 40, 10, "texture"), (200, 150, 300, 26, "texture"), (64, 64, 64, 26, "flat"), (333, 211, 900, 100, "texture"),
     (1024, 436, 5000, 100, "texture"), (130, 33, 50, 50, "ridges"),
+    # geometry of the strip pipeline: narrower than a 32-column block, five rows, exactly / just over the 96-column window of a
+    # strip row, a last strip of one row; zero cost (the square root of the update at its argument 0)
+    (31, 7, 12, 5, "texture"), (100, 5, 9, 4, "texture"), (96, 32, 30, 10, "texture"), (97, 33, 30, 10, "ridges"), (70, 50, 25, 8, "zero"),
 ])
 def test_nnfield_labels_and_neighbours_equal_reference(ctx, reference, w, h, ns, nn, kind):
     """dist_trf_nnfield_subset (epic_aux.cpp:350-401): the sweeps are reproduced operation for operation, so the label map
@@ -49,6 +52,8 @@ def test_nnfield_labels_and_neighbours_equal_reference(ctx, reference, w, h, ns,
         cost = cost + (np.arange(w)[None, :] % 17 == 0) * 5.0  # expensive ridges: many sweeps until nothing changes
         cost = cost.astype(np.float32)
     cost = np.ascontiguousarray(cost + np.float32(0.001))
+    if kind == "zero":
+        cost = np.zeros((h, w), np.float32)
     seeds = unique_seeds(w, h, ns, w * 7 + ns)
     rb, rd, rl = np.zeros((ns, nn), np.int32), np.zeros((ns, nn), np.float32), np.zeros((h, w), np.int32)
     c2 = cost.copy()
