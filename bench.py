@@ -373,7 +373,52 @@ def run_mt_secondary(ctx, torch, with_cpu, reps=3):
         out["config%d" % cid] = line
         del pins, frames
     out["epic"] = run_epic_secondary(ctx, with_cpu)
+    out["config5_mt_driver"] = run_driver_secondary()
     return out
+
+
+def run_driver_secondary(w=1280, h=1024, jets=8, S=3):
+    """BASELINE config 5, secondary: the synthetic sequence as multi-frame windows (forward AND backward solve per jet,
+    slow_flow.cpp:875-1030) through the compiled sharded driver (tools/slow_flow_gpu.cpp -> slowflow_b200/lib/slow_flow_gpu):
+    PPM frames in, .flo / _back.flo / occlusion .pbm out, with 1 and 2 host threads per GPU.  The window loop's own clock
+    (frame loading and normalize() excluded, result writing included)."""
+    import re
+    import subprocess
+    import tempfile
+    import numpy as np
+    from slowflow_b200 import synth
+    exe = os.path.join(ROOT, "slowflow_b200", "lib", "slow_flow_gpu")
+    if not os.path.exists(exe):
+        return {"unavailable": "slowflow_b200/lib/slow_flow_gpu is not built"}
+    steps = S - 1
+    n = 1 + (jets + 2) * steps
+    res = {"workload": "%d jets (= %d Variational_MT windows) of a %d-frame synthetic %dx%d PPM sequence, S=%d, config-3 parameters, "
+                       "results written to a temporary directory" % (jets, 2 * jets, n, w, h, S),
+           "api": "slow_flow_gpu (sharded window driver, one or two host threads per device)"}
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            for k in range(n):
+                f = np.clip(np.rint(synth.frame(w, h, k - steps)), 0, 255).astype(np.uint8)
+                with open(os.path.join(d, "frame_%d.ppm" % k), "wb") as fh:
+                    fh.write(b"P6\n%d %d\n255\n" % (w, h))
+                    fh.write(np.ascontiguousarray(f.transpose(1, 2, 0)).tobytes())
+            for tpg in (1, 2):
+                r = subprocess.run([exe, "--frames", os.path.join(d, "frame_%d.ppm"), "--out", os.path.join(d, "out%d" % tpg), "--start", str(steps),
+                                    "--jets", str(jets), "--S", str(S), "--gpus", "1", "--threads-per-gpu", str(tpg), "--occlusions",
+                                    "--set", "slow_flow_occlusion_reasoning=1", "--set", "slow_flow_niter_alter=2",
+                                    "--set", "slow_flow_robust_color=4", "--set", "slow_flow_robust_color_eps=0.5", "--set", "16bit=0",
+                                    "--set", "slow_flow_smoothing=1", "--set", "slow_flow_omega_0=0", "--set", "slow_flow_omega_1=2",
+                                    "--set", "slow_flow_occlusion_penalty=0.1", "--set", "slow_flow_occlusion_alpha=0.1"],
+                                   capture_output=True, text=True, timeout=300)
+                m = re.search(r"window loop: ([0-9.]+) s, ([0-9.]+) jets/s", r.stdout)
+                if r.returncode != 0 or not m:
+                    res["threads_per_gpu_%d" % tpg] = {"error": (r.stderr or r.stdout)[-200:]}
+                    continue
+                res["threads_per_gpu_%d" % tpg] = {"window_loop_s": float(m.group(1)), "jets_per_sec": float(m.group(2)),
+                                                   "windows_per_sec": 2.0 * float(m.group(2))}
+    except Exception as e:  # the secondary must never take the bench line down
+        res["error"] = repr(e)[:200]
+    return res
 
 
 def run_epic_secondary(ctx, with_cpu, reps=3):
