@@ -17,7 +17,8 @@ no data-path collective, weak scaling).
   roofline  SOR kernel: algorithmic bytes (44 B/px/sweep) / CUDA-event time of the SOR launches
   cpu_baseline  the reference's CPU objects timed on this box's host cores (rank 0, N=1 only)
   secondary the multi-frame path (BASELINE configs 3 and 4): ms per window, executed iteration counts, host /
-            kernel split, fraction of the fused streaming model, the reference's CPU seconds per outer iteration
+            kernel split, fraction of the fused streaming model, the reference's CPU seconds per outer iteration;
+            EPIC interpolation; config 5's multi-frame secondary through the sharded window driver (slow_flow_gpu)
 """
 import argparse
 import json
