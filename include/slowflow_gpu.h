@@ -168,6 +168,15 @@ int sfgpu_variational_mt(sfgpu_ctx *ctx, image_t *wx, image_t *wy, const color_i
                          const sf_mt_params_t *params, const color_image_t *channel_w,
                          image_t *occlusions_out, float avg_change_out[2]);
 
+/* Frame cache of the multi-frame entry for callers that solve many windows over ONE sequence, like the jet loop of
+ * slow_flow.cpp:706-1030: consecutive windows share frames and the backward window of a jet reads the frames of its
+ * forward window, so with the cache a frame crosses PCIe once instead of once per window that contains it.
+ * max_frames > 0: sfgpu_variational_mt keeps device copies of up to max_frames level-0 frames, keyed by the host pointer
+ * im[f]->c1 and the geometry, least recently used first out.  CONTRACT: while the cache is enabled the caller must not
+ * change the contents of a frame it has passed (normalize() first, then enable).  max_frames == 0 disables the cache and
+ * frees it; every call empties it.  Off by default: an unmodified call site keeps the reference's semantics. */
+int sfgpu_mt_frame_cache(sfgpu_ctx *ctx, int max_frames);
+
 /* normalize() of variational_mt.cpp:17-85: in place on F host frames; fills params->img_norm_* */
 int sfgpu_normalize(sfgpu_ctx *ctx, color_image_t *const *seq, int F, sf_mt_params_t *params);
 

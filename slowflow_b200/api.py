@@ -61,7 +61,7 @@ ABI_SYMBOLS = [
     "sfgpu_last_error", "sfgpu_device_count", "sfgpu_synchronize", "sfgpu_set_sor_variant", "sfgpu_set_sor_fuse",
     "sfgpu_variational", "sfgpu_variational_dev", "sfgpu_variational_sequence", "sfgpu_variational_sequence_u8",
     "sfgpu_variational_sequence_u16", "sfgpu_host_register",
-    "sfgpu_host_unregister", "sfgpu_variational_mt", "sfgpu_normalize", "sfgpu_get_mt_stats", "sfgpu_profile_enable",
+    "sfgpu_host_unregister", "sfgpu_variational_mt", "sfgpu_mt_frame_cache", "sfgpu_normalize", "sfgpu_get_mt_stats", "sfgpu_profile_enable",
     "sfgpu_profile_reset", "sfgpu_profile_get", "sfgpu_image_warp", "sfgpu_warp_frame_derivs", "sfgpu_compute_dpsis_weight",
     "sfgpu_compute_smoothness", "sfgpu_compute_data_and_match", "sfgpu_prep_two_frame", "sfgpu_sub_laplacian", "sfgpu_sor_coupled",
     "sfgpu_epic", "sfgpu_epic_nnfield", "epic_params_default", "sfgpu_version", "sfgpu_grid_mincut", "sfgpu_grid_mincut_dev", "sfgpu_prescale_size", "sfgpu_prescale", "sfgpu_raw_weighting",
@@ -298,6 +298,11 @@ class Context:
                                                        _ip(channel_w), _ip(occlusions), out),
                "sfgpu_variational_mt")
         return float(out[0]), float(out[1])
+
+    def mt_frame_cache(self, max_frames):
+        """Device-side cache of level-0 frames keyed by their host buffers (sfgpu_mt_frame_cache): for callers that solve
+        many windows over one immutable sequence.  0 disables."""
+        _check(self.lib, self.lib.sfgpu_mt_frame_cache(self.h, int(max_frames)), "sfgpu_mt_frame_cache")
 
     # --- input side of a window (slow_flow.cpp:538-542, 596-600)
     def prescale(self, src, scale):

@@ -342,6 +342,7 @@ void sfgpu_destroy(sfgpu_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (auto &p : c->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->ev_free) cudaEventDestroy(e);
+    if (c->mt_cache_pool) cudaFree(c->mt_cache_pool);
     if (c->mtw) sf::mt_work_free(c->mtw);
     if (c->stager) sf::host_stager_free(c->stager);
     if (c->cut) sf::device_cut_free(c->cut);
@@ -357,6 +358,23 @@ void sfgpu_destroy(sfgpu_ctx *c) {
     if (c->d2h) cudaStreamDestroy(c->d2h);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+
+int sfgpu_mt_frame_cache(sfgpu_ctx *c, int max_frames) {
+    if (!c || max_frames < 0 || max_frames > 64) {
+        set_error("sfgpu_mt_frame_cache: bad argument");
+        return SFGPU_ERR_ARG;
+    }
+    SF_CUDA(cudaSetDevice(c->device));
+    SF_CUDA(cudaStreamSynchronize(c->stream)); // nothing in flight reads a slot that is dropped here
+    if ((size_t)max_frames != c->mt_cache.size()) { // another capacity: the pool is re-made at the next call
+        if (c->mt_cache_pool) cudaFree(c->mt_cache_pool);
+        c->mt_cache_pool = nullptr;
+        c->mt_cache_slot_floats = 0;
+        c->mt_cache.assign((size_t)max_frames, sfgpu_ctx::MtFrameSlot());
+    }
+    for (auto &e : c->mt_cache) e.host = nullptr; // enabling (again) starts from an empty cache: the caller may have changed frames
+    return SFGPU_OK;
 }
 
 int sfgpu_synchronize(sfgpu_ctx *c) {

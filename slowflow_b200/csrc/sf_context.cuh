@@ -55,6 +55,16 @@ struct sfgpu_ctx {
     sf::Geom seq_geom{0, 0, 0};      // geometry of the frame ring left by the last sequence call
     int seq_last_slot = -1;          // ring slot that holds the last frame of that call (-1: none)
 
+    // ---- multi-frame frame cache (sfgpu_mt_frame_cache): device copies of level-0 frames keyed by the caller's host
+    // pointer, for callers that solve many windows over one immutable sequence (consecutive windows share frames, the
+    // backward window of a jet reads the frames of its forward window)
+    struct MtFrameSlot { const void *host = nullptr; size_t floats = 0; float *dev = nullptr; unsigned long long stamp = 0; };
+    std::vector<MtFrameSlot> mt_cache;
+    float *mt_cache_pool = nullptr; // ONE allocation for all slots (cudaMalloc / cudaFree per frame cost tens of ms each next to registered host memory)
+    size_t mt_cache_slot_floats = 0;
+    unsigned long long mt_cache_clock = 0;
+    unsigned long long mt_cache_hits = 0, mt_cache_misses = 0;
+
     // ---- profiling
     bool prof = false;
     struct EvPair { cudaEvent_t a, b; int kind; };

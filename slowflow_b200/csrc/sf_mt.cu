@@ -1084,8 +1084,10 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
     // ---- device memory: frames of all levels + per-level work planes sized for level 0
     const Geom g0 = geoms[0];
     const size_t P0 = g0.plane();
+    // with the frame cache (sfgpu_mt_frame_cache) the level-0 frames live in the cache's own device buffers
+    const bool cached = !c->mt_cache.empty() && (int)c->mt_cache.size() >= F;
     size_t frame_floats = 0;
-    for (int l = 0; l < L; l++) frame_floats += (size_t)F * 3 * geoms[l].plane();
+    for (int l = cached ? 1 : 0; l < L; l++) frame_floats += (size_t)F * 3 * geoms[l].plane();
     const size_t work_planes = (size_t)(F - 1) * 3 + (F - 1) + 2 /*wx wy*/ + 2 /*wx,wy of next level*/ + 2 /*uu vv*/ + 2 /*odu odv*/ + 1 /*dpsis*/ +
                                1 /*occ*/ + 2 /*d0 d1*/ + 3 /*blur tmp*/ + (channel_w ? 3 : 0) +
                                (c->mt_data_variant == 0 ? (size_t)F * 15 /*per-frame derivative planes*/ : 0);
@@ -1097,8 +1099,43 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
     }
     float *ptr = work.pool;
     std::vector<MtLevel> levels(L);
+    std::vector<bool> frame_resident(F, false); // level-0 frame already on the device (cache hit)
     for (int l = 0; l < L; l++) {
         levels[l].g = geoms[l];
+        if (l == 0 && cached) {
+            // slot per frame: the one that holds this host buffer, else the least recently used slot no frame of this call has
+            const unsigned long long now = ++c->mt_cache_clock;
+            const size_t want = 3 * P0;
+            if (c->mt_cache_slot_floats != want) { // first use, or another geometry: one pool for all slots
+                SF_CUDA(cudaStreamSynchronize(st));
+                if (c->mt_cache_pool) cudaFree(c->mt_cache_pool);
+                c->mt_cache_pool = nullptr;
+                c->mt_cache_slot_floats = 0;
+                SF_CUDA(cudaMalloc(&c->mt_cache_pool, c->mt_cache.size() * want * sizeof(float)));
+                c->mt_cache_slot_floats = want;
+                for (size_t k = 0; k < c->mt_cache.size(); k++) {
+                    c->mt_cache[k] = sfgpu_ctx::MtFrameSlot();
+                    c->mt_cache[k].dev = c->mt_cache_pool + k * want;
+                    c->mt_cache[k].floats = want;
+                }
+            }
+            for (int f = 0; f < F; f++) {
+                sfgpu_ctx::MtFrameSlot *slot = nullptr;
+                for (auto &e : c->mt_cache)
+                    if (e.host == (const void *)im[f]->c1 && e.floats == want && e.stamp != now) { slot = &e; frame_resident[f] = true; break; }
+                if (!slot) {
+                    for (auto &e : c->mt_cache)
+                        if (e.stamp != now && (!slot || e.stamp < slot->stamp)) slot = &e;
+                    slot->host = im[f]->c1;
+                    c->mt_cache_misses++;
+                } else {
+                    c->mt_cache_hits++;
+                }
+                slot->stamp = now;
+                levels[0].frames.push_back(slot->dev);
+            }
+            continue;
+        }
         for (int f = 0; f < F; f++) { levels[l].frames.push_back(ptr); ptr += 3 * geoms[l].plane(); }
     }
     auto take = [&](size_t planes) { float *r = ptr; ptr += planes * P0; return r; };
@@ -1116,7 +1153,8 @@ int sfgpu_variational_mt(sfgpu_ctx *c, image_t *wx, image_t *wy, const color_ima
     // ---- upload
     {
         std::vector<HostCopy> up;
-        for (int f = 0; f < F; f++) up.push_back(HostCopy{levels[0].frames[f], im[f]->c1, 3 * P0 * sizeof(float)});
+        for (int f = 0; f < F; f++)
+            if (!frame_resident[f]) up.push_back(HostCopy{levels[0].frames[f], im[f]->c1, 3 * P0 * sizeof(float)});
         up.push_back(HostCopy{wxa, wx->data, P0 * sizeof(float)});
         up.push_back(HostCopy{wya, wy->data, P0 * sizeof(float)});
         if (chw) up.push_back(HostCopy{chw, channel_w->c1, 3 * P0 * sizeof(float)});

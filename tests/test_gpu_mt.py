@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import mt_helpers as mh
-from slowflow_b200 import ColorImage
+from slowflow_b200 import ColorImage, Image, synth
 from slowflow_b200.metrics import epe
 from oracle.pyoracle import SOR_LEX, SOR_REDBLACK
 
@@ -314,3 +314,52 @@ def test_mt_tiny_and_ragged_windows(monkeypatch, w, h):
     mean, mx = epe(a["wx"].array, a["wy"].array, b["wx"].array, b["wy"].array, border=0)
     print("tiny window %dx%d: packed vs scalar mean %.3e max %.3e" % (w, h, mean, mx))
     assert mean <= 1e-4 and mx <= 1e-2
+
+
+def test_mt_frame_cache_same_results():
+    """sfgpu_mt_frame_cache: consecutive windows over one sequence (sharing frames, forward and reversed order like the jet
+    loop of slow_flow.cpp:875-1030) give bit-identical flows with and without the device-side frame cache; a change of
+    geometry and re-enabling after the caller changed a frame are handled."""
+    from slowflow_b200 import Context
+    S, w, h = 3, 190, 110
+    frames, _, _ = synth.window_case(w, h, 5, 20170721, 0.25, True)  # 9 frames: windows of 5 at offsets 0, 2, 4
+    seq = [ColorImage.from_array(f) for f in frames]
+    p = mh.params(S, niter_alter=2, niter_outer=2, robust_color=4, robust_color_eps=0.5)
+
+    def solve_all(ctx):
+        out = []
+        q = mh.clone_params(p)
+        ims = [f.copy() for f in seq]
+        ctx.normalize(ims, q)
+        for off in (0, 2, 4):
+            for win in (ims[off:off + 5], ims[off:off + 5][::-1]):
+                wx, wy, occ = Image(w, h), Image(w, h), Image(w, h)
+                ctx.variational_mt(wx, wy, win, q, None, occ)
+                out.append((wx.array.copy(), wy.array.copy(), occ.array.copy()))
+        return out, ims, q
+
+    with Context(0) as c0:
+        plain, _, _ = solve_all(c0)
+    with Context(0) as c1:
+        c1.mt_frame_cache(7)
+        cached, ims, q = solve_all(c1)
+        for a, b in zip(plain, cached):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+        # another geometry through the same cache, then the first one again
+        ims2, wx2, wy2 = mh.window(97, 61, S)
+        g2 = mh.run_gpu(c1, ims2, wx2, wy2, p)
+        assert np.isfinite(g2["wx"].array).all()
+        wx, wy = Image(w, h), Image(w, h)
+        c1.variational_mt(wx, wy, ims[0:5], q, None, None)
+        assert np.array_equal(wx.array, plain[0][0])
+        # the caller changes a frame: re-enabling empties the cache, the new contents are used
+        ims[2].buf[:] = ims[2].buf * 0.5
+        c1.mt_frame_cache(7)
+        wx, wy = Image(w, h), Image(w, h)
+        c1.variational_mt(wx, wy, ims[0:5], q, None, None)
+    with Context(0) as c2:
+        rx, ry = Image(w, h), Image(w, h)
+        c2.variational_mt(rx, ry, ims[0:5], q, None, None)
+    assert np.array_equal(wx.array, rx.array) and np.array_equal(wy.array, ry.array)
+    assert not np.array_equal(rx.array, plain[0][0])

@@ -21,13 +21,13 @@ with tempfile.TemporaryDirectory() as d:
         with open(os.path.join(d, "frame_%d.ppm" % k), "wb") as fh:
             fh.write(b"P6\n%d %d\n255\n" % (W, H))
             fh.write(np.ascontiguousarray(f.transpose(1, 2, 0)).tobytes())
-    for tpg in (1, 2):
-        out = os.path.join(d, "out%d" % tpg)
+    for tpg, extra in ((1, []), (2, []), (1, ["--no-frame-cache"])):
+        out = os.path.join(d, "out%d%d" % (tpg, len(extra)))
         r = subprocess.run([os.path.join(ROOT, "slowflow_b200", "lib", "slow_flow_gpu"), "--frames", os.path.join(d, "frame_%d.ppm"),
-                            "--out", out, "--start", str(steps), "--jets", str(JETS), "--S", str(S), "--threads-per-gpu", str(tpg),
+                            "--out", out, "--start", str(steps), "--jets", str(JETS), "--S", str(S), "--threads-per-gpu", str(tpg), *extra,
                             "--occlusions", "--set", "slow_flow_occlusion_reasoning=1", "--set", "slow_flow_niter_alter=2",
                             "--set", "slow_flow_robust_color=4", "--set", "slow_flow_robust_color_eps=0.5", "--set", "16bit=0",
                             "--set", "slow_flow_smoothing=1", "--set", "slow_flow_omega_0=0", "--set", "slow_flow_omega_1=2",
                             "--set", "slow_flow_occlusion_penalty=0.1", "--set", "slow_flow_occlusion_alpha=0.1"],
                            capture_output=True, text=True)
-        print("threads per GPU %d: %s" % (tpg, [l for l in r.stdout.splitlines() if "window loop" in l or "jets," in l or "worker" in l]), r.stderr[-300:])
+        print("threads per GPU %d %s: %s" % (tpg, " ".join(extra), [l for l in r.stdout.splitlines() if "window loop" in l or "jets," in l or "worker" in l]), r.stderr[-300:])

@@ -2,7 +2,7 @@
 // against the reference-shaped C++ shim (include/variational_mt_gpu.hpp) and the C ABI only: no CUDA, no OpenCV.
 //
 //   slow_flow_gpu --frames 'seq/frame_%d.ppm' --start 10 --jets 4 --out out/ [--S 3] [--skip 1] [--gpus N]
-//                 [--threads-per-gpu T] [--scale 0.5] [--occlusions] [--set key=value ...]
+//                 [--threads-per-gpu T] [--no-frame-cache] [--scale 0.5] [--occlusions] [--set key=value ...]
 //
 // What it reproduces of the reference (and what it does not):
 //   * frame indexing: frames = 1 + (Jets + 2)*steps images with index start - ref*skip + k*skip (slow_flow.cpp:411, 446-450);
@@ -26,6 +26,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <algorithm>
 #include <thread>
 #include <vector>
 
@@ -121,6 +122,7 @@ int main(int argc, char **argv) {
     std::string frames_fmt, out;
     int start = 0, jets = 1, skip = 1, gpus = 0, per_gpu = 1;
     float scale = 1.0f;
+    bool frame_cache = true; // --no-frame-cache: upload every window's frames like an unmodified caller (A/B)
     bool resume = false; // -resume: a window whose .flo already exists is skipped (slow_flow.cpp:794, :958)
     ParameterList cfg;
     cfg.insert("slow_flow_S", "3", true);
@@ -134,6 +136,7 @@ int main(int argc, char **argv) {
         else if (a == "--skip") skip = atoi(next().c_str());
         else if (a == "--gpus") gpus = atoi(next().c_str());
         else if (a == "--threads-per-gpu") per_gpu = atoi(next().c_str());
+        else if (a == "--no-frame-cache") frame_cache = false;
         else if (a == "--scale") scale = (float)atof(next().c_str());
         else if (a == "--S") cfg.insert("slow_flow_S", next(), true);
         else if (a == "--occlusions") cfg.insert("slow_flow_output_occlusions", "1", true);
@@ -208,10 +211,16 @@ int main(int argc, char **argv) {
     const auto t_loop = std::chrono::steady_clock::now();
     std::vector<std::thread> pool;
     std::vector<int> done(workers, 0), skipped(workers, 0);
-    std::vector<double> t_solve(workers, 0.0), t_out(workers, 0.0); // seconds inside variational() / writing results, per worker
+    std::vector<double> t_solve(workers, 0.0), t_out(workers, 0.0), t_setup(workers, 0.0), t_total(workers, 0.0), t_end(workers, 0.0); // seconds inside variational() / writing results, per worker
     for (int t = 0; t < workers; t++) {
         pool.emplace_back([&, t]() {
+            const auto t_w0 = std::chrono::steady_clock::now();
             if (sfgpu_set_device(t % gpus) != SFGPU_OK) die(sfgpu_last_error());
+            // the frames do not change any more (normalize() ran above): keep the ones this worker's windows share on the
+            // device -- the backward window of a jet reads the frames of its forward window, the next jet shares all but
+            // `steps` of them -- instead of uploading 2 * steps + 1 frames per window
+            if (frame_cache && sfgpu_mt_frame_cache(sf_shim_thread_context(), 2 * (2 * steps + 1)) != SFGPU_OK) die(sfgpu_last_error());
+            t_setup[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_w0).count();
             const int base = jets / workers, extra = jets % workers;
             const int lo = t * base + (t < extra ? t : extra), hi = lo + base + (t < extra ? 1 : 0);
             Variational_MT minimzer_f, minimzer_b; // contexts are created on this thread's device at first use
@@ -257,11 +266,17 @@ int main(int argc, char **argv) {
                 }
                 done[t]++;
             }
+            t_total[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_w0).count();
+            t_end[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
         });
     }
     for (auto &th : pool) th.join();
-    const double loop_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
-    printf("window loop: %.3f s, %.2f jets/s (forward + backward flow each)\n", loop_s, jets / loop_s);
+    // the loop ends when the last worker has written its last result; tearing the contexts down (thread exit: ~1 GB of
+    // workspace per context goes back to the driver) is reported separately
+    const double all_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
+    double loop_s = 0.0;
+    for (int t = 0; t < workers; t++) loop_s = std::max(loop_s, t_end[t]);
+    printf("window loop: %.3f s, %.2f jets/s (forward + backward flow each); context tear-down %.3f s\n", loop_s, jets / loop_s, all_s - loop_s);
 
     // ---- config.cfg for the next stage (:684-688)
     {
@@ -275,8 +290,8 @@ int main(int argc, char **argv) {
     }
     int total = 0;
     for (int t = 0; t < workers; t++) {
-        printf("worker %d (device %d): %d jets, %d finished flow files skipped; %.3f s in variational(), %.3f s scaling + writing results\n", t, t % gpus,
-               done[t], skipped[t], t_solve[t], t_out[t]);
+        printf("worker %d (device %d): %d jets, %d finished flow files skipped; %.3f s in variational(), %.3f s scaling + writing results, %.3f s device / context set-up, %.3f s in the loop body\n", t, t % gpus,
+               done[t], skipped[t], t_solve[t], t_out[t], t_setup[t], t_total[t]);
         total += done[t];
     }
     printf("%d jets, %dx%d, S=%d, %d device(s), %d host thread(s) per device\n", total, W, H, steps + 1, gpus, per_gpu);
