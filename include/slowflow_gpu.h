@@ -174,7 +174,9 @@ int sfgpu_variational_mt(sfgpu_ctx *ctx, image_t *wx, image_t *wy, const color_i
  * max_frames > 0: sfgpu_variational_mt keeps device copies of up to max_frames level-0 frames, keyed by the host pointer
  * im[f]->c1 and the geometry, least recently used first out.  CONTRACT: while the cache is enabled the caller must not
  * change the contents of a frame it has passed (normalize() first, then enable).  max_frames == 0 disables the cache and
- * frees it; every call empties it.  Off by default: an unmodified call site keeps the reference's semantics. */
+ * frees it; every call empties it.  A window with more than max_frames frames is solved without the cache.  Off by
+ * default: an unmodified call site keeps the reference's semantics.  SLOWFLOW_GPU_TRACE=1 prints the hit / miss counts
+ * when the context is destroyed. */
 int sfgpu_mt_frame_cache(sfgpu_ctx *ctx, int max_frames);
 
 /* normalize() of variational_mt.cpp:17-85: in place on F host frames; fills params->img_norm_* */

@@ -343,6 +343,8 @@ void sfgpu_destroy(sfgpu_ctx *c) {
     for (auto &p : c->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->ev_free) cudaEventDestroy(e);
     if (c->mt_cache_pool) cudaFree(c->mt_cache_pool);
+    if ((c->mt_cache_hits || c->mt_cache_misses) && getenv("SLOWFLOW_GPU_TRACE"))
+        fprintf(stderr, "multi-frame frame cache: %llu frames found on the device, %llu uploaded\n", c->mt_cache_hits, c->mt_cache_misses);
     if (c->mtw) sf::mt_work_free(c->mtw);
     if (c->stager) sf::host_stager_free(c->stager);
     if (c->cut) sf::device_cut_free(c->cut);
