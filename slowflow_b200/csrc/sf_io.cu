@@ -4,6 +4,7 @@
 // plus the two device-selection helpers a "one host thread per device" driver needs without linking the CUDA runtime.
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "sf_internal.cuh"
@@ -39,14 +40,22 @@ int sfgpu_write_flo(const char *filename, const image_t *flowx, const image_t *f
     const float tag = 202021.25f;
     const int w = flowx->width, h = flowx->height;
     bool ok = fwrite(&tag, sizeof(float), 1, f) == 1 && fwrite(&w, sizeof(int), 1, f) == 1 && fwrite(&h, sizeof(int), 1, f) == 1;
-    std::vector<float> row((size_t)2 * w);
-    for (int y = 0; y < h && ok; y++) {
-        const float *u = flowx->data + (size_t)y * flowx->stride, *v = flowy->data + (size_t)y * flowy->stride;
-        for (int x = 0; x < w; x++) {
-            row[2 * x] = u[x];
-            row[2 * x + 1] = v[x];
+    // interleave bands of rows and hand each band to the C library in one piece (one write per band instead of one per
+    // row: the writer is part of every window of the sharded driver)
+    const int band = std::max(1, (int)(((size_t)4 << 20) / ((size_t)2 * w * sizeof(float))));
+    std::vector<float> buf((size_t)2 * w * band);
+    for (int y0 = 0; y0 < h && ok; y0 += band) {
+        const int rows = std::min(band, h - y0);
+        for (int y = 0; y < rows; y++) {
+            const float *u = flowx->data + (size_t)(y0 + y) * flowx->stride, *v = flowy->data + (size_t)(y0 + y) * flowy->stride;
+            float *dst = buf.data() + (size_t)2 * w * y;
+            for (int x = 0; x < w; x++) {
+                dst[2 * x] = u[x];
+                dst[2 * x + 1] = v[x];
+            }
         }
-        ok = fwrite(row.data(), sizeof(float), row.size(), f) == row.size();
+        const size_t n = (size_t)2 * w * rows;
+        ok = fwrite(buf.data(), sizeof(float), n, f) == n;
     }
     ok = (fclose(f) == 0) && ok;
     if (!ok) {
@@ -122,19 +131,23 @@ int sfgpu_write_occlusion_pbm(const char *filename, const image_t *occlusions) {
     }
     const int w = occlusions->width, h = occlusions->height;
     fprintf(f, "P4\n%d %d\n", w, h);
-    std::vector<unsigned char> row((size_t)(w + 7) / 8);
-    bool ok = true;
-    for (int y = 0; y < h && ok; y++) {
-        std::fill(row.begin(), row.end(), (unsigned char)0);
+    const size_t rb = (size_t)(w + 7) / 8;
+    std::vector<unsigned char> bits(rb * (size_t)h, (unsigned char)0);
+    for (int y = 0; y < h; y++) {
+        unsigned char *row = bits.data() + rb * (size_t)y;
         const float *o = occlusions->data + (size_t)y * occlusions->stride;
-        for (int x = 0; x < w; x++) {
-            // saturate_cast<uchar>(0.5*(occ+1)*255): round half to even, clamp to [0, 255]
-            const double v = nearbyint(0.5 * ((double)o[x] + 1.0) * 255.0);
-            const int u8 = v < 0 ? 0 : (v > 255 ? 255 : (int)v);
-            if (u8 == 0) row[x >> 3] |= (unsigned char)(0x80 >> (x & 7));
+        // a pixel is black (bit 1) when saturate_cast<uchar>(0.5*(occ+1)*255) is 0: the value rounds half to even and
+        // clamps at 0, i.e. it is 0 exactly when the double product is <= 0.5 (branch-free: the labels are data)
+        auto black = [](float occ) -> unsigned { return (0.5 * ((double)occ + 1.0) * 255.0 <= 0.5) ? 1u : 0u; };
+        int x = 0;
+        for (; x + 8 <= w; x += 8) { // eight pixels per byte, most significant bit first
+            const float *q = o + x;
+            row[x >> 3] = (unsigned char)((black(q[0]) << 7) | (black(q[1]) << 6) | (black(q[2]) << 5) | (black(q[3]) << 4) |
+                                          (black(q[4]) << 3) | (black(q[5]) << 2) | (black(q[6]) << 1) | black(q[7]));
         }
-        ok = fwrite(row.data(), 1, row.size(), f) == row.size();
+        for (; x < w; x++) row[x >> 3] |= (unsigned char)((black(o[x]) << 7) >> (x & 7));
     }
+    bool ok = fwrite(bits.data(), 1, bits.size(), f) == bits.size();
     ok = (fclose(f) == 0) && ok;
     if (!ok) {
         set_error(std::string("sfgpu_write_occlusion_pbm: write failed for ") + filename);
