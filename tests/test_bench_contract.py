@@ -45,3 +45,19 @@ def test_our_arm_fails_loudly_without_a_gpu(built):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--pairs", "1"], capture_output=True,
                        text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_driver_secondary_never_takes_the_bench_line_down(built):
+    """secondary.config5_mt_driver: without a GPU the sharded driver refuses (no CPU fallback) and the secondary reports
+    that instead of raising; with a GPU it carries the jets/s of the window loop."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from slowflow_b200.api import load_library
+    res = bench.run_driver_secondary(96, 64, 1, 3)
+    assert "workload" in res and "error" not in res
+    for tpg in (1, 2):
+        leg = res["threads_per_gpu_%d" % tpg]
+        if load_library().sfgpu_device_count() > 0:
+            assert leg["jets_per_sec"] > 0 and abs(leg["windows_per_sec"] - 2 * leg["jets_per_sec"]) < 1e-9
+        else:
+            assert "no CUDA device" in leg["error"]
